@@ -1,0 +1,116 @@
+"""ctypes binding of libfuelgpu.so (the C ABI of include/fuelgpu.h).
+
+There is no CPU fallback: if the shared library is missing this module raises, and if no
+sm_100 device is present every call through it fails with FUELGPU_ENODEVICE.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libfuelgpu.so")
+
+MAX_PTS = 64
+UNKNOWN, FREE, OCCUPIED = 0, 1, 2
+ESDF_OPTIMISTIC, ESDF_SIGNED = 1, 2
+EDT_INF = 0x3FFFFFFF
+OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+
+class FuelGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("fuelgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class FuelGridDesc(C.Structure):
+    _fields_ = [("n", C.c_int32 * 3), ("resolution", C.c_double), ("origin", C.c_double * 3),
+                ("box_mind", C.c_double * 3), ("box_maxd", C.c_double * 3)]
+
+
+class FuelFrontierParams(C.Structure):
+    _fields_ = [("cluster_min", C.c_int32), ("cluster_size_xy", C.c_double),
+                ("down_sample", C.c_int32), ("min_z", C.c_double)]
+
+
+class FuelOptParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in
+                ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide", "ld_waypt",
+                 "ld_view", "ld_time", "dist0", "max_vel", "max_acc")] + [("order", C.c_int32)]
+
+
+class FuelTrajConst(C.Structure):
+    _fields_ = [("pt_dist", C.c_double), ("knot_span", C.c_double),
+                ("start", (C.c_double * 3) * 3), ("end", (C.c_double * 3) * 3),
+                ("n_end", C.c_int32), ("time_lb", C.c_double), ("n_guide", C.c_int32),
+                ("guide", (C.c_double * 3) * MAX_PTS), ("n_waypt", C.c_int32),
+                ("waypt", (C.c_double * 3) * MAX_PTS), ("waypt_idx", C.c_int32 * MAX_PTS)]
+
+
+class FuelSolveParams(C.Structure):
+    _fields_ = [("max_eval", C.c_int32), ("lbfgs_m", C.c_int32), ("xtol_rel", C.c_double)]
+
+
+# every symbol include/fuelgpu.h declares: name -> (restype, argtypes)
+_vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+SIGNATURES = {
+    "fuelgpu_version": (C.c_char_p, []),
+    "fuelgpu_last_error": (C.c_char_p, [_vp]),
+    "fuelgpu_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fuelgpu_map_create": (C.c_int, [C.POINTER(FuelGridDesc), C.c_int, C.POINTER(_vp)]),
+    "fuelgpu_map_destroy": (C.c_int, [_vp]),
+    "fuelgpu_map_set_stream": (C.c_int, [_vp, _vp]),
+    "fuelgpu_map_synchronize": (C.c_int, [_vp]),
+    "fuelgpu_map_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "fuelgpu_map_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "fuelgpu_map_upload_occupancy": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp]),
+    "fuelgpu_esdf_update": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "fuelgpu_esdf_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "fuelgpu_esdf_sample": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
+    "fuelgpu_frontier_search": (C.c_int, [_vp, _vp, _vp, C.POINTER(FuelFrontierParams),
+                                          C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "fuelgpu_frontier_fetch": (C.c_int, [_vp] + [_vp] * 7),
+    "fuelgpu_frontier_clear_flags": (C.c_int, [_vp, _i32, _vp]),
+    "fuelgpu_frontier_is_changed": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "fuelgpu_frontier_download_flags": (C.c_int, [_vp, _vp]),
+    "fuelgpu_frontier_upload_flags": (C.c_int, [_vp, _vp]),
+    "fuelgpu_bspline_cost_batch": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp, _vp,
+                                             _vp, _vp]),
+    "fuelgpu_bspline_cost_batch_dev": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp,
+                                                 _vp, _vp, _vp]),
+    "fuelgpu_bspline_optimize_batch": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp,
+                                                 C.POINTER(FuelSolveParams), _vp, _vp, _vp]),
+    "fuelgpu_edt_xy_dev": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_int, _vp, _vp]),
+    "fuelgpu_edt_z_chunks_dev": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _dbl, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libfuelgpu.so; raise loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            raise FuelGpuError(ENODEVICE, "libfuelgpu.so is not built (run `python -m fuel_b200.build` "
+                               "or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(SO)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError = the library does not export what the header declares
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        msg = lib().fuelgpu_last_error(handle)
+        raise FuelGpuError(rc, msg.decode() if msg else "")
+    return rc
+
+
+def ptr(a):
+    """numpy array (or None) -> void*"""
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,502 @@
+// api.cu -- the extern "C" boundary of libfuelgpu (see include/fuelgpu.h).
+#include "common.cuh"
+
+#include <math.h>
+#include <new>
+
+thread_local char g_fuelgpu_err[512] = "";
+
+namespace {
+
+// host occupancy -> resident byte: bits0-1 tri-state (sdf_map.h:194-200), bit2 inflate
+__global__ void ingest_logodds_kernel(const int8_t* __restrict__ inflate, const double* __restrict__ lo,
+                                      uint8_t* __restrict__ occ, int64_t n, double unknown_thr,
+                                      double occ_thr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = lo[i];
+  int t = FUELGPU_FREE;
+  if (v < unknown_thr)
+    t = FUELGPU_UNKNOWN;
+  else if (v > occ_thr)
+    t = FUELGPU_OCCUPIED;
+  occ[i] = (uint8_t)(t | ((inflate[i] == 1) ? 4 : 0));
+}
+
+__global__ void ingest_tri_kernel(const int8_t* __restrict__ inflate, const uint8_t* __restrict__ tri,
+                                  uint8_t* __restrict__ occ, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  occ[i] = (uint8_t)((tri[i] & 3) | ((inflate[i] == 1) ? 4 : 0));
+}
+
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, int64_t n,
+                                  double inf_value) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = in[i];
+  out[i] = isinf(v) ? inf_value : (double)v;
+}
+
+__global__ void clear_flags_kernel(int8_t* flag, const int* __restrict__ addr, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[addr[i]] = 0;
+}
+
+int ensure_stage(FuelMap* m, size_t bytes) {
+  if (bytes <= m->stage_bytes) return 0;
+  if (m->stage) cudaFree(m->stage);
+  m->stage = nullptr;
+  m->stage_bytes = 0;
+  FUEL_CUDA(m, cudaMalloc(&m->stage, bytes));
+  m->stage_bytes = bytes;
+  return 0;
+}
+
+int ensure_bs(FuelMap* m, size_t bytes) {
+  if (bytes <= m->bs_bytes) return 0;
+  if (m->bs_buf) cudaFree(m->bs_buf);
+  m->bs_buf = nullptr;
+  m->bs_bytes = 0;
+  FUEL_CUDA(m, cudaMalloc(&m->bs_buf, bytes));
+  m->bs_bytes = bytes;
+  return 0;
+}
+
+int check_box(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3], int lo[3], int hi[3]) {
+  const int n[3] = { m->g.nx, m->g.ny, m->g.nz };
+  for (int i = 0; i < 3; ++i) {
+    lo[i] = bmin ? bmin[i] : 0;
+    hi[i] = bmax ? bmax[i] : n[i] - 1;
+    if (lo[i] < 0 || hi[i] >= n[i] || lo[i] > hi[i])
+      return fuel_fail(m, FUELGPU_EINVAL, "box outside the map or empty on axis %s%lld", "", i);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fuelgpu_version(void) { return "fuelgpu 0.1 (sm_100a)"; }
+
+const char* fuelgpu_last_error(const FuelMap* map) { return map ? map->err : g_fuelgpu_err; }
+
+int fuelgpu_device_info(int device_id, char* name, int name_len, int* cc_major, int* cc_minor) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device_id >= count)
+    return fuel_fail(nullptr, FUELGPU_ENODEVICE, "no CUDA device %s(id %lld)", "", device_id);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess)
+    return fuel_fail(nullptr, FUELGPU_ECUDA, "cudaGetDeviceProperties failed");
+  if (name && name_len > 0) {
+    strncpy(name, prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return prop.multiProcessorCount;
+}
+
+int fuelgpu_map_create(const FuelGridDesc* grid, int device_id, FuelMap** out) {
+  if (!grid || !out) return fuel_fail(nullptr, FUELGPU_EINVAL, "null argument");
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+    return fuel_fail(nullptr, FUELGPU_ENODEVICE,
+                     "no CUDA device: libfuelgpu has no CPU fallback (the reference CPU path is the "
+                     "oracle, not the product)");
+  if (device_id < 0 || device_id >= count)
+    return fuel_fail(nullptr, FUELGPU_ENODEVICE, "device id %s%lld out of range", "", device_id);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess)
+    return fuel_fail(nullptr, FUELGPU_ECUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fuel_fail(nullptr, FUELGPU_ENODEVICE, "device is not sm_100 (Blackwell B200): %s", prop.name);
+  for (int i = 0; i < 3; ++i)
+    if (grid->n[i] < 1 || grid->n[i] > 1024)
+      return fuel_fail(nullptr, FUELGPU_EINVAL, "grid extent must be in 1..1024 per axis");
+  if (!(grid->resolution > 0)) return fuel_fail(nullptr, FUELGPU_EINVAL, "resolution must be > 0");
+  const int64_t nvox = (int64_t)grid->n[0] * grid->n[1] * grid->n[2];
+  if (nvox >= (1ll << 31)) return fuel_fail(nullptr, FUELGPU_EINVAL, "more than 2^31 voxels");
+
+  FuelMap* m = new (std::nothrow) FuelMap();
+  if (!m) return fuel_fail(nullptr, FUELGPU_ENOMEM, "host allocation failed");
+  memset(m, 0, sizeof(*m));
+  m->desc = *grid;
+  m->dev = device_id;
+  m->sm_count = prop.multiProcessorCount;
+  m->nvox = nvox;
+  Geom& g = m->g;
+  g.nx = grid->n[0];
+  g.ny = grid->n[1];
+  g.nz = grid->n[2];
+  g.res = grid->resolution;
+  g.res_inv = 1 / grid->resolution;  // sdf_map.cpp:33
+  for (int i = 0; i < 3; ++i) {
+    g.origin[i] = grid->origin[i];
+    g.map_max[i] = grid->origin[i] + grid->n[i] * grid->resolution;
+    g.box_mind[i] = grid->box_mind[i];
+    g.box_maxd[i] = grid->box_maxd[i];
+    // posToIndex(box_mind_/box_maxd_), sdf_map.cpp:83-84
+    g.box_min[i] = (int)floor((grid->box_mind[i] - grid->origin[i]) * g.res_inv);
+    g.box_max[i] = (int)floor((grid->box_maxd[i] - grid->origin[i]) * g.res_inv);
+  }
+
+#define CR(expr)                                                                        \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      snprintf(g_fuelgpu_err, 512, "map_create: %s: %s", #expr, cudaGetErrorString(_e)); \
+      fuelgpu_map_destroy(m);                                                           \
+      return _e == cudaErrorMemoryAllocation ? FUELGPU_ENOMEM : FUELGPU_ECUDA;          \
+    }                                                                                   \
+  } while (0)
+  CR(cudaSetDevice(device_id));
+  CR(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  m->stream = m->own_stream;
+  for (int t = 0; t < T_COUNT; ++t) {
+    CR(cudaEventCreate(&m->ev0[t]));
+    CR(cudaEventCreate(&m->ev1[t]));
+  }
+  CR(cudaMalloc(&m->occ, nvox));
+  CR(cudaMalloc(&m->dist, sizeof(float) * nvox));
+  CR(cudaMalloc(&m->flag, nvox));
+  CR(cudaMalloc(&m->g1, sizeof(int32_t) * nvox));
+  CR(cudaMalloc(&m->g2, sizeof(int32_t) * nvox));
+  CR(cudaMalloc(&m->stk, sizeof(uint32_t) * nvox));
+  // initMap: occupancy unknown, inflate 0, distance default_dist (0.0, algorithm.xml:41), flags 0
+  CR(cudaMemsetAsync(m->occ, 0, nvox, m->stream));
+  CR(cudaMemsetAsync(m->dist, 0, sizeof(float) * nvox, m->stream));
+  CR(cudaMemsetAsync(m->flag, 0, nvox, m->stream));
+#undef CR
+  int rc = frontier_state_create(m);
+  if (rc) {
+    strncpy(g_fuelgpu_err, m->err, 511);
+    fuelgpu_map_destroy(m);
+    return rc;
+  }
+  if (cudaStreamSynchronize(m->stream) != cudaSuccess) {
+    snprintf(g_fuelgpu_err, 512, "map_create: stream sync failed");
+    fuelgpu_map_destroy(m);
+    return FUELGPU_ECUDA;
+  }
+  m->err[0] = 0;
+  *out = m;
+  return 0;
+}
+
+int fuelgpu_map_destroy(FuelMap* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->dev);
+  if (m->own_stream) cudaStreamSynchronize(m->own_stream);
+  frontier_state_destroy(m);
+  void* ptrs[] = { m->occ, m->dist, m->dist_neg, m->flag, m->g1, m->g2, m->stk, m->stage, m->bs_buf };
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (int t = 0; t < T_COUNT; ++t) {
+    if (m->ev0[t]) cudaEventDestroy(m->ev0[t]);
+    if (m->ev1[t]) cudaEventDestroy(m->ev1[t]);
+  }
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+  return 0;
+}
+
+int fuelgpu_map_set_stream(FuelMap* m, void* cuda_stream) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+  return 0;
+}
+
+int fuelgpu_map_synchronize(FuelMap* m) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int fuelgpu_map_device_ptrs(FuelMap* m, void** occ, void** dist, void** flag) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  if (occ) *occ = m->occ;
+  if (dist) *dist = m->dist;
+  if (flag) *flag = m->flag;
+  return 0;
+}
+
+int fuelgpu_map_last_timing(FuelMap* m, float ms[8]) {
+  if (!m || !ms) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  for (int t = 0; t < T_COUNT; ++t) {
+    ms[t] = -1.f;
+    if (m->ev_valid[t]) {
+      if (cudaEventSynchronize(m->ev1[t]) == cudaSuccess) cudaEventElapsedTime(&ms[t], m->ev0[t], m->ev1[t]);
+    }
+  }
+  return 0;
+}
+
+int fuelgpu_map_upload_occupancy(FuelMap* m, const int8_t* inflate, const double* logodds,
+                                 const uint8_t* tristate, double clamp_min_log,
+                                 double min_occupancy_log, const int32_t bmin[3],
+                                 const int32_t bmax[3]) {
+  if (!m || !inflate) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if ((logodds == nullptr) == (tristate == nullptr))
+    return fuel_fail(m, FUELGPU_EINVAL, "give exactly one of logodds / tristate");
+  int lo[3], hi[3];
+  int rc = check_box(m, bmin, bmax, lo, hi);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  const int64_t plane = (int64_t)m->g.ny * m->g.nz;
+  const int64_t off = (int64_t)lo[0] * plane;
+  const int64_t cnt = (int64_t)(hi[0] - lo[0] + 1) * plane;
+  const size_t inf_bytes = ((size_t)cnt + 7) & ~(size_t)7;  // keeps the fp64 region 8-byte aligned
+  rc = ensure_stage(m, inf_bytes + (size_t)cnt * (logodds ? 8 : 1));
+  if (rc) return rc;
+  tbegin(m, T_UPLOAD);
+  int8_t* d_inf = (int8_t*)m->stage;
+  FUEL_CUDA(m, cudaMemcpyAsync(d_inf, inflate + off, cnt, cudaMemcpyHostToDevice, m->stream));
+  const unsigned nb = (unsigned)((cnt + 255) / 256);
+  if (logodds) {
+    double* d_lo = (double*)((uint8_t*)m->stage + inf_bytes);
+    FUEL_CUDA(m, cudaMemcpyAsync(d_lo, logodds + off, cnt * 8, cudaMemcpyHostToDevice, m->stream));
+    ingest_logodds_kernel<<<nb, 256, 0, m->stream>>>(d_inf, d_lo, m->occ + off, cnt, clamp_min_log - 1e-3,
+                                                     min_occupancy_log);
+  } else {
+    uint8_t* d_tri = (uint8_t*)m->stage + inf_bytes;
+    FUEL_CUDA(m, cudaMemcpyAsync(d_tri, tristate + off, cnt, cudaMemcpyHostToDevice, m->stream));
+    ingest_tri_kernel<<<nb, 256, 0, m->stream>>>(d_inf, d_tri, m->occ + off, cnt);
+  }
+  FUEL_CUDA(m, cudaGetLastError());
+  tend(m, T_UPLOAD);
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));  // host buffers may be reused by the caller
+  return 0;
+}
+
+int fuelgpu_esdf_update(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3], int flags) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  int lo[3], hi[3];
+  int rc = check_box(m, bmin, bmax, lo, hi);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  tbegin(m, T_ESDF);
+  rc = esdf_update_impl(m, lo, hi, flags);
+  tend(m, T_ESDF);
+  return rc;
+}
+
+int fuelgpu_esdf_download(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3], float* out_f32,
+                          double* out_f64) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  if ((out_f32 == nullptr) == (out_f64 == nullptr))
+    return fuel_fail(m, FUELGPU_EINVAL, "give exactly one of out_f32 / out_f64");
+  int lo[3], hi[3];
+  int rc = check_box(m, bmin, bmax, lo, hi);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  const int64_t plane = (int64_t)m->g.ny * m->g.nz;
+  const int64_t off = (int64_t)lo[0] * plane;
+  const int64_t cnt = (int64_t)(hi[0] - lo[0] + 1) * plane;
+  tbegin(m, T_DOWNLOAD);
+  if (out_f32) {
+    FUEL_CUDA(m, cudaMemcpyAsync(out_f32 + off, m->dist + off, cnt * 4, cudaMemcpyDeviceToHost, m->stream));
+  } else {
+    rc = ensure_stage(m, (size_t)cnt * 8);
+    if (rc) return rc;
+    f32_to_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, m->stream>>>(
+        m->dist + off, (double*)m->stage, cnt, m->g.res * sqrt(1.7976931348623157e308));
+    FUEL_CUDA(m, cudaGetLastError());
+    FUEL_CUDA(m, cudaMemcpyAsync(out_f64 + off, m->stage, cnt * 8, cudaMemcpyDeviceToHost, m->stream));
+  }
+  tend(m, T_DOWNLOAD);
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int fuelgpu_esdf_sample(FuelMap* m, int64_t n, const double* pos, double* dist, double* grad) {
+  if (!m || (n > 0 && (!pos || !dist || !grad))) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (n <= 0) return 0;
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  int rc = ensure_bs(m, (size_t)n * 7 * sizeof(double));
+  if (rc) return rc;
+  double* d_pos = (double*)m->bs_buf;
+  double* d_d = d_pos + 3 * n;
+  double* d_g = d_d + n;
+  FUEL_CUDA(m, cudaMemcpyAsync(d_pos, pos, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, m->stream));
+  rc = esdf_sample_impl(m, n, d_pos, d_d, d_g);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaMemcpyAsync(dist, d_d, sizeof(double) * n, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaMemcpyAsync(grad, d_g, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int fuelgpu_frontier_search(FuelMap* m, const double upd_min[3], const double upd_max[3],
+                            const FuelFrontierParams* params, int32_t* n_clusters, int32_t* n_cells,
+                            int32_t* n_filtered) {
+  if (!m || !upd_min || !upd_max || !params || !n_clusters || !n_cells || !n_filtered)
+    return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (params->down_sample < 1) return fuel_fail(m, FUELGPU_EINVAL, "down_sample must be >= 1");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  tbegin(m, T_FRONTIER);
+  int rc = frontier_search_impl(m, upd_min, upd_max, params, n_clusters, n_cells, n_filtered);
+  tend(m, T_FRONTIER);
+  return rc;
+}
+
+int fuelgpu_frontier_fetch(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr, int32_t* filt_offsets,
+                           double* filtered, double* average, double* box_min, double* box_max) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  return frontier_fetch_impl(m, cell_offsets, cell_addr, filt_offsets, filtered, average, box_min, box_max);
+}
+
+int fuelgpu_frontier_clear_flags(FuelMap* m, int32_t n, const int32_t* addr) {
+  if (!m || (n > 0 && !addr)) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (n <= 0) return 0;
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  for (int i = 0; i < n; ++i)
+    if (addr[i] < 0 || addr[i] >= m->nvox) return fuel_fail(m, FUELGPU_EINVAL, "address out of range");
+  int rc = ensure_stage(m, sizeof(int) * (size_t)n);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaMemcpyAsync(m->stage, addr, sizeof(int) * n, cudaMemcpyHostToDevice, m->stream));
+  clear_flags_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(m->flag, (const int*)m->stage, n);
+  FUEL_CUDA(m, cudaGetLastError());
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int fuelgpu_frontier_is_changed(FuelMap* m, int32_t mcl, const int32_t* cell_offsets,
+                                const int32_t* cell_addr, uint8_t* changed) {
+  if (!m || (mcl > 0 && (!cell_offsets || !cell_addr || !changed)))
+    return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return frontier_is_changed_impl(m, mcl, cell_offsets, cell_addr, changed);
+}
+
+int fuelgpu_frontier_download_flags(FuelMap* m, int8_t* out) {
+  if (!m || !out) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  FUEL_CUDA(m, cudaMemcpyAsync(out, m->flag, m->nvox, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int fuelgpu_frontier_upload_flags(FuelMap* m, const int8_t* in) {
+  if (!m || !in) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  FUEL_CUDA(m, cudaMemcpyAsync(m->flag, in, m->nvox, cudaMemcpyHostToDevice, m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+static int check_bspline_args(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
+                              const FuelOptParams* p) {
+  if (!m || !p) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (B < 0) return fuel_fail(m, FUELGPU_EINVAL, "negative batch");
+  if (n_pts < 4 || n_pts > FUELGPU_MAX_PTS)
+    return fuel_fail(m, FUELGPU_EINVAL, "n_pts must be in 4..64");
+  if (mask & FUELGPU_VIEWCONS)
+    return fuel_fail(m, FUELGPU_EUNSUPPORTED,
+                     "VIEWCONS is not supported (ld_view = 0.0 in every reference launch file)");
+  if (p->order < 1 || 2 * p->order >= n_pts) return fuel_fail(m, FUELGPU_EINVAL, "bad spline order");
+  return 0;
+}
+
+int fuelgpu_bspline_cost_batch_dev(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
+                                   const FuelOptParams* p, const void* traj_dev, const void* x_dev,
+                                   void* f_dev, void* grad_dev) {
+  int rc = check_bspline_args(m, B, n_pts, mask, p);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!traj_dev || !x_dev || !f_dev || !grad_dev) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  tbegin(m, T_BSPLINE);
+  rc = bspline_cost_batch_dev_impl(m, B, n_pts, mask, p, (const FuelTrajConst*)traj_dev,
+                                   (const double*)x_dev, (double*)f_dev, (double*)grad_dev);
+  tend(m, T_BSPLINE);
+  return rc;
+}
+
+int fuelgpu_bspline_cost_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
+                               const FuelOptParams* p, const FuelTrajConst* traj, const double* x,
+                               double* f, double* grad) {
+  int rc = check_bspline_args(m, B, n_pts, mask, p);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!traj || !x || !f || !grad) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  const int nvar = (mask & FUELGPU_MINTIME) ? 3 * n_pts + 1 : 3 * n_pts;
+  const size_t tcb = sizeof(FuelTrajConst) * (size_t)B;
+  const size_t xb = sizeof(double) * (size_t)B * nvar;
+  rc = ensure_bs(m, tcb + 2 * xb + sizeof(double) * (size_t)B + 64);
+  if (rc) return rc;
+  uint8_t* base = (uint8_t*)m->bs_buf;
+  FuelTrajConst* d_tc = (FuelTrajConst*)base;
+  double* d_x = (double*)(base + tcb);
+  double* d_g = d_x + (size_t)B * nvar;
+  double* d_f = d_g + (size_t)B * nvar;
+  FUEL_CUDA(m, cudaMemcpyAsync(d_tc, traj, tcb, cudaMemcpyHostToDevice, m->stream));
+  FUEL_CUDA(m, cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, m->stream));
+  tbegin(m, T_BSPLINE);
+  rc = bspline_cost_batch_dev_impl(m, B, n_pts, mask, p, d_tc, d_x, d_f, d_g);
+  tend(m, T_BSPLINE);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaMemcpyAsync(f, d_f, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaMemcpyAsync(grad, d_g, xb, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int fuelgpu_bspline_optimize_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
+                                   const FuelOptParams* p, const FuelTrajConst* traj,
+                                   const FuelSolveParams* solve, double* x, double* f_best,
+                                   int32_t* n_eval) {
+  int rc = check_bspline_args(m, B, n_pts, mask, p);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!traj || !x || !f_best || !n_eval || !solve) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (solve->lbfgs_m < 1 || solve->lbfgs_m > 8 || solve->max_eval < 1)
+    return fuel_fail(m, FUELGPU_EINVAL, "bad solver parameters");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  const int nvar = (mask & FUELGPU_MINTIME) ? 3 * n_pts + 1 : 3 * n_pts;
+  const size_t tcb = sizeof(FuelTrajConst) * (size_t)B;
+  const size_t xb = sizeof(double) * (size_t)B * nvar;
+  rc = ensure_bs(m, tcb + xb + sizeof(double) * (size_t)B + sizeof(int32_t) * (size_t)B + 64);
+  if (rc) return rc;
+  uint8_t* base = (uint8_t*)m->bs_buf;
+  FuelTrajConst* d_tc = (FuelTrajConst*)base;
+  double* d_x = (double*)(base + tcb);
+  double* d_f = d_x + (size_t)B * nvar;
+  int32_t* d_n = (int32_t*)(d_f + B);
+  FUEL_CUDA(m, cudaMemcpyAsync(d_tc, traj, tcb, cudaMemcpyHostToDevice, m->stream));
+  FUEL_CUDA(m, cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, m->stream));
+  tbegin(m, T_BSPLINE);
+  rc = bspline_optimize_batch_dev_impl(m, B, n_pts, mask, p, d_tc, solve, d_x, d_f, d_n);
+  tend(m, T_BSPLINE);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaMemcpyAsync(x, d_x, xb, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaMemcpyAsync(f_best, d_f, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaMemcpyAsync(n_eval, d_n, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int fuelgpu_edt_xy_dev(void* cuda_stream, const void* occ_slab, int32_t nx, int32_t ny, int32_t nzl,
+                       int flags, void* g2_out_i32, void* scratch_i32) {
+  if (!occ_slab || !g2_out_i32 || !scratch_i32) return fuel_fail(nullptr, FUELGPU_EINVAL, "null argument");
+  if (nx < 1 || ny < 1 || nzl < 1 || nx > 1024 || ny > 1024)
+    return fuel_fail(nullptr, FUELGPU_EINVAL, "slab extent out of range");
+  return edt_xy_dev_impl((cudaStream_t)cuda_stream, (const uint8_t*)occ_slab, nx, ny, nzl, flags,
+                         (int32_t*)g2_out_i32, (int32_t*)scratch_i32);
+}
+
+int fuelgpu_edt_z_chunks_dev(void* cuda_stream, const void* g2_chunks_i32, int32_t G, int32_t nxl,
+                             int32_t ny, int32_t nzl, double resolution, void* dist_out_f32,
+                             void* scratch_i32) {
+  if (!g2_chunks_i32 || !dist_out_f32 || !scratch_i32)
+    return fuel_fail(nullptr, FUELGPU_EINVAL, "null argument");
+  if (G < 1 || nxl < 1 || ny < 1 || nzl < 1 || (int64_t)G * nzl > 1024)
+    return fuel_fail(nullptr, FUELGPU_EINVAL, "chunk extent out of range");
+  return edt_z_chunks_dev_impl((cudaStream_t)cuda_stream, (const int32_t*)g2_chunks_i32, G, nxl, ny, nzl,
+                               resolution, (float*)dist_out_f32, (int32_t*)scratch_i32);
+}
+
+}  // extern "C"

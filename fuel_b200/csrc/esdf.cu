@@ -1,0 +1,419 @@
+// esdf.cu -- exact Euclidean distance transform of the occupancy grid on sm_100a.
+//
+// Replaces SDFMap::updateESDF3d / fillESDF (plan_env/src/sdf_map.cpp:116-241) and
+// SDFMap::getDistWithGrad (:497-536).  The reference runs three 1-D lower-envelope sweeps
+// (z, y, x) in fp64 with DBL_MAX as "no site".  Every finite intermediate is an integer
+// (squared voxel distance <= 3*(n-1)^2), so the device keeps the transform in exact int32
+// arithmetic and only the last pass converts: dist = resolution * sqrt(d2) in fp32.
+// "No site on this line / in this box" is FUELGPU_EDT_INF between passes and +inf in the
+// result (the reference ends with resolution*sqrt(DBL_MAX) there).
+//
+// Layout: address = (x*ny + y)*nz + z, z fastest (sdf_map.h:145-147).
+#include "common.cuh"
+
+namespace {
+
+constexpr int INF_I = FUELGPU_EDT_INF_I;
+
+struct Box {
+  int lo[3], hi[3];  // inclusive
+};
+
+// site predicate of the z sweep.  mode 0: optimistic (sdf_map.cpp:156-166) inflate==1;
+// mode 1: non-optimistic (:167-181) inflate==1 || unknown; mode 2: negative field (:203-214)
+// inflate==0.
+__device__ __forceinline__ bool is_site(uint8_t o, int mode) {
+  const bool infl = (o & 4) != 0;
+  if (mode == 0) return infl;
+  if (mode == 1) return infl || ((o & 3) == FUELGPU_UNKNOWN);
+  return !infl;
+}
+
+// ---------------------------------------------------------------------------------------
+// z sweep: one warp per (x,y) line, <= 1024 voxels.  The line's site bits are gathered with
+// warp ballots (lane j keeps the 32-bit mask of chunk j), then every voxel finds its nearest
+// set bit on both sides with clz/ffs -- no per-voxel loop, fully coalesced byte loads.
+// out = squared distance along z (int32) or INF.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) zsweep_warp_kernel(const uint8_t* __restrict__ occ,
+                                                          int32_t* __restrict__ out, int ny, int nz,
+                                                          Box b, int mode, int nlines) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= nlines) return;
+  const int nyb = b.hi[1] - b.lo[1] + 1;
+  const int x = b.lo[0] + warp / nyb;
+  const int y = b.lo[1] + warp % nyb;
+  const int z0 = b.lo[2];
+  const int n = b.hi[2] - b.lo[2] + 1;
+  const int64_t base = ((int64_t)x * ny + y) * nz + z0;
+  const int nchunks = (n + 31) >> 5;
+
+  unsigned mymask = 0;
+  for (int i = 0; i < nchunks; ++i) {
+    const int p = (i << 5) + lane;
+    bool s = false;
+    if (p < n) s = is_site(__ldg(occ + base + p), mode);
+    const unsigned m = __ballot_sync(0xffffffffu, s);
+    if (lane == i) mymask = m;
+  }
+  const unsigned nzb = __ballot_sync(0xffffffffu, mymask != 0);
+  const int mylast = mymask ? 31 - __clz(mymask) : 0;
+  const int myfirst = mymask ? __ffs(mymask) - 1 : 0;
+
+  for (int i = 0; i < nchunks; ++i) {
+    const unsigned m = __shfl_sync(0xffffffffu, mymask, i);
+    const int pos = (i << 5) + lane;
+    // nearest site at or below pos
+    const unsigned prev = nzb & ((1u << i) - 1u);
+    const int pc = prev ? 31 - __clz(prev) : 0;
+    const int plast = __shfl_sync(0xffffffffu, mylast, pc);
+    const unsigned next = nzb & ~((2u << i) - 1u);
+    const int nc = next ? __ffs(next) - 1 : 0;
+    const int nfirst = __shfl_sync(0xffffffffu, myfirst, nc);
+
+    int d = INF_I;
+    const unsigned ml = m & (0xffffffffu >> (31 - lane));
+    if (ml)
+      d = lane - (31 - __clz(ml));
+    else if (prev)
+      d = pos - ((pc << 5) + plast);
+    const unsigned mr = m & (0xffffffffu << lane);
+    int dr = INF_I;
+    if (mr)
+      dr = (__ffs(mr) - 1) - lane;
+    else if (next)
+      dr = ((nc << 5) + nfirst) - pos;
+    d = min(d, dr);
+    if (pos < n) out[base + pos] = (d == INF_I) ? INF_I : d * d;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Envelope sweep along y or x: one thread per line, lanes along z so that every global
+// access of a warp is a contiguous run.  Felzenszwalb-Huttenlocher lower envelope restated
+// in exact integers: parabola of site v has height h(v) = f(v) + v^2; the abscissa where w
+// overtakes u is (h(w)-h(u)) / (2(w-u)); all comparisons are cross-multiplied, no division.
+// The hull stack lives in `stk` (same layout as the volume, slot k of a line at the line's
+// k-th element); the two topmost entries are cached in registers.
+// Stack entry = v (10 bits) | h (22 bits): requires n <= 1024 per axis.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_vh(int v, int h) { return ((uint32_t)v << 22) | (uint32_t)h; }
+__device__ __forceinline__ int unpack_v(uint32_t e) { return (int)(e >> 22); }
+__device__ __forceinline__ int unpack_h(uint32_t e) { return (int)(e & 0x3fffffu); }
+
+struct LineMap {
+  int n;            // samples per line
+  int64_t stride;   // elements between consecutive samples
+  int nz_run;       // lines along z per row (fastest)
+  int n_outer;      // rows of lines
+  int64_t outer_stride;  // elements between rows of lines
+  int64_t base;     // element offset of line (0,0), sample 0
+};
+
+template <bool FINAL>
+__global__ void __launch_bounds__(128) envelope_kernel(const int32_t* __restrict__ in,
+                                                       void* __restrict__ outv,
+                                                       uint32_t* __restrict__ stk, LineMap lm,
+                                                       float res) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)lm.nz_run * lm.n_outer) return;
+  const int zi = (int)(t % lm.nz_run);
+  const int oi = (int)(t / lm.nz_run);
+  const int64_t off0 = lm.base + (int64_t)oi * lm.outer_stride + zi;
+  const int n = lm.n;
+  const int64_t S = lm.stride;
+
+  int k = -1;
+  int v1 = 0, h1 = 0, v0 = 0, h0 = 0;
+  for (int q = 0; q < n; ++q) {
+    const int f = in[off0 + q * S];
+    if (f >= INF_I) continue;
+    const int h = f + q * q;
+    while (k >= 1) {
+      // pop while  s(top,q) <= s(second,top)
+      const long long lhs = (long long)(h - h1) * (long long)(v1 - v0);
+      const long long rhs = (long long)(h1 - h0) * (long long)(q - v1);
+      if (lhs > rhs) break;
+      --k;
+      v1 = v0;
+      h1 = h0;
+      if (k >= 1) {
+        const uint32_t e = stk[off0 + (int64_t)(k - 1) * S];
+        v0 = unpack_v(e);
+        h0 = unpack_h(e);
+      }
+    }
+    ++k;
+    stk[off0 + (int64_t)k * S] = pack_vh(q, h);
+    v0 = v1;
+    h0 = h1;
+    v1 = q;
+    h1 = h;
+  }
+  const int kmax = k;
+
+  int32_t* outi = (int32_t*)outv;
+  float* outf = (float*)outv;
+  if (kmax < 0) {
+    for (int q = 0; q < n; ++q) {
+      if (FINAL)
+        outf[off0 + q * S] = __int_as_float(0x7f800000);
+      else
+        outi[off0 + q * S] = INF_I;
+    }
+    return;
+  }
+  int kc = 0;
+  uint32_t e = stk[off0];
+  int vc = unpack_v(e), hc = unpack_h(e);
+  int vn = 0, hn = 0;
+  if (kmax >= 1) {
+    e = stk[off0 + S];
+    vn = unpack_v(e);
+    hn = unpack_h(e);
+  }
+  for (int q = 0; q < n; ++q) {
+    // advance while the next parabola's take-over abscissa is < q
+    while (kc < kmax && (hn - hc) < 2 * q * (vn - vc)) {
+      ++kc;
+      vc = vn;
+      hc = hn;
+      if (kc < kmax) {
+        e = stk[off0 + (int64_t)(kc + 1) * S];
+        vn = unpack_v(e);
+        hn = unpack_h(e);
+      }
+    }
+    const int val = hc + q * q - 2 * q * vc;  // (q-vc)^2 + f(vc)
+    if (FINAL)
+      outf[off0 + q * S] = res * sqrtf((float)val);
+    else
+      outi[off0 + q * S] = val;
+  }
+}
+
+// merge of the negative field, sdf_map.cpp:232-239
+__global__ void signed_merge_kernel(float* __restrict__ dist, const float* __restrict__ neg, int ny,
+                                    int nz, Box b, float res) {
+  const int nzb = b.hi[2] - b.lo[2] + 1, nyb = b.hi[1] - b.lo[1] + 1, nxb = b.hi[0] - b.lo[0] + 1;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)nzb * nyb * nxb) return;
+  const int z = b.lo[2] + (int)(t % nzb);
+  const int y = b.lo[1] + (int)((t / nzb) % nyb);
+  const int x = b.lo[0] + (int)(t / ((int64_t)nzb * nyb));
+  const int64_t a = ((int64_t)x * ny + y) * nz + z;
+  const float ng = neg[a];
+  if (ng > 0.0f) dist[a] += (-ng + res);
+}
+
+__global__ void sample_kernel(Geom g, const float* __restrict__ dist, int64_t n,
+                              const double* __restrict__ pos, double* __restrict__ d,
+                              double* __restrict__ grad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double p[3] = { pos[3 * i], pos[3 * i + 1], pos[3 * i + 2] };
+  double gr[3];
+  d[i] = dev_dist_with_grad(g, dist, p, gr);
+  grad[3 * i] = gr[0];
+  grad[3 * i + 1] = gr[1];
+  grad[3 * i + 2] = gr[2];
+}
+
+int run_three_pass(cudaStream_t s, const uint8_t* occ, int32_t* g1, int32_t* g2, uint32_t* stk,
+                   float* out, int nx, int ny, int nz, const Box& b, int mode, float res) {
+  (void)nx;
+  const int nxb = b.hi[0] - b.lo[0] + 1, nyb = b.hi[1] - b.lo[1] + 1, nzb = b.hi[2] - b.lo[2] + 1;
+  // z sweep
+  {
+    const int nlines = nxb * nyb;
+    const int wpb = 8;
+    zsweep_warp_kernel<<<(nlines + wpb - 1) / wpb, wpb * 32, 0, s>>>(occ, g1, ny, nz, b, mode, nlines);
+  }
+  // y sweep: lines (x,z)
+  {
+    LineMap lm;
+    lm.n = nyb;
+    lm.stride = nz;
+    lm.nz_run = nzb;
+    lm.n_outer = nxb;
+    lm.outer_stride = (int64_t)ny * nz;
+    lm.base = ((int64_t)b.lo[0] * ny + b.lo[1]) * nz + b.lo[2];
+    const int64_t nl = (int64_t)nzb * nxb;
+    envelope_kernel<false><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g1, g2, stk, lm, res);
+  }
+  // x sweep: lines (y,z), writes metres
+  {
+    LineMap lm;
+    lm.n = nxb;
+    lm.stride = (int64_t)ny * nz;
+    lm.nz_run = nzb;
+    lm.n_outer = nyb;
+    lm.outer_stride = nz;
+    lm.base = ((int64_t)b.lo[0] * ny + b.lo[1]) * nz + b.lo[2];
+    const int64_t nl = (int64_t)nzb * nyb;
+    envelope_kernel<true><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g2, out, stk, lm, res);
+  }
+  return 0;
+}
+
+}  // namespace
+
+int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags) {
+  Box b;
+  for (int i = 0; i < 3; ++i) {
+    b.lo[i] = bmin[i];
+    b.hi[i] = bmax[i];
+  }
+  const int mode = (flags & FUELGPU_ESDF_OPTIMISTIC) ? 0 : 1;
+  const float res = (float)m->g.res;
+  run_three_pass(m->stream, m->occ, m->g1, m->g2, m->stk, m->dist, m->g.nx, m->g.ny, m->g.nz, b, mode,
+                 res);
+  if (flags & FUELGPU_ESDF_SIGNED) {
+    if (!m->dist_neg) FUEL_CUDA(m, cudaMalloc(&m->dist_neg, sizeof(float) * m->nvox));
+    run_three_pass(m->stream, m->occ, m->g1, m->g2, m->stk, m->dist_neg, m->g.nx, m->g.ny, m->g.nz, b,
+                   2, res);
+    const int64_t nb = (int64_t)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
+    signed_merge_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, m->stream>>>(m->dist, m->dist_neg,
+                                                                          m->g.ny, m->g.nz, b, res);
+  }
+  FUEL_CUDA(m, cudaGetLastError());
+  return 0;
+}
+
+int esdf_sample_impl(FuelMap* m, int64_t n, const double* pos, double* d, double* grad) {
+  if (n <= 0) return 0;
+  sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, m->stream>>>(m->g, m->dist, n, pos, d, grad);
+  FUEL_CUDA(m, cudaGetLastError());
+  return 0;
+}
+
+// ---- multi-GPU building blocks ----------------------------------------------------------
+// z-sharded volume: each rank owns nzl planes of every (x,y) column.  The x and y sweeps
+// never cross z, so they run on the local slab first (the transform is separable and exact
+// in integers, so the sweep order is immaterial); after one all-to-all the z sweep sees whole
+// columns assembled from G chunks.
+namespace {
+
+// first sweep along y straight from the occupancy byte: 1-D distance to the nearest site on
+// the (x,z) line.  Thread per line, lanes along z.
+__global__ void ysweep_binary_kernel(const uint8_t* __restrict__ occ, int32_t* __restrict__ out,
+                                     int nx, int ny, int nz, int mode) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)nx * nz) return;
+  const int z = (int)(t % nz);
+  const int x = (int)(t / nz);
+  const int64_t off0 = (int64_t)x * ny * nz + z;
+  int last = -1;
+  for (int y = 0; y < ny; ++y) {
+    if (is_site(occ[off0 + (int64_t)y * nz], mode)) last = y;
+    out[off0 + (int64_t)y * nz] = last < 0 ? INF_I : (y - last);
+  }
+  int nxt = -1;
+  for (int y = ny - 1; y >= 0; --y) {
+    int d = out[off0 + (int64_t)y * nz];
+    if (d == 0) nxt = y;
+    int dr = nxt < 0 ? INF_I : (nxt - y);
+    d = min(d, dr);
+    out[off0 + (int64_t)y * nz] = (d == INF_I) ? INF_I : d * d;
+  }
+}
+
+// final z sweep over columns split in G chunks [G][nxl][ny][nzl]; thread per column.
+// z is contiguous inside a chunk; columns are strided by nzl so this kernel stages through
+// a per-thread walk (the volume of this pass is 1/G of the map per rank).
+__global__ void zsweep_chunks_kernel(const int32_t* __restrict__ in, float* __restrict__ out,
+                                     uint32_t* __restrict__ stk, int G, int nxl, int ny, int nzl,
+                                     float res) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t ncol = (int64_t)nxl * ny;
+  if (t >= ncol) return;
+  const int n = G * nzl;
+  const int64_t chunk = ncol * nzl;
+  const int64_t col = t * nzl;
+  const int64_t so = t * (int64_t)n;  // stack and output are [nxl][ny][G*nzl]
+  int k = -1;
+  int v1 = 0, h1 = 0, v0 = 0, h0 = 0;
+  for (int q = 0; q < n; ++q) {
+    const int f = in[(int64_t)(q / nzl) * chunk + col + (q % nzl)];
+    if (f >= INF_I) continue;
+    const int h = f + q * q;
+    while (k >= 1) {
+      const long long lhs = (long long)(h - h1) * (long long)(v1 - v0);
+      const long long rhs = (long long)(h1 - h0) * (long long)(q - v1);
+      if (lhs > rhs) break;
+      --k;
+      v1 = v0;
+      h1 = h0;
+      if (k >= 1) {
+        const uint32_t e = stk[so + (k - 1)];
+        v0 = unpack_v(e);
+        h0 = unpack_h(e);
+      }
+    }
+    ++k;
+    stk[so + k] = pack_vh(q, h);
+    v0 = v1;
+    h0 = h1;
+    v1 = q;
+    h1 = h;
+  }
+  const int kmax = k;
+  if (kmax < 0) {
+    for (int q = 0; q < n; ++q) out[so + q] = __int_as_float(0x7f800000);
+    return;
+  }
+  int kc = 0;
+  uint32_t e = stk[so];
+  int vc = unpack_v(e), hc = unpack_h(e), vn = 0, hn = 0;
+  if (kmax >= 1) {
+    e = stk[so + 1];
+    vn = unpack_v(e);
+    hn = unpack_h(e);
+  }
+  for (int q = 0; q < n; ++q) {
+    while (kc < kmax && (hn - hc) < 2 * q * (vn - vc)) {
+      ++kc;
+      vc = vn;
+      hc = hn;
+      if (kc < kmax) {
+        e = stk[so + kc + 1];
+        vn = unpack_v(e);
+        hn = unpack_h(e);
+      }
+    }
+    out[so + q] = res * sqrtf((float)(hc + q * q - 2 * q * vc));
+  }
+}
+
+}  // namespace
+
+int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl, int flags,
+                    int32_t* g2, int32_t* scratch) {
+  const int mode = (flags & FUELGPU_ESDF_OPTIMISTIC) ? 0 : 1;
+  // y sweep from the bytes into scratch (used as g1), x sweep scratch -> g2 with the hull
+  // stack aliased on g2's own lines is not possible (in/out differ), so the stack uses the
+  // upper half of scratch: scratch must hold 2*nx*ny*nzl int32.
+  int32_t* g1 = scratch;
+  uint32_t* stk = (uint32_t*)(scratch + (int64_t)nx * ny * nzl);
+  const int64_t nl = (int64_t)nx * nzl;
+  ysweep_binary_kernel<<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(occ, g1, nx, ny, nzl, mode);
+  LineMap lm;
+  lm.n = nx;
+  lm.stride = (int64_t)ny * nzl;
+  lm.nz_run = nzl;
+  lm.n_outer = ny;
+  lm.outer_stride = nzl;
+  lm.base = 0;
+  const int64_t nl2 = (int64_t)nzl * ny;
+  envelope_kernel<false><<<(unsigned)((nl2 + 127) / 128), 128, 0, s>>>(g1, g2, stk, lm, 0.f);
+  return cudaGetLastError() == cudaSuccess ? 0 : FUELGPU_ECUDA;
+}
+
+int edt_z_chunks_dev_impl(cudaStream_t s, const int32_t* g2c, int G, int nxl, int ny, int nzl,
+                          double res, float* out, int32_t* scratch) {
+  const int64_t ncol = (int64_t)nxl * ny;
+  zsweep_chunks_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, s>>>(g2c, out, (uint32_t*)scratch, G,
+                                                                    nxl, ny, nzl, (float)res);
+  return cudaGetLastError() == cudaSuccess ? 0 : FUELGPU_ECUDA;
+}

@@ -1,0 +1,974 @@
+// frontier.cu -- frontier voxel sweep, region-grow clustering and PCA split on sm_100a.
+//
+// Replaces FrontierFinder::searchFrontiers' voxel-scale work
+// (active_perception/src/frontier_finder.cpp:94-118), expandFrontier (:123-164),
+// computeFrontierInfo (:374-390), downsample (:757-774, PCL VoxelGrid restated) and
+// splitLargeFrontiers/splitHorizontally (:166-242, Eigen EigenSolver<Matrix2d> restated).
+//
+// The reference grows clusters one BFS at a time in scan order.  The same partition is
+// obtained here without any sequential walk (DESIGN.md "frontier clustering"):
+//   P(c)  = flag==0 && FREE && a 6-neighbour is UNKNOWN            (:113, :862-877)
+//   E     = P && isInBox(idx) && pos.z >= min_z                    (cells a BFS may absorb, :146-152)
+//   S     = P && inside the search box && !E                       (cells that can only be seeds)
+//   1. ordered compaction of E and S cells (ascending address)
+//   2. union-find over E with 26-connectivity (allNeighbors, :848-860)
+//   3. claimer(component) = min( first E cell of the component inside the search box,
+//                                first S cell 26-adjacent to the component )
+//      -- exactly the seed whose BFS reaches the component first in the reference's scan.
+//      Components with no claimer are never reached (flags untouched).
+//   4. cluster = all components sharing a claimer (+ the S seed itself); clusters in
+//      ascending seed address = tmp_frontiers_ order; size <= cluster_min dropped but flagged.
+//   5. level-synchronous PCA split of all clusters at once.
+#include "common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+constexpr int NONE = 0x7fffffff;
+
+struct FParams {
+  int dom_lo[3], dom_n[3];   // sweep domain (index box, inclusive lo, extent)
+  int s_lo[3], s_hi[3];      // search box, inclusive
+  int z_min_idx;             // first z index with pos.z >= min_z
+  int cluster_min;
+  double size_xy;
+  float leaf, leaf_inv;      // PCL leaf size (float) and its float inverse
+};
+
+__device__ __forceinline__ int tri_at(const Geom& g, const uint8_t* __restrict__ occ, int x, int y,
+                                      int z) {
+  // getOccupancy(idx): -1 outside the map (sdf_map.h:194-196)
+  if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz) return -1;
+  return __ldg(occ + addr_of(g, x, y, z)) & 3;
+}
+
+__device__ __forceinline__ bool frontier_pred(const Geom& g, const uint8_t* __restrict__ occ, int x,
+                                              int y, int z) {
+  // knownfree && isNeighborUnknown (frontier_finder.cpp:862-877)
+  if (tri_at(g, occ, x, y, z) != FUELGPU_FREE) return false;
+  return tri_at(g, occ, x - 1, y, z) == FUELGPU_UNKNOWN || tri_at(g, occ, x + 1, y, z) == FUELGPU_UNKNOWN ||
+         tri_at(g, occ, x, y - 1, z) == FUELGPU_UNKNOWN || tri_at(g, occ, x, y + 1, z) == FUELGPU_UNKNOWN ||
+         tri_at(g, occ, x, y, z - 1) == FUELGPU_UNKNOWN || tri_at(g, occ, x, y, z + 1) == FUELGPU_UNKNOWN;
+}
+
+// ---- 1. classify + ordered compaction -------------------------------------------------
+// One thread per domain voxel (z fastest).  Writes a class byte word per warp (two ballot
+// masks) and the per-block count; a second kernel turns masks + scanned block offsets into
+// the compact, address-ordered cell list.
+constexpr int CLS_BLOCK = 1024;
+
+__global__ void __launch_bounds__(CLS_BLOCK) classify_kernel(Geom g, FParams fp,
+                                                             const uint8_t* __restrict__ occ,
+                                                             const int8_t* __restrict__ flag,
+                                                             uint32_t* __restrict__ maskE,
+                                                             uint32_t* __restrict__ maskS,
+                                                             int* __restrict__ blockcnt, int64_t ndom) {
+  const int64_t L = (int64_t)blockIdx.x * CLS_BLOCK + threadIdx.x;
+  bool isE = false, isS = false;
+  if (L < ndom) {
+    const int z = fp.dom_lo[2] + (int)(L % fp.dom_n[2]);
+    const int y = fp.dom_lo[1] + (int)((L / fp.dom_n[2]) % fp.dom_n[1]);
+    const int x = fp.dom_lo[0] + (int)(L / ((int64_t)fp.dom_n[2] * fp.dom_n[1]));
+    if (flag[addr_of(g, x, y, z)] == 0 && frontier_pred(g, occ, x, y, z)) {
+      const bool inbox = x >= g.box_min[0] && x < g.box_max[0] && y >= g.box_min[1] &&
+                         y < g.box_max[1] && z >= g.box_min[2] && z < g.box_max[2];
+      isE = inbox && z >= fp.z_min_idx;
+      const bool ins = x >= fp.s_lo[0] && x <= fp.s_hi[0] && y >= fp.s_lo[1] && y <= fp.s_hi[1] &&
+                       z >= fp.s_lo[2] && z <= fp.s_hi[2];
+      isS = ins && !isE;
+    }
+  }
+  const unsigned mE = __ballot_sync(0xffffffffu, isE);
+  const unsigned mS = __ballot_sync(0xffffffffu, isS);
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) {
+    maskE[L >> 5] = mE;
+    maskS[L >> 5] = mS;
+  }
+  __shared__ int wsum[CLS_BLOCK / 32];
+  if (lane == 0) wsum[threadIdx.x >> 5] = __popc(mE) + __popc(mS);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = wsum[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = v;
+  }
+}
+
+// exclusive scan of n ints by one CTA of 1024 threads (n up to a few million)
+__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                    int n, int* __restrict__ total) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < n) out[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void __launch_bounds__(CLS_BLOCK) compact_kernel(Geom g, FParams fp,
+                                                            const uint32_t* __restrict__ maskE,
+                                                            const uint32_t* __restrict__ maskS,
+                                                            const int* __restrict__ blockoff,
+                                                            int* __restrict__ cell_addr,
+                                                            uint8_t* __restrict__ cell_cls,
+                                                            int* __restrict__ cellidx, int64_t ndom) {
+  const int64_t L = (int64_t)blockIdx.x * CLS_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned mE = 0, mS = 0;
+  if ((L - lane) < ndom) {
+    mE = maskE[L >> 5];
+    mS = maskS[L >> 5];
+  }
+  const unsigned m = mE | mS;
+  __shared__ int wsum[CLS_BLOCK / 32];
+  if (lane == 0) wsum[w] = __popc(m);
+  __syncthreads();
+  int woff = 0;
+  for (int i = 0; i < w; ++i) woff += wsum[i];
+  if ((m >> lane) & 1u) {
+    const int idx = blockoff[blockIdx.x] + woff + __popc(m & ((1u << lane) - 1u));
+    const int z = fp.dom_lo[2] + (int)(L % fp.dom_n[2]);
+    const int y = fp.dom_lo[1] + (int)((L / fp.dom_n[2]) % fp.dom_n[1]);
+    const int x = fp.dom_lo[0] + (int)(L / ((int64_t)fp.dom_n[2] * fp.dom_n[1]));
+    const int a = (int)addr_of(g, x, y, z);
+    cell_addr[idx] = a;
+    cell_cls[idx] = ((mE >> lane) & 1u) ? 1 : 2;  // 1 = E, 2 = S
+    cellidx[a] = idx;
+  }
+}
+
+// ---- 2. union-find over E cells, 26-connectivity -----------------------------------------
+__device__ __forceinline__ int uf_find(const int* parent, int i) {
+  int p = parent[i];
+  while (p != i) {
+    i = p;
+    p = parent[i];
+  }
+  return i;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(&parent[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void init_parent_kernel(int* parent, int* claim, int* csize, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    parent[i] = i;
+    claim[i] = NONE;
+    csize[i] = 0;
+  }
+}
+
+__device__ __forceinline__ void addr_to_idx(const Geom& g, int a, int& x, int& y, int& z) {
+  z = a % g.nz;
+  const int r = a / g.nz;
+  y = r % g.ny;
+  x = r / g.ny;
+}
+
+__global__ void union_kernel(Geom g, const int* __restrict__ cell_addr,
+                             const uint8_t* __restrict__ cell_cls, const int* __restrict__ cellidx,
+                             int* parent, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || cell_cls[i] != 1) return;
+  int x, y, z;
+  addr_to_idx(g, cell_addr[i], x, y, z);
+  // the 13 neighbours with smaller address
+  for (int dx = -1; dx <= 0; ++dx)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dz = -1; dz <= 1; ++dz) {
+        if (dx == 0 && (dy > 0 || (dy == 0 && dz >= 0))) continue;
+        const int X = x + dx, Y = y + dy, Z = z + dz;
+        if (X < 0 || Y < 0 || Z < 0 || Y >= g.ny || Z >= g.nz) continue;
+        const int j = cellidx[addr_of(g, X, Y, Z)];
+        if (j >= 0 && cell_cls[j] == 1) uf_union(parent, i, j);
+      }
+}
+
+__global__ void flatten_kernel(int* parent, const uint8_t* __restrict__ cell_cls, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || cell_cls[i] != 1) return;
+  parent[i] = uf_find(parent, i);
+}
+
+// ---- 3. claimers ----------------------------------------------------------------------------
+__global__ void claim_kernel(Geom g, FParams fp, const int* __restrict__ cell_addr,
+                             const uint8_t* __restrict__ cell_cls, const int* __restrict__ cellidx,
+                             const int* __restrict__ label, int* claim, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x, y, z;
+  addr_to_idx(g, cell_addr[i], x, y, z);
+  if (cell_cls[i] == 1) {
+    const bool ins = x >= fp.s_lo[0] && x <= fp.s_hi[0] && y >= fp.s_lo[1] && y <= fp.s_hi[1] &&
+                     z >= fp.s_lo[2] && z <= fp.s_hi[2];
+    if (ins) atomicMin(&claim[label[i]], i);
+  } else {
+    for (int dx = -1; dx <= 1; ++dx)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dz = -1; dz <= 1; ++dz) {
+          if (dx == 0 && dy == 0 && dz == 0) continue;
+          const int X = x + dx, Y = y + dy, Z = z + dz;
+          if (X < 0 || Y < 0 || Z < 0 || X >= g.nx || Y >= g.ny || Z >= g.nz) continue;
+          const int j = cellidx[addr_of(g, X, Y, Z)];
+          if (j >= 0 && cell_cls[j] == 1) atomicMin(&claim[label[j]], i);
+        }
+  }
+}
+
+// ---- 4. cluster id (= seed cell index) per cell, sizes, flags --------------------------------
+__global__ void assign_kernel(const int* __restrict__ cell_addr, const uint8_t* __restrict__ cell_cls,
+                              const int* __restrict__ label, const int* __restrict__ claim,
+                              int* __restrict__ seed, int* csize, int8_t* __restrict__ flag, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = cell_cls[i] == 1 ? claim[label[i]] : i;
+  seed[i] = s;
+  if (s != NONE) {
+    atomicAdd(&csize[s], 1);
+    flag[cell_addr[i]] = 1;  // frontier_flag_ set for every absorbed cell (:132,:155)
+  }
+}
+
+// per cell: 1 if it is the seed of a kept cluster (for the rank scan), and kept-cell marks
+__global__ void mark_kernel(const int* __restrict__ seed, const int* __restrict__ csize, int cluster_min,
+                            int* __restrict__ is_root, int* __restrict__ is_kept, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = seed[i];
+  const bool kept = s != NONE && csize[s] > cluster_min;  // expanded.size() > cluster_min_ (:157)
+  is_kept[i] = kept ? 1 : 0;
+  is_root[i] = (kept && s == i) ? 1 : 0;
+}
+
+__global__ void reset_cellidx_kernel(const int* __restrict__ cell_addr, int* __restrict__ cellidx, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cellidx[cell_addr[i]] = -1;
+}
+
+// kept cells -> dense arrays; cellidx now maps voxel -> kept index
+__global__ void gather_kept_kernel(const int* __restrict__ cell_addr, const int* __restrict__ seed,
+                                   const int* __restrict__ is_kept, const int* __restrict__ kept_off,
+                                   const int* __restrict__ root_rank, int* __restrict__ k_addr,
+                                   int* __restrict__ k_cl, int* __restrict__ cellidx, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (is_kept[i]) {
+    const int k = kept_off[i];
+    k_addr[k] = cell_addr[i];
+    k_cl[k] = root_rank[seed[i]];
+    cellidx[cell_addr[i]] = k;
+  } else {
+    cellidx[cell_addr[i]] = -1;
+  }
+}
+
+// ---- 5. split levels ----------------------------------------------------------------------------
+struct ClusterMeta {  // persistent per cluster
+  int root;           // rank of the root cluster (tmp_frontiers_ order before the split)
+  unsigned path;      // split path, left aligned (bit 31 = first split; 0 = ftr1, 1 = ftr2)
+  int depth;
+  int active;         // 1 while the cluster may still split
+  double mean[3];
+  double pc[2];
+  int do_split;
+  int new_id;
+};
+
+struct ClusterStat {  // per cluster, rebuilt every level while the cluster is active
+  long long sx, sy, sz;
+  int n;
+  int lo[3], hi[3];
+  // covariance of filtered cells in exact two-part fixed point
+  long long cxx_hi, cxx_lo, cxy_hi, cxy_lo, cyy_hi, cyy_lo;
+  int nfilt;
+  int need_split;
+  int cnt0, cnt1;  // partition sizes
+};
+
+
+__global__ void stat_reset_kernel(ClusterStat* st, const ClusterMeta* __restrict__ meta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C || !meta[c].active) return;  // finished clusters keep their last statistics
+  ClusterStat s;
+  memset(&s, 0, sizeof(s));
+  s.lo[0] = s.lo[1] = s.lo[2] = NONE;
+  s.hi[0] = s.hi[1] = s.hi[2] = -1;
+  st[c] = s;
+}
+
+__global__ void stat_accum_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int c = k_cl[k];
+  if (!meta[c].active) return;
+  int x, y, z;
+  addr_to_idx(g, k_addr[k], x, y, z);
+  ClusterStat* s = &st[c];
+  atomicAdd((unsigned long long*)&s->sx, (unsigned long long)x);
+  atomicAdd((unsigned long long*)&s->sy, (unsigned long long)y);
+  atomicAdd((unsigned long long*)&s->sz, (unsigned long long)z);
+  atomicAdd(&s->n, 1);
+  atomicMin(&s->lo[0], x);
+  atomicMin(&s->lo[1], y);
+  atomicMin(&s->lo[2], z);
+  atomicMax(&s->hi[0], x);
+  atomicMax(&s->hi[1], y);
+  atomicMax(&s->hi[2], z);
+}
+
+// average_ of computeFrontierInfo (:376-386).  The reference sums positions sequentially in
+// fp64; here the index sums are exact integers and the mean is formed once (differs from
+// the sequential sum by rounding only, ~1e-16 relative).
+__global__ void mean_kernel(Geom g, ClusterMeta* meta, const ClusterStat* __restrict__ st, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C || !meta[c].active) return;
+  const ClusterStat& s = st[c];
+  const double inv = 1.0 / (double)s.n;
+  meta[c].mean[0] = ((double)s.sx * inv + 0.5) * g.res + g.origin[0];
+  meta[c].mean[1] = ((double)s.sy * inv + 0.5) * g.res + g.origin[1];
+  meta[c].mean[2] = ((double)s.sz * inv + 0.5) * g.res + g.origin[2];
+}
+
+__device__ __forceinline__ float cell_posf(const Geom& g, int id, int axis) {
+  // (float) of indexToPos (sdf_map.h:132-135); PointXYZ narrowing at frontier_finder.cpp:762
+  return (float)((id + 0.5) * g.res + g.origin[axis]);
+}
+// leaf coordinate of PCL VoxelGrid: (int)(floorf(p * inv_leaf) - (float)min_b)
+__device__ __forceinline__ int leaf_coord(const Geom& g, const FParams& fp, int id, int axis, int min_b) {
+  return (int)(floorf(cell_posf(g, id, axis) * fp.leaf_inv) - (float)min_b);
+}
+
+// PCL VoxelGrid restated per cell: the min-address cell of every occupied leaf computes the
+// leaf centroid (float accumulation in ascending address order) and contributes to the split
+// test (:183-189) and the covariance (:194-200).
+__global__ void downsample_kernel(Geom g, FParams fp, const int* __restrict__ k_addr,
+                                  const int* __restrict__ k_cl, const int* __restrict__ cellidx,
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st,
+                                  float* __restrict__ k_cent, int* __restrict__ k_leaf, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int c = k_cl[k];
+  if (!meta[c].active) return;
+  k_leaf[k] = -1;
+  int id[3];
+  addr_to_idx(g, k_addr[k], id[0], id[1], id[2]);
+  const ClusterStat& s = st[c];
+  int min_b[3], lc[3], lo[3], hi[3], div_b[3];
+  const int nmax[3] = { g.nx, g.ny, g.nz };
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = (int)floorf(cell_posf(g, s.lo[a], a) * fp.leaf_inv);
+    const int max_b = (int)floorf(cell_posf(g, s.hi[a], a) * fp.leaf_inv);
+    div_b[a] = max_b - min_b[a] + 1;
+    lc[a] = leaf_coord(g, fp, id[a], a, min_b[a]);
+    lo[a] = id[a];
+    hi[a] = id[a];
+    while (lo[a] - 1 >= 0 && lo[a] - 1 >= s.lo[a] && leaf_coord(g, fp, lo[a] - 1, a, min_b[a]) == lc[a]) --lo[a];
+    while (hi[a] + 1 < nmax[a] && hi[a] + 1 <= s.hi[a] && leaf_coord(g, fp, hi[a] + 1, a, min_b[a]) == lc[a]) ++hi[a];
+  }
+  // ascending address order over the leaf's voxels
+  float sum[3] = { 0.f, 0.f, 0.f };
+  int cnt = 0;
+  for (int x = lo[0]; x <= hi[0]; ++x)
+    for (int y = lo[1]; y <= hi[1]; ++y)
+      for (int z = lo[2]; z <= hi[2]; ++z) {
+        const int j = cellidx[addr_of(g, x, y, z)];
+        if (j < 0 || k_cl[j] != c) continue;
+        if (cnt == 0 && j != k) return;  // a smaller-address cell owns this leaf
+        sum[0] += cell_posf(g, x, 0);
+        sum[1] += cell_posf(g, y, 1);
+        sum[2] += cell_posf(g, z, 2);
+        ++cnt;
+      }
+  const float fc = (float)cnt;
+  const float cx = sum[0] / fc, cy = sum[1] / fc, cz = sum[2] / fc;
+  k_cent[3 * k] = cx;
+  k_cent[3 * k + 1] = cy;
+  k_cent[3 * k + 2] = cz;
+  k_leaf[k] = lc[0] + lc[1] * div_b[0] + lc[2] * div_b[0] * div_b[1];
+  atomicAdd(&st[c].nfilt, 1);
+  const double dx = (double)cx - meta[c].mean[0], dy = (double)cy - meta[c].mean[1];
+  if (sqrt(dx * dx + dy * dy) > fp.size_xy) atomicOr(&st[c].need_split, 1);
+}
+
+// covariance terms as exact two-part fixed point: p = hi*2^-20 + lo*2^-82
+__device__ __forceinline__ void fx_add(long long* hi, long long* lo, double p) {
+  const double h = rint(p * 1048576.0);             // 2^20
+  const double l = (p - h * (1.0 / 1048576.0));     // exact, |l| <= 2^-21
+  atomicAdd((unsigned long long*)hi, (unsigned long long)(long long)h);
+  atomicAdd((unsigned long long*)lo, (unsigned long long)(long long)rint(l * 4835703278458516698824704.0));  // 2^82
+}
+__device__ __forceinline__ double fx_get(long long hi, long long lo) {
+  return (double)hi * (1.0 / 1048576.0) + (double)lo * (1.0 / 4835703278458516698824704.0);
+}
+
+__global__ void cov_kernel(const int* __restrict__ k_cl, const int* __restrict__ k_leaf,
+                           const float* __restrict__ k_cent, const ClusterMeta* __restrict__ meta,
+                           ClusterStat* st, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int c = k_cl[k];
+  if (!meta[c].active || k_leaf[k] < 0 || !st[c].need_split) return;
+  const double dx = (double)k_cent[3 * k] - meta[c].mean[0];
+  const double dy = (double)k_cent[3 * k + 1] - meta[c].mean[1];
+  fx_add(&st[c].cxx_hi, &st[c].cxx_lo, dx * dx);
+  fx_add(&st[c].cxy_hi, &st[c].cxy_lo, dx * dy);
+  fx_add(&st[c].cyy_hi, &st[c].cyy_lo, dy * dy);
+}
+
+// Eigen 3.3 EigenSolver<Matrix2d> restated for a symmetric matrix (same procedure as
+// oracle/fuel_oracle.c orc_principal_axis_2x2; third-party convention, unpinned).
+__device__ void make_givens(double p, double q, double* c, double* s) {
+  if (q == 0.0) {
+    *c = p < 0 ? -1.0 : 1.0;
+    *s = 0.0;
+  } else if (p == 0.0) {
+    *c = 0.0;
+    *s = q < 0 ? 1.0 : -1.0;
+  } else if (fabs(p) > fabs(q)) {
+    double t = q / p;
+    double u = sqrt(1.0 + t * t);
+    if (p < 0) u = -u;
+    *c = 1.0 / u;
+    *s = -t * (*c);
+  } else {
+    double t = p / q;
+    double u = sqrt(1.0 + t * t);
+    if (q < 0) u = -u;
+    *s = -1.0 / u;
+    *c = -t * (*s);
+  }
+}
+// products and sums are kept un-contracted (no FMA) to follow the host arithmetic
+#define MUL(a, b) __dmul_rn((a), (b))
+#define ADD(a, b) __dadd_rn((a), (b))
+__device__ void principal_axis_2x2(double a, double b, double d, double pc[2]) {
+  const double eps = 2.220446049250313e-16;
+  double T[2][2] = { { a, b }, { b, d } };
+  double U[2][2] = { { 1, 0 }, { 0, 1 } };
+  const double norm = fabs(a) + fabs(b) + fabs(b) + fabs(d);
+  if (norm != 0.0) {
+    const double s = fabs(T[0][0]) + fabs(T[1][1]);
+    const double thr = MUL(s, eps);
+    if (!(fabs(T[1][0]) <= thr)) {
+      const double p = MUL(0.5, T[0][0] - T[1][1]);
+      const double q = ADD(MUL(p, p), MUL(T[1][0], T[0][1]));
+      if (q >= 0) {
+        const double z = sqrt(fabs(q));
+        double c, sn;
+        if (p >= 0)
+          make_givens(p + z, T[1][0], &c, &sn);
+        else
+          make_givens(p - z, T[1][0], &c, &sn);
+        for (int j = 0; j < 2; ++j) {
+          const double x = T[0][j], y = T[1][j];
+          T[0][j] = ADD(MUL(c, x), -MUL(sn, y));
+          T[1][j] = ADD(MUL(sn, x), MUL(c, y));
+        }
+        for (int i = 0; i < 2; ++i) {
+          const double x = T[i][0], y = T[i][1];
+          T[i][0] = ADD(MUL(c, x), -MUL(sn, y));
+          T[i][1] = ADD(MUL(sn, x), MUL(c, y));
+        }
+        T[1][0] = 0.0;
+        for (int i = 0; i < 2; ++i) {
+          const double x = U[i][0], y = U[i][1];
+          U[i][0] = ADD(MUL(c, x), -MUL(sn, y));
+          U[i][1] = ADD(MUL(sn, x), MUL(c, y));
+        }
+      }
+    } else {
+      T[1][0] = 0.0;
+    }
+  }
+  double e1[2];
+  {
+    const double w = T[0][0] - T[1][1];
+    const double r = T[0][1];
+    e1[0] = (w != 0.0) ? -r / w : -r / MUL(eps, norm);
+    e1[1] = 1.0;
+  }
+  double v0[2] = { ADD(MUL(U[0][0], 1.0), MUL(U[0][1], 0.0)), ADD(MUL(U[1][0], 1.0), MUL(U[1][1], 0.0)) };
+  double v1[2] = { ADD(MUL(U[0][0], e1[0]), MUL(U[0][1], e1[1])), ADD(MUL(U[1][0], e1[0]), MUL(U[1][1], e1[1])) };
+  const double n0 = sqrt(ADD(MUL(v0[0], v0[0]), MUL(v0[1], v0[1])));
+  const double n1 = sqrt(ADD(MUL(v1[0], v1[0]), MUL(v1[1], v1[1])));
+  if (n0 > 0) { v0[0] /= n0; v0[1] /= n0; }
+  if (n1 > 0) { v1[0] /= n1; v1[1] /= n1; }
+  const int max_idx = (T[1][1] > T[0][0]) ? 1 : 0;  // ties -> 0 (:207-212)
+  pc[0] = max_idx == 0 ? v0[0] : v1[0];
+  pc[1] = max_idx == 0 ? v0[1] : v1[1];
+}
+
+__global__ void pca_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C || !meta[c].active) return;
+  const ClusterStat& s = st[c];
+  meta[c].do_split = 0;
+  if (!s.need_split || meta[c].depth >= 32) return;
+  const double m = (double)s.nfilt;
+  const double cxx = fx_get(s.cxx_hi, s.cxx_lo) / m, cxy = fx_get(s.cxy_hi, s.cxy_lo) / m,
+               cyy = fx_get(s.cyy_hi, s.cyy_lo) / m;
+  principal_axis_2x2(cxx, cxy, cyy, meta[c].pc);
+  meta[c].do_split = 1;
+}
+
+__device__ __forceinline__ int cell_side(const Geom& g, const ClusterMeta& mt, int addr) {
+  int x, y, z;
+  addr_to_idx(g, addr, x, y, z);
+  const double px = (x + 0.5) * g.res + g.origin[0], py = (y + 0.5) * g.res + g.origin[1];
+  // (cell.head<2>() - mean).dot(first_pc) >= 0 -> ftr1 (:218-223)
+  const double d = ADD(MUL(px - mt.mean[0], mt.pc[0]), MUL(py - mt.mean[1], mt.pc[1]));
+  return d >= 0 ? 0 : 1;
+}
+
+__global__ void side_count_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int c = k_cl[k];
+  if (!meta[c].active || !meta[c].do_split) return;
+  if (cell_side(g, meta[c], k_addr[k]) == 0)
+    atomicAdd(&st[c].cnt0, 1);
+  else
+    atomicAdd(&st[c].cnt1, 1);
+}
+
+// decide splits, allocate ids for the ftr2 halves, update metadata.  Single thread block
+// scan over clusters keeps ids deterministic.
+__global__ void __launch_bounds__(1024) split_alloc_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st,
+                                                           int C, int* __restrict__ n_new) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < C; base += 1024) {
+    const int c = base + threadIdx.x;
+    int v = 0;
+    if (c < C && meta[c].active) {
+      if (meta[c].do_split && st[c].cnt0 > 0 && st[c].cnt1 > 0)
+        v = 1;
+      else {
+        meta[c].do_split = 0;
+        meta[c].active = 0;  // final
+      }
+    }
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (v) {
+      const int nid = C + carry + sh[threadIdx.x] - 1;
+      ClusterMeta& p = meta[c];
+      ClusterMeta ch = p;
+      p.new_id = nid;
+      ch.path = p.path | (1u << (31 - p.depth));
+      ch.depth = p.depth + 1;
+      ch.active = 1;
+      ch.do_split = 0;
+      p.depth += 1;
+      meta[nid] = ch;  // child fields that matter: root, path, depth, active
+      // parent's mean/pc are still needed by relabel_kernel this level; child's copy is unused
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_new = carry;
+}
+
+__global__ void relabel_kernel(Geom g, const int* __restrict__ k_addr, int* __restrict__ k_cl,
+                               const ClusterMeta* __restrict__ meta, int K, int C_old) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int c = k_cl[k];
+  if (c >= C_old || !meta[c].do_split) return;
+  if (cell_side(g, meta[c], k_addr[k]) == 1) k_cl[k] = meta[c].new_id;
+}
+
+__global__ void clear_do_split_kernel(ClusterMeta* meta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) meta[c].do_split = 0;
+}
+
+__global__ void init_meta_kernel(ClusterMeta* meta, int R) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= R) return;
+  ClusterMeta m;
+  memset(&m, 0, sizeof(m));
+  m.root = c;
+  m.active = 1;
+  meta[c] = m;
+}
+
+__global__ void is_changed_kernel(Geom g, const uint8_t* __restrict__ occ, const int* __restrict__ offs,
+                                  const int* __restrict__ addr, uint8_t* __restrict__ changed, int m) {
+  // isFrontierChanged (:365-372): one block per stored cluster
+  const int c = blockIdx.x;
+  if (c >= m) return;
+  __shared__ int any;
+  if (threadIdx.x == 0) any = 0;
+  __syncthreads();
+  for (int i = offs[c] + threadIdx.x; i < offs[c + 1]; i += blockDim.x) {
+    int x, y, z;
+    addr_to_idx(g, addr[i], x, y, z);
+    if (!frontier_pred(g, occ, x, y, z)) any = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) changed[c] = (uint8_t)any;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 1024;
+    if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) return FUELGPU_ENOMEM;
+    cap = want;
+    return 0;
+  }
+  // grow keeping the first `keep` elements (stream-ordered copy on `s`)
+  int grow_preserve(size_t n, size_t keep, cudaStream_t s) {
+    if (n <= cap) return 0;
+    T* np = nullptr;
+    size_t want = n + n / 2 + 1024;
+    if (cudaMalloc(&np, want * sizeof(T)) != cudaSuccess) return FUELGPU_ENOMEM;
+    if (p && keep) {
+      cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      cudaStreamSynchronize(s);
+    }
+    if (p) cudaFree(p);
+    p = np;
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct FrontierState {
+  int* cellidx = nullptr;  // voxel -> cell index, -1 elsewhere (persistent, sparse use)
+  DevBuf<uint32_t> maskE, maskS;
+  DevBuf<int> blockcnt, blockoff;
+  DevBuf<int> cell_addr, parent, claim, csize, seed, is_root, is_kept, root_rank, kept_off;
+  DevBuf<uint8_t> cell_cls;
+  DevBuf<int> k_addr, k_cl, k_leaf;
+  DevBuf<float> k_cent;
+  DevBuf<ClusterStat> stat;
+  DevBuf<ClusterMeta> meta;
+  int* d_counters = nullptr;  // [0] n_cand [1] n_roots [2] n_kept [3] n_new
+  // results of the last search (host side, CSR)
+  std::vector<int32_t> h_cell_off, h_cell_addr, h_filt_off;
+  std::vector<double> h_filtered, h_avg, h_bmin, h_bmax;
+};
+
+int frontier_state_create(FuelMap* m) {
+  m->fs = new FrontierState();
+  FUEL_CUDA(m, cudaMalloc(&m->fs->cellidx, sizeof(int) * m->nvox));
+  FUEL_CUDA(m, cudaMemsetAsync(m->fs->cellidx, 0xff, sizeof(int) * m->nvox, m->stream));
+  FUEL_CUDA(m, cudaMalloc(&m->fs->d_counters, sizeof(int) * 8));
+  return 0;
+}
+
+void frontier_state_destroy(FuelMap* m) {
+  if (!m->fs) return;
+  FrontierState* f = m->fs;
+  if (f->cellidx) cudaFree(f->cellidx);
+  if (f->d_counters) cudaFree(f->d_counters);
+  f->maskE.release(); f->maskS.release(); f->blockcnt.release(); f->blockoff.release();
+  f->cell_addr.release(); f->parent.release(); f->claim.release(); f->csize.release();
+  f->seed.release(); f->is_root.release(); f->is_kept.release(); f->root_rank.release();
+  f->kept_off.release(); f->cell_cls.release(); f->k_addr.release(); f->k_cl.release();
+  f->k_leaf.release(); f->k_cent.release(); f->stat.release(); f->meta.release();
+  delete f;
+  m->fs = nullptr;
+}
+
+#define ENSURE(buf, n)                                         \
+  do {                                                         \
+    if ((buf).ensure(n)) return fuel_fail(m, FUELGPU_ENOMEM, "frontier: device allocation failed"); \
+  } while (0)
+
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
+                         const FuelFrontierParams* p, int32_t* n_clusters, int32_t* n_cells,
+                         int32_t* n_filtered) {
+  FrontierState* f = m->fs;
+  const Geom& g = m->g;
+  cudaStream_t s = m->stream;
+  const int nmax[3] = { g.nx, g.ny, g.nz };
+
+  // search box: updated box inflated by (1,1,0.5) m, clamped to the exploration box, then
+  // posToIndex (frontier_finder.cpp:94-104)
+  FParams fp;
+  const double infl[3] = { 1, 1, 0.5 };
+  for (int k = 0; k < 3; ++k) {
+    double lo = umin[k] - infl[k], hi = umax[k] + infl[k];
+    lo = lo > g.box_mind[k] ? lo : g.box_mind[k];
+    hi = hi < g.box_maxd[k] ? hi : g.box_maxd[k];
+    int ilo = (int)floor((lo - g.origin[k]) * g.res_inv);
+    int ihi = (int)floor((hi - g.origin[k]) * g.res_inv);
+    // cells outside the map are never knownfree; clip (the reference indexes out of bounds
+    // there)
+    fp.s_lo[k] = ilo < 0 ? 0 : ilo;
+    fp.s_hi[k] = ihi > nmax[k] - 1 ? nmax[k] - 1 : ihi;
+    // sweep domain: exploration box [box_min, box_max] united with the search box
+    int dlo = g.box_min[k] < fp.s_lo[k] ? g.box_min[k] : fp.s_lo[k];
+    int dhi = g.box_max[k] > fp.s_hi[k] ? g.box_max[k] : fp.s_hi[k];
+    dlo = dlo < 0 ? 0 : dlo;
+    dhi = dhi > nmax[k] - 1 ? nmax[k] - 1 : dhi;
+    fp.dom_lo[k] = dlo;
+    fp.dom_n[k] = dhi - dlo + 1;
+    if (fp.dom_n[k] <= 0) {
+      fp.dom_n[k] = 0;
+    }
+  }
+  // first z index whose centre is not below min_z: `pos[2] < 0.4 -> continue` (:152)
+  {
+    int zi = 0;
+    while (zi < g.nz && ((zi + 0.5) * g.res + g.origin[2]) < p->min_z) ++zi;
+    fp.z_min_idx = zi;
+  }
+  fp.cluster_min = p->cluster_min;
+  fp.size_xy = p->cluster_size_xy;
+  fp.leaf = (float)(g.res * p->down_sample);  // setLeafSize(float) narrowing
+  fp.leaf_inv = 1.0f / fp.leaf;
+
+  f->h_cell_off.assign(1, 0);
+  f->h_cell_addr.clear();
+  f->h_filt_off.assign(1, 0);
+  f->h_filtered.clear();
+  f->h_avg.clear();
+  f->h_bmin.clear();
+  f->h_bmax.clear();
+  *n_clusters = *n_cells = *n_filtered = 0;
+
+  const int64_t ndom = (int64_t)fp.dom_n[0] * fp.dom_n[1] * fp.dom_n[2];
+  if (ndom <= 0) return 0;
+  const unsigned nb = nblk(ndom, CLS_BLOCK);
+  const size_t nwords = (size_t)nb * (CLS_BLOCK / 32);
+  ENSURE(f->maskE, nwords);
+  ENSURE(f->maskS, nwords);
+  ENSURE(f->blockcnt, nb);
+  ENSURE(f->blockoff, nb);
+
+  classify_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, m->occ, m->flag, f->maskE.p, f->maskS.p, f->blockcnt.p, ndom);
+  scan_kernel<<<1, 1024, 0, s>>>(f->blockcnt.p, f->blockoff.p, (int)nb, f->d_counters + 0);
+  int n_cand = 0;
+  FUEL_CUDA(m, cudaMemcpyAsync(&n_cand, f->d_counters, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaStreamSynchronize(s));
+  if (n_cand == 0) return 0;
+
+  ENSURE(f->cell_addr, n_cand); ENSURE(f->cell_cls, n_cand); ENSURE(f->parent, n_cand);
+  ENSURE(f->claim, n_cand); ENSURE(f->csize, n_cand); ENSURE(f->seed, n_cand);
+  ENSURE(f->is_root, n_cand); ENSURE(f->is_kept, n_cand); ENSURE(f->root_rank, n_cand);
+  ENSURE(f->kept_off, n_cand);
+
+  compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p,
+                                          f->cell_cls.p, f->cellidx, ndom);
+  const unsigned cb = nblk(n_cand, 256);
+  init_parent_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->claim.p, f->csize.p, n_cand);
+  union_kernel<<<cb, 256, 0, s>>>(g, f->cell_addr.p, f->cell_cls.p, f->cellidx, f->parent.p, n_cand);
+  flatten_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->cell_cls.p, n_cand);
+  claim_kernel<<<cb, 256, 0, s>>>(g, fp, f->cell_addr.p, f->cell_cls.p, f->cellidx, f->parent.p, f->claim.p, n_cand);
+  assign_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cell_cls.p, f->parent.p, f->claim.p, f->seed.p,
+                                   f->csize.p, m->flag, n_cand);
+  mark_kernel<<<cb, 256, 0, s>>>(f->seed.p, f->csize.p, fp.cluster_min, f->is_root.p, f->is_kept.p, n_cand);
+  scan_kernel<<<1, 1024, 0, s>>>(f->is_root.p, f->root_rank.p, n_cand, f->d_counters + 1);
+  scan_kernel<<<1, 1024, 0, s>>>(f->is_kept.p, f->kept_off.p, n_cand, f->d_counters + 2);
+  int cnt[3];
+  FUEL_CUDA(m, cudaMemcpyAsync(cnt, f->d_counters, sizeof(int) * 3, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaStreamSynchronize(s));
+  const int R = cnt[1], K = cnt[2];
+  if (R == 0 || K == 0) {
+    reset_cellidx_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cellidx, n_cand);
+    FUEL_CUDA(m, cudaGetLastError());
+    return 0;
+  }
+  ENSURE(f->k_addr, K); ENSURE(f->k_cl, K); ENSURE(f->k_leaf, K); ENSURE(f->k_cent, (size_t)3 * K);
+  gather_kept_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->seed.p, f->is_kept.p, f->kept_off.p,
+                                        f->root_rank.p, f->k_addr.p, f->k_cl.p, f->cellidx, n_cand);
+
+  // ---- split levels -------------------------------------------------------------------
+  // at most one new cluster per kept cell; K bounds the cluster count
+  ENSURE(f->meta, (size_t)2 * R + 1024);
+  ENSURE(f->stat, (size_t)2 * R + 1024);
+  int C = R;
+  init_meta_kernel<<<nblk(R, 256), 256, 0, s>>>(f->meta.p, R);
+  const unsigned kb = nblk(K, 256);
+  for (int level = 0; level < 40; ++level) {
+    // every active cluster may spawn one new cluster this level
+    if (f->meta.grow_preserve((size_t)2 * C, C, s) || f->stat.grow_preserve((size_t)2 * C, C, s))
+      return fuel_fail(m, FUELGPU_ENOMEM, "frontier: device allocation failed");
+    const unsigned ccb = nblk(C, 256);
+    stat_reset_kernel<<<ccb, 256, 0, s>>>(f->stat.p, f->meta.p, C);
+    stat_accum_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, K);
+    mean_kernel<<<ccb, 256, 0, s>>>(g, f->meta.p, f->stat.p, C);
+    downsample_kernel<<<kb, 256, 0, s>>>(g, fp, f->k_addr.p, f->k_cl.p, f->cellidx, f->meta.p, f->stat.p,
+                                         f->k_cent.p, f->k_leaf.p, K);
+    cov_kernel<<<kb, 256, 0, s>>>(f->k_cl.p, f->k_leaf.p, f->k_cent.p, f->meta.p, f->stat.p, K);
+    pca_kernel<<<ccb, 256, 0, s>>>(f->meta.p, f->stat.p, C);
+    side_count_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, K);
+    split_alloc_kernel<<<1, 1024, 0, s>>>(f->meta.p, f->stat.p, C, f->d_counters + 3);
+    relabel_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, K, C);
+    int n_new = 0;
+    FUEL_CUDA(m, cudaMemcpyAsync(&n_new, f->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FUEL_CUDA(m, cudaStreamSynchronize(s));
+    if (n_new == 0) break;
+    clear_do_split_kernel<<<ccb, 256, 0, s>>>(f->meta.p, C);
+    C += n_new;
+  }
+
+  // ---- download and marshal into CSR (ordering only; no geometry is decided here) ------
+  std::vector<int> h_addr(K), h_cl(K), h_leaf(K);
+  std::vector<float> h_cent((size_t)3 * K);
+  std::vector<ClusterMeta> h_meta(C);
+  std::vector<ClusterStat> h_stat(C);
+  FUEL_CUDA(m, cudaMemcpyAsync(h_addr.data(), f->k_addr.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_cl.data(), f->k_cl.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_leaf.data(), f->k_leaf.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_cent.data(), f->k_cent.p, sizeof(float) * 3 * K, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_meta.data(), f->meta.p, sizeof(ClusterMeta) * C, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_stat.data(), f->stat.p, sizeof(ClusterStat) * C, cudaMemcpyDeviceToHost, s));
+  reset_cellidx_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cellidx, n_cand);
+  FUEL_CUDA(m, cudaGetLastError());
+  FUEL_CUDA(m, cudaStreamSynchronize(s));
+
+  // cluster order: (root, path) lexicographic = the reference's in-place list replacement
+  std::vector<int> order(C);
+  for (int c = 0; c < C; ++c) order[c] = c;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    if (h_meta[a].root != h_meta[b].root) return h_meta[a].root < h_meta[b].root;
+    return h_meta[a].path < h_meta[b].path;
+  });
+  std::vector<int> rank(C);
+  for (int i = 0; i < C; ++i) rank[order[i]] = i;
+
+  f->h_cell_off.assign(C + 1, 0);
+  f->h_filt_off.assign(C + 1, 0);
+  for (int k = 0; k < K; ++k) {
+    f->h_cell_off[rank[h_cl[k]] + 1]++;
+    if (h_leaf[k] >= 0) f->h_filt_off[rank[h_cl[k]] + 1]++;
+  }
+  for (int c = 0; c < C; ++c) {
+    f->h_cell_off[c + 1] += f->h_cell_off[c];
+    f->h_filt_off[c + 1] += f->h_filt_off[c];
+  }
+  f->h_cell_addr.resize(K);
+  const int NF = f->h_filt_off[C];
+  std::vector<std::pair<int, int>> filt_keys(NF);  // (leaf, kept index) per slot
+  {
+    std::vector<int> cur(f->h_cell_off.begin(), f->h_cell_off.end() - 1);
+    std::vector<int> curf(f->h_filt_off.begin(), f->h_filt_off.end() - 1);
+    for (int k = 0; k < K; ++k) {  // k ascending = address ascending (stable)
+      const int r = rank[h_cl[k]];
+      f->h_cell_addr[cur[r]++] = h_addr[k];
+      if (h_leaf[k] >= 0) filt_keys[curf[r]++] = std::make_pair(h_leaf[k], k);
+    }
+  }
+  f->h_filtered.resize((size_t)3 * NF);
+  for (int c = 0; c < C; ++c) {
+    // VoxelGrid emits centroids in ascending leaf index
+    std::sort(filt_keys.begin() + f->h_filt_off[c], filt_keys.begin() + f->h_filt_off[c + 1]);
+    for (int i = f->h_filt_off[c]; i < f->h_filt_off[c + 1]; ++i) {
+      const int k = filt_keys[i].second;
+      for (int a = 0; a < 3; ++a) f->h_filtered[(size_t)3 * i + a] = (double)h_cent[(size_t)3 * k + a];
+    }
+  }
+  f->h_avg.resize((size_t)3 * C);
+  f->h_bmin.resize((size_t)3 * C);
+  f->h_bmax.resize((size_t)3 * C);
+  for (int c = 0; c < C; ++c) {
+    const int r = rank[c];
+    for (int a = 0; a < 3; ++a) {
+      f->h_avg[(size_t)3 * r + a] = h_meta[c].mean[a];
+      f->h_bmin[(size_t)3 * r + a] = (h_stat[c].lo[a] + 0.5) * g.res + g.origin[a];
+      f->h_bmax[(size_t)3 * r + a] = (h_stat[c].hi[a] + 0.5) * g.res + g.origin[a];
+    }
+  }
+  *n_clusters = C;
+  *n_cells = K;
+  *n_filtered = NF;
+  return 0;
+}
+
+int frontier_fetch_impl(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr, int32_t* filt_offsets,
+                        double* filtered, double* average, double* box_min, double* box_max) {
+  FrontierState* f = m->fs;
+  if (cell_offsets) memcpy(cell_offsets, f->h_cell_off.data(), sizeof(int32_t) * f->h_cell_off.size());
+  if (cell_addr) memcpy(cell_addr, f->h_cell_addr.data(), sizeof(int32_t) * f->h_cell_addr.size());
+  if (filt_offsets) memcpy(filt_offsets, f->h_filt_off.data(), sizeof(int32_t) * f->h_filt_off.size());
+  if (filtered) memcpy(filtered, f->h_filtered.data(), sizeof(double) * f->h_filtered.size());
+  if (average) memcpy(average, f->h_avg.data(), sizeof(double) * f->h_avg.size());
+  if (box_min) memcpy(box_min, f->h_bmin.data(), sizeof(double) * f->h_bmin.size());
+  if (box_max) memcpy(box_max, f->h_bmax.data(), sizeof(double) * f->h_bmax.size());
+  return 0;
+}
+
+int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const int32_t* addr,
+                             uint8_t* changed) {
+  if (mcl <= 0) return 0;
+  const int ncell = offs[mcl];
+  int *d_off = nullptr, *d_addr = nullptr;
+  uint8_t* d_ch = nullptr;
+  FUEL_CUDA(m, cudaMalloc(&d_off, sizeof(int) * (mcl + 1)));
+  FUEL_CUDA(m, cudaMalloc(&d_addr, sizeof(int) * (ncell > 0 ? ncell : 1)));
+  FUEL_CUDA(m, cudaMalloc(&d_ch, mcl));
+  cudaStream_t s = m->stream;
+  FUEL_CUDA(m, cudaMemcpyAsync(d_off, offs, sizeof(int) * (mcl + 1), cudaMemcpyHostToDevice, s));
+  if (ncell > 0) FUEL_CUDA(m, cudaMemcpyAsync(d_addr, addr, sizeof(int) * ncell, cudaMemcpyHostToDevice, s));
+  is_changed_kernel<<<mcl, 128, 0, s>>>(m->g, m->occ, d_off, d_addr, d_ch, mcl);
+  FUEL_CUDA(m, cudaMemcpyAsync(changed, d_ch, mcl, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaStreamSynchronize(s));
+  cudaFree(d_off);
+  cudaFree(d_addr);
+  cudaFree(d_ch);
+  return 0;
+}

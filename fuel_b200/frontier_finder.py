@@ -1,0 +1,160 @@
+"""Host-side mirror of fast_planner::FrontierFinder's hot path over the C ABI.
+
+Mirrors active_perception/include/active_perception/frontier_finder.h:25-133 and
+active_perception/src/frontier_finder.cpp:23-121 (file:line under /root/reference/fuel_planner/):
+`searchFrontiers()` with the stored-frontier bookkeeping (haveOverlap :353-363,
+isFrontierChanged :365-372, removed_ids_) on the host and every voxel-scale step in
+libfuelgpu.  Viewpoint sampling / cost matrix (computeFrontiersToVisit etc.) are outside
+the hot path and not mirrored.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import FuelFrontierParams, check, lib, ptr
+
+
+class Frontier:
+    """frontier_finder.h:34-51"""
+    __slots__ = ("cells_addr_", "filtered_cells_", "average_", "id_", "box_min_", "box_max_", "_map")
+
+    def __init__(self, m, addr, filtered, average, box_min, box_max):
+        self._map = m
+        self.cells_addr_ = addr
+        self.filtered_cells_ = filtered
+        self.average_ = average
+        self.box_min_ = box_min
+        self.box_max_ = box_max
+        self.id_ = -1
+
+    @property
+    def cells_(self):
+        """voxel-centre positions (indexToPos of every cell), [n,3] float64"""
+        m = self._map
+        a = self.cells_addr_.astype(np.int64)
+        nyz = m.shape[1] * m.shape[2]
+        idx = np.stack([a // nyz, (a % nyz) // m.shape[2], a % m.shape[2]], axis=1)
+        return (idx + 0.5) * m.resolution_ + m.map_origin_
+
+
+class FrontierFinder:
+    def __init__(self, edt, cluster_min=100, cluster_size_xy=2.0, down_sample=3, min_z=0.4):
+        """frontier_finder.cpp:23-49; defaults = exploration_manager/launch/algorithm.xml:103-114."""
+        self.edt_env_ = edt
+        self.cluster_min_ = int(cluster_min)
+        self.cluster_size_xy_ = float(cluster_size_xy)
+        self.down_sample_ = int(down_sample)
+        self.min_z_ = float(min_z)
+        self.frontiers_ = []
+        self.dormant_frontiers_ = []
+        self.tmp_frontiers_ = []
+        self.removed_ids_ = []
+
+    @property
+    def _map(self):
+        return self.edt_env_.sdf_map_
+
+    def _params(self):
+        p = FuelFrontierParams()
+        p.cluster_min, p.cluster_size_xy, p.down_sample, p.min_z = (
+            self.cluster_min_, self.cluster_size_xy_, self.down_sample_, self.min_z_)
+        return p
+
+    @staticmethod
+    def haveOverlap(min1, max1, min2, max2):
+        """frontier_finder.cpp:353-363"""
+        for i in range(3):
+            bmin = max(min1[i], min2[i])
+            bmax = min(max1[i], max2[i])
+            if bmin > bmax + 1e-3:
+                return False
+        return True
+
+    def _changed(self, ftrs):
+        """isFrontierChanged (:365-372) for a list of stored frontiers, on the device."""
+        if not ftrs:
+            return np.zeros(0, dtype=np.uint8)
+        offs = np.zeros(len(ftrs) + 1, dtype=np.int32)
+        for i, f in enumerate(ftrs):
+            offs[i + 1] = offs[i] + f.cells_addr_.size
+        addr = np.ascontiguousarray(np.concatenate([f.cells_addr_ for f in ftrs]).astype(np.int32))
+        changed = np.zeros(len(ftrs), dtype=np.uint8)
+        h = self._map.handle
+        check(lib().fuelgpu_frontier_is_changed(h, len(ftrs), ptr(offs), ptr(addr), ptr(changed)), h)
+        return changed
+
+    def _remove_changed(self, ftrs, update_min, update_max, record_ids):
+        cand = [i for i, f in enumerate(ftrs)
+                if self.haveOverlap(f.box_min_, f.box_max_, update_min, update_max)]
+        changed = self._changed([ftrs[i] for i in cand])
+        drop = {cand[j] for j in range(len(cand)) if changed[j]}
+        if drop:
+            addr = np.ascontiguousarray(
+                np.concatenate([ftrs[i].cells_addr_ for i in sorted(drop)]).astype(np.int32))
+            h = self._map.handle
+            check(lib().fuelgpu_frontier_clear_flags(h, addr.size, ptr(addr)), h)  # resetFlag :62-69
+        kept = []
+        rmv_idx = 0
+        for i, f in enumerate(ftrs):
+            if i in drop:
+                if record_ids:
+                    self.removed_ids_.append(rmv_idx)  # :75-84
+            else:
+                rmv_idx += 1
+                kept.append(f)
+        return kept
+
+    def searchFrontiers(self):
+        """frontier_finder.cpp:54-121"""
+        m = self._map
+        self.tmp_frontiers_ = []
+        update_min, update_max = m.getUpdatedBox(True)
+        self.removed_ids_ = []
+        self.frontiers_ = self._remove_changed(self.frontiers_, update_min, update_max, True)
+        self.dormant_frontiers_ = self._remove_changed(self.dormant_frontiers_, update_min, update_max, False)
+        self.tmp_frontiers_ = self.search_box(update_min, update_max)
+        return self.tmp_frontiers_
+
+    def search_box(self, update_min, update_max):
+        """The sweep + expandFrontier + splitLargeFrontiers part (:94-118) for a given updated box."""
+        m = self._map
+        h = m.handle
+        umin = np.ascontiguousarray(update_min, dtype=np.float64)
+        umax = np.ascontiguousarray(update_max, dtype=np.float64)
+        p = self._params()
+        nc, ncell, nf = C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib().fuelgpu_frontier_search(h, ptr(umin), ptr(umax), C.byref(p), C.byref(nc), C.byref(ncell),
+                                            C.byref(nf)), h)
+        nc, ncell, nf = nc.value, ncell.value, nf.value
+        offs = np.zeros(nc + 1, dtype=np.int32)
+        addr = np.zeros(ncell, dtype=np.int32)
+        foffs = np.zeros(nc + 1, dtype=np.int32)
+        filt = np.zeros((nf, 3), dtype=np.float64)
+        avg = np.zeros((nc, 3), dtype=np.float64)
+        bmin = np.zeros((nc, 3), dtype=np.float64)
+        bmax = np.zeros((nc, 3), dtype=np.float64)
+        check(lib().fuelgpu_frontier_fetch(h, ptr(offs), ptr(addr), ptr(foffs), ptr(filt), ptr(avg), ptr(bmin),
+                                           ptr(bmax)), h)
+        return [Frontier(m, addr[offs[i]:offs[i + 1]].copy(), filt[foffs[i]:foffs[i + 1]].copy(), avg[i].copy(),
+                         bmin[i].copy(), bmax[i].copy()) for i in range(nc)]
+
+    def getFrontiers(self):
+        return [f.cells_ for f in self.frontiers_]
+
+    def getDormantFrontiers(self):
+        return [f.cells_ for f in self.dormant_frontiers_]
+
+    def getFrontierBoxes(self):
+        """frontier_finder.cpp getFrontierBoxes: (centre, scale) per stored frontier"""
+        return [((f.box_max_ + f.box_min_) / 2, f.box_max_ - f.box_min_) for f in self.frontiers_]
+
+    def download_flags(self):
+        m = self._map
+        out = np.zeros(m.shape, dtype=np.int8)
+        check(lib().fuelgpu_frontier_download_flags(m.handle, ptr(out)), m.handle)
+        return out
+
+    def upload_flags(self, flags):
+        m = self._map
+        f = np.ascontiguousarray(flags, dtype=np.int8).reshape(m.shape)
+        check(lib().fuelgpu_frontier_upload_flags(m.handle, ptr(f)), m.handle)

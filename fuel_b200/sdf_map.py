@@ -1,0 +1,258 @@
+"""Host-side mirror of fast_planner::SDFMap and EDTEnvironment over the C ABI.
+
+Same method names, argument meaning and sentinel behaviour as
+plan_env/include/plan_env/sdf_map.h:27-84 and plan_env/include/plan_env/edt_environment.h:21-51
+(file:line under /root/reference/fuel_planner/).  All voxel-scale work runs in libfuelgpu
+(hand-written sm_100a CUDA); this class owns the host copies the reference's random
+single-point readers need (occupancy bytes, and the ESDF after `download()`).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import FuelGridDesc, check, lib, ptr
+
+
+def logit(p):
+    return math.log(p / (1 - p))  # sdf_map.cpp:50
+
+
+class SDFMap:
+    UNKNOWN, FREE, OCCUPIED = 0, 1, 2  # sdf_map.h:32
+
+    def __init__(self, voxel_num, resolution, origin, box_min=None, box_max=None, optimistic=False,
+                 signed_dist=False, p_min=0.12, p_occ=0.80, default_dist=0.0, device=0):
+        """initMap (sdf_map.cpp:12-93) with the ROS parameters passed explicitly.
+
+        voxel_num = map_voxel_num_, origin = map_origin_, box_min/box_max = box_mind_/box_maxd_
+        in metres (default: the whole map, sdf_map.cpp:79-82)."""
+        self.map_voxel_num_ = np.asarray(voxel_num, dtype=np.int32)
+        self.resolution_ = float(resolution)
+        self.resolution_inv_ = 1 / self.resolution_
+        self.map_origin_ = np.asarray(origin, dtype=np.float64)
+        self.map_min_boundary_ = self.map_origin_.copy()
+        self.map_max_boundary_ = self.map_origin_ + self.map_voxel_num_ * self.resolution_
+        self.box_mind_ = np.asarray(self.map_min_boundary_ if box_min is None else box_min, dtype=np.float64)
+        self.box_maxd_ = np.asarray(self.map_max_boundary_ if box_max is None else box_max, dtype=np.float64)
+        self.box_min_ = self.posToIndex(self.box_mind_)
+        self.box_max_ = self.posToIndex(self.box_maxd_)
+        self.optimistic_ = bool(optimistic)
+        self.signed_dist_ = bool(signed_dist)
+        self.clamp_min_log_ = logit(p_min)
+        self.min_occupancy_log_ = logit(p_occ)
+        self.default_dist_ = float(default_dist)
+        shape = tuple(int(v) for v in self.map_voxel_num_)
+        self.shape = shape
+        # host mirrors of MapData (sdf_map.h:107-125)
+        self.occupancy_buffer_inflate_ = np.zeros(shape, dtype=np.int8)
+        self.occupancy_tri_ = np.zeros(shape, dtype=np.uint8)  # getOccupancy() of occupancy_buffer_
+        self.distance_buffer_ = None  # filled by download()
+        self.local_bound_min_ = np.zeros(3, dtype=np.int32)
+        self.local_bound_max_ = self.map_voxel_num_ - 1
+        self.update_min_ = np.zeros(3)
+        self.update_max_ = np.zeros(3)
+        self.reset_updated_box_ = True
+
+        d = FuelGridDesc()
+        for i in range(3):
+            d.n[i] = shape[i]
+            d.origin[i] = self.map_origin_[i]
+            d.box_mind[i] = self.box_mind_[i]
+            d.box_maxd[i] = self.box_maxd_[i]
+        d.resolution = self.resolution_
+        self._desc = d
+        h = C.c_void_p()
+        check(lib().fuelgpu_map_create(C.byref(d), int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    # ---- lifetime -------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fuelgpu_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream):
+        check(lib().fuelgpu_map_set_stream(self._h, C.c_void_p(cuda_stream)), self._h)
+
+    def synchronize(self):
+        check(lib().fuelgpu_map_synchronize(self._h), self._h)
+
+    def last_timing(self):
+        ms = (C.c_float * 8)()
+        check(lib().fuelgpu_map_last_timing(self._h, ms), self._h)
+        return dict(esdf=ms[0], frontier=ms[1], bspline=ms[2], upload=ms[3], download=ms[4])
+
+    def device_ptrs(self):
+        occ, dist, flag = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().fuelgpu_map_device_ptrs(self._h, C.byref(occ), C.byref(dist), C.byref(flag)), self._h)
+        return occ.value, dist.value, flag.value
+
+    # ---- index helpers (sdf_map.h:127-192) ---------------------------------------------
+    def posToIndex(self, pos):
+        return np.floor((np.asarray(pos, dtype=np.float64) - self.map_origin_) *
+                        self.resolution_inv_).astype(np.int32)
+
+    def indexToPos(self, idx):
+        return (np.asarray(idx) + 0.5) * self.resolution_ + self.map_origin_
+
+    def boundIndex(self, idx):
+        return np.maximum(np.minimum(np.asarray(idx), self.map_voxel_num_ - 1), 0).astype(np.int32)
+
+    def toAddress(self, idx):
+        idx = np.asarray(idx)
+        return (idx[..., 0] * self.shape[1] + idx[..., 1]) * self.shape[2] + idx[..., 2]
+
+    def isInMap(self, p):
+        p = np.asarray(p)
+        if p.dtype.kind == "f":
+            return bool(np.all(p >= self.map_min_boundary_ + 1e-4) and np.all(p <= self.map_max_boundary_ - 1e-4))
+        return bool(np.all(p >= 0) and np.all(p <= self.map_voxel_num_ - 1))
+
+    def isInBox(self, p):
+        p = np.asarray(p)
+        if p.dtype.kind == "f":
+            return bool(np.all(p > self.box_mind_) and np.all(p < self.box_maxd_))
+        return bool(np.all(p >= self.box_min_) and np.all(p < self.box_max_))
+
+    def boundBox(self, low, up):
+        return np.maximum(low, self.box_mind_), np.minimum(up, self.box_maxd_)
+
+    def getResolution(self):
+        return self.resolution_
+
+    def getVoxelNum(self):
+        return int(np.prod(self.map_voxel_num_))
+
+    def getRegion(self):
+        return self.map_origin_.copy(), self.map_voxel_num_ * self.resolution_
+
+    def getBox(self):
+        return self.box_mind_.copy(), self.box_maxd_.copy()
+
+    def getUpdatedBox(self, reset=False):
+        bmin, bmax = self.update_min_.copy(), self.update_max_.copy()
+        if reset:
+            self.reset_updated_box_ = True
+        return bmin, bmax
+
+    # ---- occupancy (host mirrors; offline recipe of plan_manage/test/compare_topo.cpp:122-133) --
+    def resetBuffer(self):
+        self.occupancy_buffer_inflate_[...] = 0  # sdf_map.cpp:95-114
+        self.local_bound_min_ = np.zeros(3, dtype=np.int32)
+        self.local_bound_max_ = (self.map_voxel_num_ - 1).astype(np.int32)
+
+    def setOccupied(self, pos, occ=1):
+        """sdf_map.h:210-215, vectorised over [n,3] positions."""
+        pos = np.asarray(pos, dtype=np.float64).reshape(-1, 3)
+        ok = np.all(pos >= self.map_min_boundary_ + 1e-4, axis=1) & np.all(
+            pos <= self.map_max_boundary_ - 1e-4, axis=1)
+        idx = self.posToIndex(pos[ok])
+        self.occupancy_buffer_inflate_[idx[:, 0], idx[:, 1], idx[:, 2]] = occ
+
+    def setOccupancyBuffer(self, logodds=None, tristate=None):
+        """Set occupancy_buffer_ either as log-odds (thresholded like getOccupancy,
+        sdf_map.h:194-200) or directly as its tri-state."""
+        if (logodds is None) == (tristate is None):
+            raise ValueError("give exactly one of logodds / tristate")
+        if tristate is not None:
+            self.occupancy_tri_[...] = np.asarray(tristate, dtype=np.uint8).reshape(self.shape)
+        else:
+            lo = np.asarray(logodds, dtype=np.float64).reshape(self.shape)
+            t = np.full(self.shape, self.FREE, dtype=np.uint8)
+            t[lo < self.clamp_min_log_ - 1e-3] = self.UNKNOWN
+            t[lo > self.min_occupancy_log_] = self.OCCUPIED
+            self.occupancy_tri_[...] = t
+
+    def getOccupancy(self, p):
+        idx = self.posToIndex(p) if np.asarray(p).dtype.kind == "f" else np.asarray(p)
+        if not self.isInMap(idx.astype(np.int64)):
+            return -1
+        return int(self.occupancy_tri_[idx[0], idx[1], idx[2]])
+
+    def getInflateOccupancy(self, p):
+        idx = self.posToIndex(p) if np.asarray(p).dtype.kind == "f" else np.asarray(p)
+        if not self.isInMap(idx.astype(np.int64)):
+            return -1
+        return int(self.occupancy_buffer_inflate_[idx[0], idx[1], idx[2]])
+
+    def upload(self, bmin=None, bmax=None, logodds=None):
+        """H2D of the occupancy state.  With `logodds` the device thresholds the fp64 buffer
+        itself (9 B/voxel ingest); otherwise the host tri-state byte is sent (2 B/voxel)."""
+        bmin_a = None if bmin is None else np.ascontiguousarray(bmin, dtype=np.int32)
+        bmax_a = None if bmax is None else np.ascontiguousarray(bmax, dtype=np.int32)
+        inf = np.ascontiguousarray(self.occupancy_buffer_inflate_)
+        if logodds is not None:
+            lo = np.ascontiguousarray(logodds, dtype=np.float64)
+            check(lib().fuelgpu_map_upload_occupancy(self._h, ptr(inf), ptr(lo), None, self.clamp_min_log_,
+                                                     self.min_occupancy_log_, ptr(bmin_a), ptr(bmax_a)), self._h)
+        else:
+            tri = np.ascontiguousarray(self.occupancy_tri_)
+            check(lib().fuelgpu_map_upload_occupancy(self._h, ptr(inf), None, ptr(tri), self.clamp_min_log_,
+                                                     self.min_occupancy_log_, ptr(bmin_a), ptr(bmax_a)), self._h)
+
+    # ---- ESDF ------------------------------------------------------------------------------
+    def updateESDF3d(self):
+        """sdf_map.cpp:152-241 over [local_bound_min_, local_bound_max_]."""
+        flags = (_lib.ESDF_OPTIMISTIC if self.optimistic_ else 0) | (_lib.ESDF_SIGNED if self.signed_dist_ else 0)
+        bmin = np.ascontiguousarray(self.local_bound_min_, dtype=np.int32)
+        bmax = np.ascontiguousarray(self.local_bound_max_, dtype=np.int32)
+        check(lib().fuelgpu_esdf_update(self._h, ptr(bmin), ptr(bmax), flags), self._h)
+
+    def download(self, bmin=None, bmax=None, dtype=np.float32):
+        """Mirror distance_buffer_ to the host for getDistance()."""
+        if self.distance_buffer_ is None or self.distance_buffer_.dtype != dtype:
+            self.distance_buffer_ = np.full(self.shape, self.default_dist_, dtype=dtype)
+        bmin_a = None if bmin is None else np.ascontiguousarray(bmin, dtype=np.int32)
+        bmax_a = None if bmax is None else np.ascontiguousarray(bmax, dtype=np.int32)
+        if dtype == np.float32:
+            check(lib().fuelgpu_esdf_download(self._h, ptr(bmin_a), ptr(bmax_a), ptr(self.distance_buffer_), None), self._h)
+        else:
+            check(lib().fuelgpu_esdf_download(self._h, ptr(bmin_a), ptr(bmax_a), None, ptr(self.distance_buffer_)), self._h)
+        return self.distance_buffer_
+
+    def getDistance(self, p):
+        """sdf_map.h:228-237 on the host mirror (call download() after updateESDF3d)."""
+        idx = self.posToIndex(p) if np.asarray(p).dtype.kind == "f" else np.asarray(p)
+        if not self.isInMap(idx.astype(np.int64)):
+            return -1.0
+        return float(self.distance_buffer_[idx[0], idx[1], idx[2]])
+
+    def getDistWithGrad(self, pos):
+        """sdf_map.cpp:497-536 for [n,3] positions, evaluated on the device ESDF."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        n = pos.shape[0]
+        d = np.empty(n, dtype=np.float64)
+        g = np.empty((n, 3), dtype=np.float64)
+        check(lib().fuelgpu_esdf_sample(self._h, n, ptr(pos), ptr(d), ptr(g)), self._h)
+        return d, g
+
+
+class EDTEnvironment:
+    """edt_environment.h:21-51: the facade every consumer reaches the map through."""
+
+    def __init__(self):
+        self.sdf_map_ = None
+
+    def setMap(self, sdf_map):
+        self.sdf_map_ = sdf_map
+        self.resolution_inv_ = 1 / sdf_map.getResolution()
+
+    def evaluateEDTWithGrad(self, pos, time=-1.0):
+        """edt_environment.cpp:78-87 -- pure pass-through to getDistWithGrad (`time` unused)."""
+        return self.sdf_map_.getDistWithGrad(pos)
+
+    def evaluateCoarseEDT(self, pos, time=-1.0):
+        return self.sdf_map_.getDistance(np.asarray(pos, dtype=np.float64))

@@ -1,0 +1,226 @@
+/*
+ * fuelgpu.h -- C ABI of the B200-native replacement for FUEL's per-replan hot path.
+ *
+ * The reference (HKUST-Aerial-Robotics/FUEL) exposes no C ABI or plugin interface: its
+ * boundary is the public C++ surface of SDFMap / EDTEnvironment / FrontierFinder /
+ * BsplineOptimizer linked through catkin shared libraries.  Every entry
+ * point below cites the reference method (file:line under fuel_planner/) whose body it
+ * replaces; INTEGRATION.md shows the C++ shim a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns 0 on success, a negative FUELGPU_E* code otherwise;
+ *     fuelgpu_last_error() gives the message (per handle; NULL handle = creation errors).
+ *   - host buffers are caller-owned.  Volume buffers use the reference layout
+ *     address = x*ny*nz + y*nz + z (SDFMap::toAddress, plan_env/include/plan_env/sdf_map.h:145-147).
+ *   - one opaque handle per map; all device state (occupancy byte, ESDF, frontier flags,
+ *     scratch) lives in HBM behind it.  Calls on one handle are serialised on its stream
+ *     (the reference is single-threaded for these, exploration_node.cpp:19);
+ *     fuelgpu_bspline_* calls are re-entrant across handles.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     FUELGPU_ENODEVICE.
+ */
+#ifndef FUELGPU_H
+#define FUELGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FUELGPU_API __attribute__((visibility("default")))
+#else
+#define FUELGPU_API
+#endif
+
+#define FUELGPU_OK 0
+#define FUELGPU_EINVAL -1    /* bad argument                                  */
+#define FUELGPU_ENODEVICE -2 /* no CUDA device / wrong architecture          */
+#define FUELGPU_ECUDA -3     /* CUDA runtime error (see fuelgpu_last_error)  */
+#define FUELGPU_ENOMEM -4    /* device or host allocation failed             */
+#define FUELGPU_EUNSUPPORTED -5
+
+typedef struct FuelMap FuelMap;
+
+/* Grid geometry = the fields of MapParam that the hot path reads
+ * (plan_env/include/plan_env/sdf_map.h:86-105; filled by SDFMap::initMap, sdf_map.cpp:12-93). */
+typedef struct {
+  int32_t n[3];       /* map_voxel_num_                      */
+  double resolution;  /* resolution_                         */
+  double origin[3];   /* map_origin_ (= map_min_boundary_)   */
+  double box_mind[3]; /* box_mind_  exploration box, metres  */
+  double box_maxd[3]; /* box_maxd_                           */
+} FuelGridDesc;
+
+/* Occupancy tri-state of SDFMap::getOccupancy (sdf_map.h:32,194-200). */
+enum { FUELGPU_UNKNOWN = 0, FUELGPU_FREE = 1, FUELGPU_OCCUPIED = 2 };
+
+/* ---- lifetime --------------------------------------------------------------------- */
+/* Replaces the allocations of SDFMap::initMap (sdf_map.cpp:62-76) and the frontier_flag_
+ * allocation of FrontierFinder::FrontierFinder (active_perception/src/frontier_finder.cpp:23-27). */
+FUELGPU_API int fuelgpu_map_create(const FuelGridDesc* grid, int device_id, FuelMap** out);
+FUELGPU_API int fuelgpu_map_destroy(FuelMap* map);
+FUELGPU_API const char* fuelgpu_last_error(const FuelMap* map);
+/* Run all work of this handle on `cuda_stream` (a cudaStream_t; NULL = the handle's own). */
+FUELGPU_API int fuelgpu_map_set_stream(FuelMap* map, void* cuda_stream);
+FUELGPU_API int fuelgpu_map_synchronize(FuelMap* map);
+/* Device pointers of the resident state, for zero-copy callers (torch tensors, NCCL):
+ * occ  = uint8 per voxel: bits0-1 tri-state, bit2 occupancy_buffer_inflate_
+ * dist = float32 per voxel: distance_buffer_ in metres
+ * flag = int8 per voxel: frontier_flag_ */
+FUELGPU_API int fuelgpu_map_device_ptrs(FuelMap* map, void** occ, void** dist, void** flag);
+/* Milliseconds spent on the device by the last call of each stage (CUDA events on the
+ * handle's stream): [0] esdf_update [1] frontier_search [2] bspline batch [3] upload [4] download */
+FUELGPU_API int fuelgpu_map_last_timing(FuelMap* map, float ms[8]);
+
+/* ---- ingest: host occupancy -> resident occupancy byte ------------------------------
+ * Replaces nothing in the reference (its buffers are already in RAM); this is the H2D leg.
+ * inflate  : occupancy_buffer_inflate_ (char {0,1}), full volume                (sdf_map.h:110)
+ * logodds  : occupancy_buffer_ (double log-odds), full volume, or NULL          (sdf_map.h:109)
+ * tristate : precomputed getOccupancy() per voxel, or NULL.  Exactly one of logodds /
+ *            tristate must be given.  With logodds the device applies sdf_map.h:196-199:
+ *            occ < clamp_min_log-1e-3 -> UNKNOWN, occ > min_occupancy_log -> OCCUPIED.
+ * bmin/bmax: inclusive index box to refresh (NULL = whole map).  The x-slab range
+ *            [bmin[0],bmax[0]] is copied (x is the slowest axis, so that is contiguous). */
+FUELGPU_API int fuelgpu_map_upload_occupancy(FuelMap* map, const int8_t* inflate, const double* logodds,
+                                 const uint8_t* tristate, double clamp_min_log,
+                                 double min_occupancy_log, const int32_t bmin[3],
+                                 const int32_t bmax[3]);
+
+/* ---- ESDF -------------------------------------------------------------------------- */
+#define FUELGPU_ESDF_OPTIMISTIC 1 /* mp_->optimistic_  (sdf_map.cpp:156) */
+#define FUELGPU_ESDF_SIGNED 2     /* mp_->signed_dist_ (sdf_map.cpp:201) */
+/* Replaces SDFMap::updateESDF3d (plan_env/src/sdf_map.cpp:152-241) incl. fillESDF (:116-150).
+ * bmin/bmax = md_->local_bound_min_/max_ (inclusive).  Result: distance_buffer_ inside the
+ * box, float32 metres.  A voxel with no site anywhere in the box gets +inf (the reference
+ * stores resolution*sqrt(DBL_MAX) ~ 1.34e153 there; see DESIGN.md "sentinel"). */
+FUELGPU_API int fuelgpu_esdf_update(FuelMap* map, const int32_t bmin[3], const int32_t bmax[3], int flags);
+/* distance_buffer_ -> host, for the scattered single-point CPU readers of
+ * SDFMap::getDistance (sdf_map.h:228-237).  Exactly one of out_f32/out_f64 non-NULL; full
+ * volume layout; the x-slab range of the box is copied. */
+FUELGPU_API int fuelgpu_esdf_download(FuelMap* map, const int32_t bmin[3], const int32_t bmax[3],
+                          float* out_f32, double* out_f64);
+/* Replaces SDFMap::getDistWithGrad (sdf_map.cpp:497-536) = EDTEnvironment::evaluateEDTWithGrad
+ * (plan_env/src/edt_environment.cpp:78-87) for n positions.  pos [n][3], dist [n], grad [n][3]. */
+FUELGPU_API int fuelgpu_esdf_sample(FuelMap* map, int64_t n, const double* pos, double* dist, double* grad);
+
+/* ---- frontier ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t cluster_min;    /* frontier/cluster_min     frontier_finder.cpp:29 */
+  double cluster_size_xy; /* frontier/cluster_size_xy frontier_finder.cpp:30 */
+  int32_t down_sample;    /* frontier/down_sample     frontier_finder.cpp:38 */
+  double min_z;           /* the literal 0.4 of frontier_finder.cpp:152      */
+} FuelFrontierParams;
+
+/* Replaces the voxel-scale part of FrontierFinder::searchFrontiers
+ * (active_perception/src/frontier_finder.cpp:94-118): the sweep over the inflated updated
+ * box, expandFrontier (:123-164), computeFrontierInfo (:374-390), downsample (:757-774)
+ * and splitLargeFrontiers / splitHorizontally (:166-242).  upd_min/upd_max = the box
+ * returned by SDFMap::getUpdatedBox (metres).  frontier_flag_ stays on the device and is
+ * updated exactly as the reference does (cells of dropped small clusters stay flagged).
+ * Outputs the sizes needed for fuelgpu_frontier_fetch.  Clusters come in tmp_frontiers_
+ * order; cells of a cluster in ascending address order (DESIGN.md "frontier cell order"). */
+FUELGPU_API int fuelgpu_frontier_search(FuelMap* map, const double upd_min[3], const double upd_max[3],
+                            const FuelFrontierParams* params, int32_t* n_clusters,
+                            int32_t* n_cells, int32_t* n_filtered);
+/* cell_offsets [n_clusters+1], cell_addr [n_cells] (toAddress), filt_offsets [n_clusters+1],
+ * filtered [n_filtered][3] (Frontier::filtered_cells_), average/box_min/box_max [n_clusters][3]
+ * (Frontier::average_/box_min_/box_max_, frontier_finder.h:34-51).  Any pointer may be NULL. */
+FUELGPU_API int fuelgpu_frontier_fetch(FuelMap* map, int32_t* cell_offsets, int32_t* cell_addr,
+                           int32_t* filt_offsets, double* filtered, double* average,
+                           double* box_min, double* box_max);
+/* Replaces the resetFlag lambda of searchFrontiers (:62-69): frontier_flag_[addr] = 0. */
+FUELGPU_API int fuelgpu_frontier_clear_flags(FuelMap* map, int32_t n, const int32_t* addr);
+/* Replaces FrontierFinder::isFrontierChanged (:365-372) for m stored clusters given in CSR
+ * form; changed[i] = 1 iff some cell of cluster i stopped being a frontier cell. */
+FUELGPU_API int fuelgpu_frontier_is_changed(FuelMap* map, int32_t m, const int32_t* cell_offsets,
+                                const int32_t* cell_addr, uint8_t* changed);
+FUELGPU_API int fuelgpu_frontier_download_flags(FuelMap* map, int8_t* out);
+FUELGPU_API int fuelgpu_frontier_upload_flags(FuelMap* map, const int8_t* in);
+
+/* ---- B-spline cost ------------------------------------------------------------------ */
+/* cost-term bits = BsplineOptimizer::SMOOTHNESS..MINTIME (bspline_opt/src/bspline_optimizer.cpp:10-18) */
+#define FUELGPU_SMOOTHNESS (1 << 0)
+#define FUELGPU_DISTANCE (1 << 1)
+#define FUELGPU_FEASIBILITY (1 << 2)
+#define FUELGPU_START (1 << 3)
+#define FUELGPU_END (1 << 4)
+#define FUELGPU_GUIDE (1 << 5)
+#define FUELGPU_WAYPOINTS (1 << 6)
+#define FUELGPU_VIEWCONS (1 << 7) /* rejected: ld_view is 0.0 in every launch file (algorithm.xml:177) */
+#define FUELGPU_MINTIME (1 << 8)
+
+/* BsplineOptimizer::setParam (bspline_optimizer.cpp:25-57) */
+typedef struct {
+  double ld_smooth, ld_dist, ld_feasi, ld_start, ld_end, ld_guide, ld_waypt, ld_view, ld_time;
+  double dist0, max_vel, max_acc;
+  int32_t order; /* order_ = bspline_degree_ */
+} FuelOptParams;
+
+#define FUELGPU_MAX_PTS 64
+/* per-trajectory constants frozen by BsplineOptimizer::optimize() before the solver runs
+ * (bspline_optimizer.cpp:116-141) plus the setters (:82-108) */
+typedef struct {
+  double pt_dist;     /* pt_dist_ (:136-140)                     */
+  double knot_span;   /* knot_span_, used when MINTIME is off    */
+  double start[3][3]; /* start_state_: pos, vel, acc             */
+  double end[3][3];   /* end_state_                               */
+  int32_t n_end;      /* end_state_.size(), 1..3                  */
+  double time_lb;     /* time_lb_                                 */
+  int32_t n_guide;    /* guide_pts_.size()                        */
+  double guide[FUELGPU_MAX_PTS][3];
+  int32_t n_waypt;    /* waypoints_.size()                        */
+  double waypt[FUELGPU_MAX_PTS][3];
+  int32_t waypt_idx[FUELGPU_MAX_PTS];
+} FuelTrajConst;
+
+/* Replaces BsplineOptimizer::combineCost (bspline_optimizer.cpp:518-647) and the calc*Cost
+ * it calls (:255-516) for B trajectories of n_pts control points (dim_ == 3) against this
+ * map's ESDF.  x [B][nvar], nvar = 3*n_pts (+1 = dt when MINTIME); f [B]; grad [B][nvar].
+ * B == 1 is the BsplineOptimizer::costFunction trampoline (:693-706). */
+FUELGPU_API int fuelgpu_bspline_cost_batch(FuelMap* map, int32_t B, int32_t n_pts, int32_t cost_mask,
+                               const FuelOptParams* params, const FuelTrajConst* traj,
+                               const double* x, double* f, double* grad);
+/* Same, all pointers in device memory (traj = device array of FuelTrajConst). */
+FUELGPU_API int fuelgpu_bspline_cost_batch_dev(FuelMap* map, int32_t B, int32_t n_pts, int32_t cost_mask,
+                                   const FuelOptParams* params, const void* traj_dev,
+                                   const void* x_dev, void* f_dev, void* grad_dev);
+
+/* Replaces the solver loop of BsplineOptimizer::optimize() (bspline_optimizer.cpp:165-253:
+ * clamp to box+-0.1, bounds, maxeval stop, best-x tracking of costFunction :693-706) for a
+ * whole batch on the device.  NLopt (third party, LD_LBFGS) is replaced by a projected
+ * L-BFGS run per trajectory inside one persistent kernel; iterate-level parity with NLopt
+ * is unpinned, the CPU twin is oracle/orc_optimize_batch.
+ * x [B][nvar] in/out (best_variable_), f_best [B], n_eval [B]. */
+typedef struct {
+  int32_t max_eval; /* max_iteration_num_[id]  (algorithm.xml:184-187) */
+  int32_t lbfgs_m;  /* history pairs, <= 8                              */
+  double xtol_rel;  /* 1e-5 (bspline_optimizer.cpp:173)                 */
+} FuelSolveParams;
+FUELGPU_API int fuelgpu_bspline_optimize_batch(FuelMap* map, int32_t B, int32_t n_pts, int32_t cost_mask,
+                                   const FuelOptParams* params, const FuelTrajConst* traj,
+                                   const FuelSolveParams* solve, double* x, double* f_best,
+                                   int32_t* n_eval);
+
+/* ---- multi-GPU building blocks (z-sharded ESDF, DESIGN.md "multi-GPU") --------------
+ * These operate on caller-owned DEVICE buffers so that torch.distributed/NCCL can move
+ * them between ranks.  A slab is nx*ny*nzl voxels, z fastest.
+ * xy passes: occupancy byte slab -> squared 2-D distance (int32, FUELGPU_EDT_INF = none)
+ * z pass   : G received chunks [G][nxl][ny][nzl] -> float32 metres [nxl][ny][G*nzl]       */
+#define FUELGPU_EDT_INF 0x3fffffff
+FUELGPU_API int fuelgpu_edt_xy_dev(void* cuda_stream, const void* occ_slab, int32_t nx, int32_t ny,
+                       int32_t nzl, int flags, void* g2_out_i32, void* scratch_i32);
+FUELGPU_API int fuelgpu_edt_z_chunks_dev(void* cuda_stream, const void* g2_chunks_i32, int32_t G, int32_t nxl,
+                             int32_t ny, int32_t nzl, double resolution, void* dist_out_f32,
+                             void* scratch_i32);
+
+/* Library / device info.  Fills name with the device name; returns the SM count or <0. */
+FUELGPU_API int fuelgpu_device_info(int device_id, char* name, int name_len, int* cc_major, int* cc_minor);
+FUELGPU_API const char* fuelgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUELGPU_H */

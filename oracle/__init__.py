@@ -1,0 +1,254 @@
+"""ctypes binding of the CPU oracle (oracle/fuel_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  fuel_b200/ must never import this package.
+PARITY UNPINNED by reference tests (the reference ships none for this path); see
+fuel_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfuel_oracle.so")
+
+ORC_MAX_PTS = 64
+
+UNKNOWN, FREE, OCCUPIED = 0, 1, 2
+SMOOTHNESS, DISTANCE, FEASIBILITY, START, END, GUIDE, WAYPOINTS, VIEWCONS, MINTIME = (
+    1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7, 1 << 8)
+NORMAL_PHASE = SMOOTHNESS | DISTANCE | FEASIBILITY | START | END
+GUIDE_PHASE = SMOOTHNESS | GUIDE | START | END
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc -O3, the reference's flags)."""
+    src = [os.path.join(_HERE, f) for f in ("fuel_oracle.c", "fuel_oracle.h", "Makefile")]
+    if (not force and os.path.exists(_SO)
+            and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src)):
+        return _SO
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+class OrcGrid(C.Structure):
+    _fields_ = [("n", C.c_int32 * 3), ("res", C.c_double), ("origin", C.c_double * 3),
+                ("box_mind", C.c_double * 3), ("box_maxd", C.c_double * 3)]
+
+
+class OrcFrontierParams(C.Structure):
+    _fields_ = [("cluster_min", C.c_int32), ("cluster_size_xy", C.c_double),
+                ("down_sample", C.c_int32), ("min_z", C.c_double), ("cell_order", C.c_int32)]
+
+
+class OrcOptParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in
+                ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide",
+                 "ld_waypt", "ld_view", "ld_time", "dist0", "max_vel", "max_acc")] + [
+                     ("order", C.c_int32)]
+
+
+class OrcTrajConst(C.Structure):
+    _fields_ = [("pt_dist", C.c_double), ("knot_span", C.c_double),
+                ("start", (C.c_double * 3) * 3), ("end", (C.c_double * 3) * 3),
+                ("n_end", C.c_int32), ("time_lb", C.c_double), ("n_guide", C.c_int32),
+                ("guide", (C.c_double * 3) * ORC_MAX_PTS), ("n_waypt", C.c_int32),
+                ("waypt", (C.c_double * 3) * ORC_MAX_PTS), ("waypt_idx", C.c_int32 * ORC_MAX_PTS)]
+
+
+class OrcSolveParams(C.Structure):
+    _fields_ = [("max_eval", C.c_int32), ("lbfgs_m", C.c_int32), ("xtol_rel", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_dist_with_grad.restype = C.c_double
+        _lib.orc_pt_dist.restype = C.c_double
+        _lib.orc_frontier_search.restype = C.c_void_p
+        for name in ("orc_frontier_count", "orc_frontier_num_cells", "orc_frontier_num_filtered",
+                     "orc_frontier_is_changed", "orc_is_frontier_cell", "orc_is_in_map_pos"):
+            getattr(_lib, name).restype = C.c_int32
+    return _lib
+
+
+def _p(a, ty=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_grid(n, res, origin, box_mind=None, box_maxd=None):
+    g = OrcGrid()
+    for i in range(3):
+        g.n[i] = int(n[i])
+        g.origin[i] = float(origin[i])
+    g.res = float(res)
+    if box_mind is None:
+        box_mind = [origin[i] for i in range(3)]
+    if box_maxd is None:
+        box_maxd = [origin[i] + n[i] * res for i in range(3)]
+    for i in range(3):
+        g.box_mind[i] = float(box_mind[i])
+        g.box_maxd[i] = float(box_maxd[i])
+    return g
+
+
+def pos_to_index(g, pos):
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    out = np.zeros(3, dtype=np.int32)
+    lib().orc_pos_to_index(C.byref(g), _p(pos), _p(out))
+    return out
+
+
+def tristate_from_logodds(logodds, clamp_min_log, min_occupancy_log):
+    logodds = np.ascontiguousarray(logodds, dtype=np.float64)
+    tri = np.empty(logodds.shape, dtype=np.uint8)
+    lib().orc_tristate_from_logodds(_p(logodds), C.c_int64(logodds.size), C.c_double(clamp_min_log),
+                                    C.c_double(min_occupancy_log), _p(tri))
+    return tri
+
+
+def update_esdf3d(g, inflate, tri, bmin, bmax, optimistic, signed_dist, dist=None, threads=1):
+    """updateESDF3d.  inflate int8 [nx,ny,nz]; tri uint8 or None.  Returns distance_buffer_
+    (float64 [nx,ny,nz]); voxels outside the box keep their previous value (`dist` in, or 0 =
+    sdf_map/default_dist of algorithm.xml:41)."""
+    shape = tuple(g.n)
+    inflate = np.ascontiguousarray(inflate, dtype=np.int8).reshape(shape)
+    if tri is not None:
+        tri = np.ascontiguousarray(tri, dtype=np.uint8).reshape(shape)
+    if dist is None:
+        dist = np.zeros(shape, dtype=np.float64)
+    else:
+        dist = np.ascontiguousarray(dist, dtype=np.float64).reshape(shape)
+    neg = np.zeros(shape, dtype=np.float64) if signed_dist else None
+    t1 = np.zeros(shape, dtype=np.float64)
+    t2 = np.zeros(shape, dtype=np.float64)
+    bmin = np.ascontiguousarray(bmin, dtype=np.int32)
+    bmax = np.ascontiguousarray(bmax, dtype=np.int32)
+    lib().orc_update_esdf3d(C.byref(g), _p(inflate), _p(tri), _p(bmin), _p(bmax),
+                            C.c_int(int(optimistic)), C.c_int(int(signed_dist)), _p(dist), _p(neg),
+                            _p(t1), _p(t2), C.c_int(threads))
+    return dist
+
+
+def dist_with_grad(g, dist_buf, pos):
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+    dist_buf = np.ascontiguousarray(dist_buf, dtype=np.float64)
+    d = np.empty(pos.shape[0], dtype=np.float64)
+    gr = np.empty((pos.shape[0], 3), dtype=np.float64)
+    lib().orc_dist_with_grad_batch(C.byref(g), _p(dist_buf), C.c_int64(pos.shape[0]), _p(pos), _p(d),
+                                   _p(gr))
+    return d, gr
+
+
+def frontier_params(cluster_min=100, cluster_size_xy=2.0, down_sample=3, min_z=0.4, cell_order=0):
+    p = OrcFrontierParams()
+    p.cluster_min, p.cluster_size_xy, p.down_sample, p.min_z, p.cell_order = (
+        cluster_min, cluster_size_xy, down_sample, min_z, cell_order)
+    return p
+
+
+def frontier_search(g, tri, flag, upd_min, upd_max, params):
+    """searchFrontiers core.  flag (int8, full volume) is updated in place.  Returns a list of
+    dicts {addr, filtered, average, box_min, box_max} in tmp_frontiers_ order."""
+    L = lib()
+    tri = np.ascontiguousarray(tri, dtype=np.uint8)
+    assert flag.dtype == np.int8 and flag.flags["C_CONTIGUOUS"]
+    umin = np.ascontiguousarray(upd_min, dtype=np.float64)
+    umax = np.ascontiguousarray(upd_max, dtype=np.float64)
+    h = C.c_void_p(L.orc_frontier_search(C.byref(g), _p(tri), _p(flag), _p(umin), _p(umax),
+                                         C.byref(params)))
+    out = []
+    try:
+        for i in range(L.orc_frontier_count(h)):
+            n = L.orc_frontier_num_cells(h, i)
+            m = L.orc_frontier_num_filtered(h, i)
+            addr = np.empty(n, dtype=np.int32)
+            filt = np.empty((m, 3), dtype=np.float64)
+            avg = np.empty(3)
+            bmin = np.empty(3)
+            bmax = np.empty(3)
+            L.orc_frontier_get(h, i, _p(addr), _p(filt), _p(avg), _p(bmin), _p(bmax))
+            out.append(dict(addr=addr, filtered=filt, average=avg, box_min=bmin, box_max=bmax))
+    finally:
+        L.orc_frontier_free(h)
+    return out
+
+
+def principal_axis_2x2(a, b, d):
+    pc = np.empty(2)
+    lib().orc_principal_axis_2x2(C.c_double(a), C.c_double(b), C.c_double(d), _p(pc))
+    return pc
+
+
+def opt_params(ld_smooth=20.0, ld_dist=10.0, ld_feasi=2.0, ld_start=100.0, ld_end=0.5, ld_guide=1.5,
+               ld_waypt=0.3, ld_view=0.0, ld_time=1.0, dist0=0.7, max_vel=2.0, max_acc=2.0, order=3):
+    """Defaults = exploration_manager/launch/algorithm.xml:170-181 and exploration.launch max_vel/acc."""
+    p = OrcOptParams()
+    (p.ld_smooth, p.ld_dist, p.ld_feasi, p.ld_start, p.ld_end, p.ld_guide, p.ld_waypt, p.ld_view,
+     p.ld_time, p.dist0, p.max_vel, p.max_acc, p.order) = (ld_smooth, ld_dist, ld_feasi, ld_start,
+                                                           ld_end, ld_guide, ld_waypt, ld_view,
+                                                           ld_time, dist0, max_vel, max_acc, order)
+    return p
+
+
+def traj_consts(B):
+    return (OrcTrajConst * B)()
+
+
+def fill_traj_const(tc, pt_dist, knot_span, start, end, time_lb=-1.0, guide=None, waypt=None,
+                    waypt_idx=None):
+    tc.pt_dist = float(pt_dist)
+    tc.knot_span = float(knot_span)
+    start = np.asarray(start, dtype=np.float64).reshape(3, 3)
+    end = np.asarray(end, dtype=np.float64).reshape(-1, 3)
+    for i in range(3):
+        for k in range(3):
+            tc.start[i][k] = start[i, k]
+    tc.n_end = end.shape[0]
+    for i in range(end.shape[0]):
+        for k in range(3):
+            tc.end[i][k] = end[i, k]
+    tc.time_lb = float(time_lb)
+    tc.n_guide = 0
+    tc.n_waypt = 0
+    if guide is not None:
+        guide = np.asarray(guide, dtype=np.float64).reshape(-1, 3)
+        tc.n_guide = guide.shape[0]
+        for i in range(guide.shape[0]):
+            for k in range(3):
+                tc.guide[i][k] = guide[i, k]
+    if waypt is not None:
+        waypt = np.asarray(waypt, dtype=np.float64).reshape(-1, 3)
+        tc.n_waypt = waypt.shape[0]
+        for i in range(waypt.shape[0]):
+            for k in range(3):
+                tc.waypt[i][k] = waypt[i, k]
+            tc.waypt_idx[i] = int(waypt_idx[i])
+
+
+def pt_dist(ctrl):
+    ctrl = np.ascontiguousarray(ctrl, dtype=np.float64).reshape(-1, 3)
+    return lib().orc_pt_dist(_p(ctrl), C.c_int32(ctrl.shape[0]))
+
+
+def combine_cost_batch(g, dist_buf, p, tcs, n_pts, mask, x, threads=1):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    B = x.shape[0]
+    nvar = 3 * n_pts + (1 if mask & MINTIME else 0)
+    assert x.shape[1] == nvar
+    dist_buf = np.ascontiguousarray(dist_buf, dtype=np.float64)
+    f = np.empty(B, dtype=np.float64)
+    grad = np.empty((B, nvar), dtype=np.float64)
+    lib().orc_combine_cost_batch(C.byref(g), _p(dist_buf), C.byref(p), tcs, C.c_int32(n_pts),
+                                 C.c_int32(mask), C.c_int32(B), _p(x), _p(f), _p(grad),
+                                 C.c_int(threads))
+    return f, grad

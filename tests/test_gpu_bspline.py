@@ -1,0 +1,169 @@
+"""B-spline cost/gradient parity: fuelgpu_bspline_cost_batch vs the CPU oracle of
+BsplineOptimizer::combineCost (bspline_opt/src/bspline_optimizer.cpp:518-647).
+Tolerance (north_star): 1e-4 relative on cost and gradient."""
+import numpy as np
+import pytest
+
+from fuel_b200 import workloads as W
+from tests.helpers import make_sdf_map, orc_grid
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def scene(fuel, orc):
+    g, inflate = W.office_map()
+    tri = W.office_known(g, inflate)
+    m = make_sdf_map(fuel, g, inflate, tri, optimistic=True)
+    m.updateESDF3d()
+    d32 = m.download().copy()
+    env = fuel.EDTEnvironment()
+    env.setMap(m)
+    opt = fuel.BsplineOptimizer()
+    opt.setEnvironment(env)
+    # the oracle reads the reference's own fp64 field (resolution*sqrt(int) in double)
+    d64 = orc.update_esdf3d(orc_grid(orc, g), inflate, tri, [0, 0, 0], np.array(g.n) - 1, True, False, threads=8)
+    yield dict(g=g, inflate=inflate, m=m, opt=opt, d32=d32, d64=d64)
+    m.close()
+
+
+def orc_consts(orc, tr, B, guide=None, waypt=None, waypt_idx=None, n_end=1, time_lb=None):
+    tcs = orc.traj_consts(B)
+    for b in range(B):
+        end = np.zeros((n_end, 3))
+        end[0] = tr["end_pos"][b]
+        orc.fill_traj_const(tcs[b], tr["pt_dist"][b], tr["dt"][b], tr["start"][b], end,
+                            -1.0 if time_lb is None else time_lb[b],
+                            None if guide is None else guide[b], None if waypt is None else waypt[b], waypt_idx)
+    return tcs
+
+
+def gpu_consts(fuel, tr, B, guide=None, waypt=None, waypt_idx=None, n_end=1, time_lb=None):
+    from fuel_b200._lib import FuelTrajConst
+    tcs = (FuelTrajConst * B)()
+    for b in range(B):
+        end = np.zeros((n_end, 3))
+        end[0] = tr["end_pos"][b]
+        fuel.BsplineOptimizer.fill_traj_const(tcs[b], tr["pt_dist"][b], tr["dt"][b], tr["start"][b], end,
+                                              -1.0 if time_lb is None else time_lb[b],
+                                              None if guide is None else guide[b],
+                                              None if waypt is None else waypt[b], waypt_idx)
+    return tcs
+
+
+def check(f, g, fr, gr):
+    assert np.all(np.abs(f - fr) <= RTOL * np.abs(fr) + 1e-12), np.max(np.abs(f - fr) / np.abs(fr))
+    scale = np.max(np.abs(gr), axis=1, keepdims=True)
+    err = np.abs(g - gr)
+    # every component within 1e-4 of its own magnitude, with the trajectory's gradient
+    # scale as the floor for components that cancel to ~0
+    assert np.all(err <= RTOL * np.maximum(np.abs(gr), 1e-3 * scale) + 1e-12), np.max(err / scale)
+
+
+def test_benchmark_objective(fuel, orc, scene):
+    """NORMAL_PHASE | MINTIME (the exploration objective, planner_manager.cpp:304-305) on the
+    config-2 batch."""
+    B, N = 1024, 20
+    tr = W.make_trajectories(scene["g"], scene["inflate"], B=B, n_pts=N)
+    mask = fuel.BsplineOptimizer.NORMAL_PHASE | fuel.BsplineOptimizer.MINTIME
+    x = W.pack_x(tr["ctrl"], tr["dt"])
+    f, g = scene["opt"].combineCostBatch(x, gpu_consts(fuel, tr, B), N, mask)
+    fr, gr = orc.combine_cost_batch(orc_grid(orc, scene["g"]), scene["d64"], orc.opt_params(),
+                                    orc_consts(orc, tr, B), N, mask, x, threads=8)
+    check(f, g, fr, gr)
+    # the distance term must be active for a realistic share of control points
+    d, _ = scene["m"].getDistWithGrad(tr["ctrl"].reshape(-1, 3))
+    frac = np.mean(d < 0.7)
+    assert 0.15 < frac < 0.8, frac
+    # vectorised constant builder gives the same bytes as the field-by-field one
+    arr = fuel.BsplineOptimizer.traj_consts_from_arrays(tr["pt_dist"], tr["dt"], tr["start"], tr["end_pos"])
+    f2, g2 = scene["opt"].combineCostBatch(x, arr, N, mask)
+    assert np.array_equal(f, f2) and np.array_equal(g, g2)
+
+
+@pytest.mark.parametrize("mask_name", ["SMOOTHNESS", "DISTANCE", "FEASIBILITY", "START", "END", "MINTIME",
+                                       "NORMAL_PHASE"])
+def test_single_terms(fuel, orc, scene, mask_name):
+    B, N = 64, 20
+    tr = W.make_trajectories(scene["g"], scene["inflate"], B=B, n_pts=N, seed=5)
+    O = fuel.BsplineOptimizer
+    mask = getattr(O, mask_name)
+    if mask_name == "MINTIME":
+        mask |= O.SMOOTHNESS
+    x = W.pack_x(tr["ctrl"], tr["dt"], mintime=bool(mask & O.MINTIME))
+    # make feasibility bite: shrink dt for half of the batch
+    if mask & O.MINTIME:
+        x[::2, -1] *= 0.5
+    else:
+        tr["dt"][::2] *= 0.5
+    f, g = scene["opt"].combineCostBatch(x, gpu_consts(fuel, tr, B), N, mask)
+    fr, gr = orc.combine_cost_batch(orc_grid(orc, scene["g"]), scene["d64"], orc.opt_params(),
+                                    orc_consts(orc, tr, B), N, mask, x)
+    check(f, g, fr, gr)
+
+
+def test_guide_waypoints_end3_timelb(fuel, orc, scene):
+    """GUIDE_PHASE, WAYPOINTS, a 3-entry end_state_ and an active time lower bound."""
+    B, N = 32, 24
+    tr = W.make_trajectories(scene["g"], scene["inflate"], B=B, n_pts=N, seed=9)
+    O = fuel.BsplineOptimizer
+    rng = np.random.default_rng(3)
+    guide = tr["ctrl"][:, 3:N - 3] + rng.normal(scale=0.2, size=(B, N - 6, 3))
+    widx = [0, 4, 9, N - 3]
+    waypt = rng.uniform(-1, 1, size=(B, len(widx), 3)) + tr["ctrl"][:, [1, 5, 10, N - 2]]
+    time_lb = (N - 3) * tr["dt"] * 1.3
+    for mask, n_end in ((O.GUIDE_PHASE, 1), (O.SMOOTHNESS | O.WAYPOINTS, 1), (O.NORMAL_PHASE | O.MINTIME, 3),
+                        (O.SMOOTHNESS | O.WAYPOINTS | O.START | O.END, 2)):
+        x = W.pack_x(tr["ctrl"], tr["dt"], mintime=bool(mask & O.MINTIME))
+        kw = dict(guide=guide, waypt=waypt, waypt_idx=widx, n_end=n_end, time_lb=time_lb)
+        tg = gpu_consts(fuel, tr, B, **kw)
+        to = orc_consts(orc, tr, B, **kw)
+        if n_end > 1:
+            for b in range(B):
+                for i in range(1, n_end):
+                    for k in range(3):
+                        v = float(rng.normal())
+                        tg[b].end[i][k] = v
+                        to[b].end[i][k] = v
+        f, g = scene["opt"].combineCostBatch(x, tg, N, mask)
+        fr, gr = orc.combine_cost_batch(orc_grid(orc, scene["g"]), scene["d64"], orc.opt_params(), to, N, mask, x)
+        check(f, g, fr, gr)
+
+
+def test_adversarial_positions(fuel, orc, scene):
+    """Control points on the map boundary, outside the map, and in flat ESDF regions."""
+    B, N = 48, 20
+    g = scene["g"]
+    tr = W.make_trajectories(g, scene["inflate"], B=B, n_pts=N, seed=13)
+    ctrl = tr["ctrl"].copy()
+    ctrl[0:8, 5] = g.origin + [0.02, 0.5, 0.5]        # stencil pokes outside the map
+    ctrl[8:16, 7] = g.map_max + 0.3                   # outside the map -> (0, 0-grad)
+    ctrl[16:24, 9] = g.map_max - [1e-4, 0.5, 0.5]     # the isInMap margin
+    tr["ctrl"] = ctrl
+    O = fuel.BsplineOptimizer
+    mask = O.NORMAL_PHASE | O.MINTIME
+    x = W.pack_x(ctrl, tr["dt"])
+    f, gg = scene["opt"].combineCostBatch(x, gpu_consts(fuel, tr, B), N, mask)
+    fr, gr = orc.combine_cost_batch(orc_grid(orc, g), scene["d64"], orc.opt_params(), orc_consts(orc, tr, B), N,
+                                    mask, x)
+    check(f, gg, fr, gr)
+
+
+def test_b1_trampoline_and_rejects(fuel, orc, scene):
+    """B == 1 (the costFunction trampoline, :693-706) and argument errors."""
+    O = fuel.BsplineOptimizer
+    tr = W.make_trajectories(scene["g"], scene["inflate"], B=1, n_pts=20, seed=2)
+    opt = scene["opt"]
+    opt.setBoundaryStates(list(tr["start"][0]), [tr["end_pos"][0]])
+    opt.begin(tr["ctrl"][0], tr["dt"][0], O.NORMAL_PHASE | O.MINTIME)
+    x = opt.initial_variables()
+    f, g = opt.costFunction(x)
+    tcs = orc.traj_consts(1)
+    orc.fill_traj_const(tcs[0], opt.pt_dist_, tr["dt"][0], tr["start"][0], tr["end_pos"][0][None, :])
+    assert abs(opt.pt_dist_ - orc.pt_dist(tr["ctrl"][0])) < 1e-15
+    fr, gr = orc.combine_cost_batch(orc_grid(orc, scene["g"]), scene["d64"], orc.opt_params(), tcs, 20,
+                                    O.NORMAL_PHASE | O.MINTIME, x[None, :])
+    check(np.array([f]), g[None, :], fr, gr)
+    with pytest.raises(fuel.FuelGpuError):
+        opt.combineCostBatch(x[None, :], opt._tc, 20, O.NORMAL_PHASE | O.MINTIME | O.VIEWCONS)
