@@ -71,6 +71,8 @@ SIGNATURES = {
     "fuelgpu_frontier_fetch": (C.c_int, [_vp] + [_vp] * 7),
     "fuelgpu_frontier_clear_flags": (C.c_int, [_vp, _i32, _vp]),
     "fuelgpu_frontier_is_changed": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "fuelgpu_frontier_reset_flags": (C.c_int, [_vp]),
+    "fuelgpu_map_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "fuelgpu_frontier_download_flags": (C.c_int, [_vp, _vp]),
     "fuelgpu_frontier_upload_flags": (C.c_int, [_vp, _vp]),
     "fuelgpu_bspline_cost_batch": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp, _vp,
@@ -79,6 +81,8 @@ SIGNATURES = {
                                                  _vp, _vp, _vp]),
     "fuelgpu_bspline_optimize_batch": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp,
                                                  C.POINTER(FuelSolveParams), _vp, _vp, _vp]),
+    "fuelgpu_bspline_optimize_batch_dev": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp,
+                                                     C.POINTER(FuelSolveParams), _vp, _vp, _vp]),
     "fuelgpu_edt_xy_dev": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_int, _vp, _vp]),
     "fuelgpu_edt_z_chunks_dev": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _dbl, _vp, _vp]),
 }

@@ -163,6 +163,24 @@ class BsplineOptimizer:
                                                ptr(f), ptr(g)), h)
         return f, g
 
+    def optimizeBatch(self, x, traj_consts, n_pts, cost_function, max_eval, lbfgs_m=6, xtol_rel=1e-5):
+        """The solver loop of optimize() (:165-253) for B trajectories in one persistent kernel.
+        x [B, nvar] initial variables (clamped to the box shrunk by 0.1 m on the device, :196-204).
+        Returns (x_best [B, nvar], f_best [B], n_eval [B])."""
+        mask = int(cost_function)
+        x = np.array(x, dtype=np.float64, order="C", copy=True)
+        B = x.shape[0]
+        if x.shape[1] != self.nvar(n_pts, mask):
+            raise ValueError("x must be [B, %d]" % self.nvar(n_pts, mask))
+        sp = FuelSolveParams()
+        sp.max_eval, sp.lbfgs_m, sp.xtol_rel = int(max_eval), int(lbfgs_m), float(xtol_rel)
+        fb = np.empty(B, dtype=np.float64)
+        ne = np.empty(B, dtype=np.int32)
+        h = self.edt_environment_.sdf_map_.handle
+        check(lib().fuelgpu_bspline_optimize_batch(h, B, n_pts, mask, C.byref(self.params_), traj_consts,
+                                                   C.byref(sp), ptr(x), ptr(fb), ptr(ne)), h)
+        return x, fb, ne
+
     def _own_traj_const(self, ctrl, dt):
         tc = (FuelTrajConst * 1)()
         start = np.zeros((3, 3))

@@ -265,6 +265,7 @@ int fuelgpu_map_upload_occupancy(FuelMap* m, const int8_t* inflate, const double
     FUEL_CUDA(m, cudaMemcpyAsync(d_tri, tristate + off, cnt, cudaMemcpyHostToDevice, m->stream));
     ingest_tri_kernel<<<nb, 256, 0, m->stream>>>(d_inf, d_tri, m->occ + off, cnt);
   }
+  m->launches += 1;
   FUEL_CUDA(m, cudaGetLastError());
   tend(m, T_UPLOAD);
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));  // host buffers may be reused by the caller
@@ -303,6 +304,7 @@ int fuelgpu_esdf_download(FuelMap* m, const int32_t bmin[3], const int32_t bmax[
     if (rc) return rc;
     f32_to_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, m->stream>>>(
         m->dist + off, (double*)m->stage, cnt, m->g.res * sqrt(1.7976931348623157e308));
+    m->launches += 1;
     FUEL_CUDA(m, cudaGetLastError());
     FUEL_CUDA(m, cudaMemcpyAsync(out_f64 + off, m->stage, cnt * 8, cudaMemcpyDeviceToHost, m->stream));
   }
@@ -358,6 +360,7 @@ int fuelgpu_frontier_clear_flags(FuelMap* m, int32_t n, const int32_t* addr) {
   if (rc) return rc;
   FUEL_CUDA(m, cudaMemcpyAsync(m->stage, addr, sizeof(int) * n, cudaMemcpyHostToDevice, m->stream));
   clear_flags_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(m->flag, (const int*)m->stage, n);
+  m->launches += 1;
   FUEL_CUDA(m, cudaGetLastError());
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
   return 0;
@@ -369,6 +372,19 @@ int fuelgpu_frontier_is_changed(FuelMap* m, int32_t mcl, const int32_t* cell_off
     return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
   return frontier_is_changed_impl(m, mcl, cell_offsets, cell_addr, changed);
+}
+
+int fuelgpu_frontier_reset_flags(FuelMap* m) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  FUEL_CUDA(m, cudaMemsetAsync(m->flag, 0, m->nvox, m->stream));
+  return 0;
+}
+
+int fuelgpu_map_launch_count(FuelMap* m, int64_t* count) {
+  if (!m || !count) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  *count = m->launches;
+  return 0;
 }
 
 int fuelgpu_frontier_download_flags(FuelMap* m, int8_t* out) {
@@ -443,6 +459,25 @@ int fuelgpu_bspline_cost_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mas
   FUEL_CUDA(m, cudaMemcpyAsync(grad, d_g, xb, cudaMemcpyDeviceToHost, m->stream));
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
   return 0;
+}
+
+int fuelgpu_bspline_optimize_batch_dev(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
+                                       const FuelOptParams* p, const void* traj_dev,
+                                       const FuelSolveParams* solve, void* x_dev, void* f_best_dev,
+                                       void* n_eval_dev) {
+  int rc = check_bspline_args(m, B, n_pts, mask, p);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!traj_dev || !x_dev || !f_best_dev || !n_eval_dev || !solve)
+    return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (solve->lbfgs_m < 1 || solve->lbfgs_m > 8 || solve->max_eval < 1)
+    return fuel_fail(m, FUELGPU_EINVAL, "bad solver parameters");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  tbegin(m, T_BSPLINE);
+  rc = bspline_optimize_batch_dev_impl(m, B, n_pts, mask, p, (const FuelTrajConst*)traj_dev, solve,
+                                       (double*)x_dev, (double*)f_best_dev, (int32_t*)n_eval_dev);
+  tend(m, T_BSPLINE);
+  return rc;
 }
 
 int fuelgpu_bspline_optimize_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,

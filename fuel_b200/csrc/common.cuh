@@ -50,6 +50,7 @@ struct FuelMap {
   // bspline scratch (device)
   void* bs_buf;
   size_t bs_bytes;
+  long long launches;  // kernels launched so far
   char err[512];
 };
 

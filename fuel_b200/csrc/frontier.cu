@@ -800,7 +800,9 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   ENSURE(f->blockoff, nb);
 
   classify_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, m->occ, m->flag, f->maskE.p, f->maskS.p, f->blockcnt.p, ndom);
+  m->launches += 1;
   scan_kernel<<<1, 1024, 0, s>>>(f->blockcnt.p, f->blockoff.p, (int)nb, f->d_counters + 0);
+  m->launches += 1;
   int n_cand = 0;
   FUEL_CUDA(m, cudaMemcpyAsync(&n_cand, f->d_counters, sizeof(int), cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
@@ -813,28 +815,39 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
 
   compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p,
                                           f->cell_cls.p, f->cellidx, ndom);
+  m->launches += 1;
   const unsigned cb = nblk(n_cand, 256);
   init_parent_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->claim.p, f->csize.p, n_cand);
+  m->launches += 1;
   union_kernel<<<cb, 256, 0, s>>>(g, f->cell_addr.p, f->cell_cls.p, f->cellidx, f->parent.p, n_cand);
+  m->launches += 1;
   flatten_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->cell_cls.p, n_cand);
+  m->launches += 1;
   claim_kernel<<<cb, 256, 0, s>>>(g, fp, f->cell_addr.p, f->cell_cls.p, f->cellidx, f->parent.p, f->claim.p, n_cand);
+  m->launches += 1;
   assign_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cell_cls.p, f->parent.p, f->claim.p, f->seed.p,
                                    f->csize.p, m->flag, n_cand);
+  m->launches += 1;
   mark_kernel<<<cb, 256, 0, s>>>(f->seed.p, f->csize.p, fp.cluster_min, f->is_root.p, f->is_kept.p, n_cand);
+  m->launches += 1;
   scan_kernel<<<1, 1024, 0, s>>>(f->is_root.p, f->root_rank.p, n_cand, f->d_counters + 1);
+  m->launches += 1;
   scan_kernel<<<1, 1024, 0, s>>>(f->is_kept.p, f->kept_off.p, n_cand, f->d_counters + 2);
+  m->launches += 1;
   int cnt[3];
   FUEL_CUDA(m, cudaMemcpyAsync(cnt, f->d_counters, sizeof(int) * 3, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
   const int R = cnt[1], K = cnt[2];
   if (R == 0 || K == 0) {
     reset_cellidx_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cellidx, n_cand);
+  m->launches += 1;
     FUEL_CUDA(m, cudaGetLastError());
     return 0;
   }
   ENSURE(f->k_addr, K); ENSURE(f->k_cl, K); ENSURE(f->k_leaf, K); ENSURE(f->k_cent, (size_t)3 * K);
   gather_kept_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->seed.p, f->is_kept.p, f->kept_off.p,
                                         f->root_rank.p, f->k_addr.p, f->k_cl.p, f->cellidx, n_cand);
+  m->launches += 1;
 
   // ---- split levels -------------------------------------------------------------------
   // at most one new cluster per kept cell; K bounds the cluster count
@@ -842,6 +855,7 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   ENSURE(f->stat, (size_t)2 * R + 1024);
   int C = R;
   init_meta_kernel<<<nblk(R, 256), 256, 0, s>>>(f->meta.p, R);
+  m->launches += 1;
   const unsigned kb = nblk(K, 256);
   for (int level = 0; level < 40; ++level) {
     // every active cluster may spawn one new cluster this level
@@ -849,20 +863,30 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
       return fuel_fail(m, FUELGPU_ENOMEM, "frontier: device allocation failed");
     const unsigned ccb = nblk(C, 256);
     stat_reset_kernel<<<ccb, 256, 0, s>>>(f->stat.p, f->meta.p, C);
+  m->launches += 1;
     stat_accum_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, K);
+  m->launches += 1;
     mean_kernel<<<ccb, 256, 0, s>>>(g, f->meta.p, f->stat.p, C);
+  m->launches += 1;
     downsample_kernel<<<kb, 256, 0, s>>>(g, fp, f->k_addr.p, f->k_cl.p, f->cellidx, f->meta.p, f->stat.p,
                                          f->k_cent.p, f->k_leaf.p, K);
+  m->launches += 1;
     cov_kernel<<<kb, 256, 0, s>>>(f->k_cl.p, f->k_leaf.p, f->k_cent.p, f->meta.p, f->stat.p, K);
+  m->launches += 1;
     pca_kernel<<<ccb, 256, 0, s>>>(f->meta.p, f->stat.p, C);
+  m->launches += 1;
     side_count_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, K);
+  m->launches += 1;
     split_alloc_kernel<<<1, 1024, 0, s>>>(f->meta.p, f->stat.p, C, f->d_counters + 3);
+  m->launches += 1;
     relabel_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, K, C);
+  m->launches += 1;
     int n_new = 0;
     FUEL_CUDA(m, cudaMemcpyAsync(&n_new, f->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
     FUEL_CUDA(m, cudaStreamSynchronize(s));
     if (n_new == 0) break;
     clear_do_split_kernel<<<ccb, 256, 0, s>>>(f->meta.p, C);
+  m->launches += 1;
     C += n_new;
   }
 
@@ -878,6 +902,7 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   FUEL_CUDA(m, cudaMemcpyAsync(h_meta.data(), f->meta.p, sizeof(ClusterMeta) * C, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaMemcpyAsync(h_stat.data(), f->stat.p, sizeof(ClusterStat) * C, cudaMemcpyDeviceToHost, s));
   reset_cellidx_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cellidx, n_cand);
+  m->launches += 1;
   FUEL_CUDA(m, cudaGetLastError());
   FUEL_CUDA(m, cudaStreamSynchronize(s));
 
@@ -965,6 +990,7 @@ int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const
   FUEL_CUDA(m, cudaMemcpyAsync(d_off, offs, sizeof(int) * (mcl + 1), cudaMemcpyHostToDevice, s));
   if (ncell > 0) FUEL_CUDA(m, cudaMemcpyAsync(d_addr, addr, sizeof(int) * ncell, cudaMemcpyHostToDevice, s));
   is_changed_kernel<<<mcl, 128, 0, s>>>(m->g, m->occ, d_off, d_addr, d_ch, mcl);
+  m->launches += 1;
   FUEL_CUDA(m, cudaMemcpyAsync(changed, d_ch, mcl, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
   cudaFree(d_off);

@@ -148,6 +148,10 @@ class FrontierFinder:
         """frontier_finder.cpp getFrontierBoxes: (centre, scale) per stored frontier"""
         return [((f.box_max_ + f.box_min_) / 2, f.box_max_ - f.box_min_) for f in self.frontiers_]
 
+    def reset_flags(self):
+        """frontier_flag_ = 0 (the constructor's fill, frontier_finder.cpp:26-27)"""
+        check(lib().fuelgpu_frontier_reset_flags(self._map.handle), self._map.handle)
+
     def download_flags(self):
         m = self._map
         out = np.zeros(m.shape, dtype=np.int8)

@@ -95,6 +95,11 @@ class SDFMap:
         check(lib().fuelgpu_map_last_timing(self._h, ms), self._h)
         return dict(esdf=ms[0], frontier=ms[1], bspline=ms[2], upload=ms[3], download=ms[4])
 
+    def launch_count(self):
+        n = C.c_int64()
+        check(lib().fuelgpu_map_launch_count(self._h, C.byref(n)), self._h)
+        return n.value
+
     def device_ptrs(self):
         occ, dist, flag = C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(lib().fuelgpu_map_device_ptrs(self._h, C.byref(occ), C.byref(dist), C.byref(flag)), self._h)

@@ -74,6 +74,8 @@ FUELGPU_API int fuelgpu_map_device_ptrs(FuelMap* map, void** occ, void** dist, v
 /* Milliseconds spent on the device by the last call of each stage (CUDA events on the
  * handle's stream): [0] esdf_update [1] frontier_search [2] bspline batch [3] upload [4] download */
 FUELGPU_API int fuelgpu_map_last_timing(FuelMap* map, float ms[8]);
+/* Number of kernels this handle has launched since creation (every <<<>>> is counted). */
+FUELGPU_API int fuelgpu_map_launch_count(FuelMap* map, int64_t* count);
 
 /* ---- ingest: host occupancy -> resident occupancy byte ------------------------------
  * Replaces nothing in the reference (its buffers are already in RAM); this is the H2D leg.
@@ -137,6 +139,8 @@ FUELGPU_API int fuelgpu_frontier_clear_flags(FuelMap* map, int32_t n, const int3
  * form; changed[i] = 1 iff some cell of cluster i stopped being a frontier cell. */
 FUELGPU_API int fuelgpu_frontier_is_changed(FuelMap* map, int32_t m, const int32_t* cell_offsets,
                                 const int32_t* cell_addr, uint8_t* changed);
+/* frontier_flag_ = 0 everywhere: the fill of FrontierFinder::FrontierFinder (frontier_finder.cpp:26-27). */
+FUELGPU_API int fuelgpu_frontier_reset_flags(FuelMap* map);
 FUELGPU_API int fuelgpu_frontier_download_flags(FuelMap* map, int8_t* out);
 FUELGPU_API int fuelgpu_frontier_upload_flags(FuelMap* map, const int8_t* in);
 
@@ -203,6 +207,12 @@ FUELGPU_API int fuelgpu_bspline_optimize_batch(FuelMap* map, int32_t B, int32_t 
                                    const FuelOptParams* params, const FuelTrajConst* traj,
                                    const FuelSolveParams* solve, double* x, double* f_best,
                                    int32_t* n_eval);
+
+/* Same, all pointers in device memory. */
+FUELGPU_API int fuelgpu_bspline_optimize_batch_dev(FuelMap* map, int32_t B, int32_t n_pts, int32_t cost_mask,
+                                       const FuelOptParams* params, const void* traj_dev,
+                                       const FuelSolveParams* solve, void* x_dev, void* f_best_dev,
+                                       void* n_eval_dev);
 
 /* ---- multi-GPU building blocks (z-sharded ESDF, DESIGN.md "multi-GPU") --------------
  * These operate on caller-owned DEVICE buffers so that torch.distributed/NCCL can move

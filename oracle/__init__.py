@@ -252,3 +252,17 @@ def combine_cost_batch(g, dist_buf, p, tcs, n_pts, mask, x, threads=1):
                                  C.c_int32(mask), C.c_int32(B), _p(x), _p(f), _p(grad),
                                  C.c_int(threads))
     return f, grad
+
+
+def optimize_batch(g, dist_buf, p, tcs, n_pts, mask, x, max_eval=64, lbfgs_m=6, xtol_rel=1e-5, threads=1):
+    """CPU twin of fuelgpu_bspline_optimize_batch (NOT NLopt).  Returns (x_best, f_best, n_eval)."""
+    x = np.array(x, dtype=np.float64, order="C", copy=True)
+    B = x.shape[0]
+    dist_buf = np.ascontiguousarray(dist_buf, dtype=np.float64)
+    sp = OrcSolveParams()
+    sp.max_eval, sp.lbfgs_m, sp.xtol_rel = max_eval, lbfgs_m, xtol_rel
+    fb = np.empty(B, dtype=np.float64)
+    ne = np.empty(B, dtype=np.int32)
+    lib().orc_optimize_batch(C.byref(g), _p(dist_buf), C.byref(p), tcs, C.c_int32(n_pts), C.c_int32(mask),
+                             C.c_int32(B), C.byref(sp), _p(x), _p(fb), _p(ne), C.c_int(threads))
+    return x, fb, ne

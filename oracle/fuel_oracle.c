@@ -1075,3 +1075,136 @@ void orc_combine_cost_batch(const OrcGrid* g, const double* dist_buf, const OrcO
     orc_combine_cost(g, dist_buf, p, &tc[b], n, mask, x + (int64_t)b * nvar, &f[b],
                      grad + (int64_t)b * nvar);
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* CPU twin of the device-side batched solver (fuelgpu_bspline_optimize_batch).           */
+/* NOT a restatement of NLopt.  Restates what optimize() itself does around the solver   */
+/* (bspline_optimizer.cpp:175-217 clamp + bounds, :170 maxeval, :173 xtol_rel, :693-706  */
+/* best-x tracking) around the same projected L-BFGS the device runs.                    */
+/* ------------------------------------------------------------------------------------ */
+#define ORC_MAXM 8
+#define ORC_MAXVAR (3 * ORC_MAX_PTS + 1)
+
+static double vdot(const double* a, const double* b, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+
+static void optimize_one(const OrcGrid* g, const double* dist_buf, const OrcOptParams* p,
+                         const OrcTrajConst* tc, int n, int mask, const OrcSolveParams* sp, double* x,
+                         double* f_best, int32_t* n_eval) {
+  const int opt_time = (mask & ORC_MINTIME) != 0;
+  const int nv = opt_time ? 3 * n + 1 : 3 * n;
+  const int m = sp->lbfgs_m;
+  double X[ORC_MAXVAR], G[ORC_MAXVAR], lb[ORC_MAXVAR], ub[ORC_MAXVAR], PG[ORC_MAXVAR], D[ORC_MAXVAR],
+      Q[ORC_MAXVAR], XN[ORC_MAXVAR], GN[ORC_MAXVAR], dx[ORC_MAXVAR];
+  static _Thread_local double S[ORC_MAXM][ORC_MAXVAR], Y[ORC_MAXM][ORC_MAXVAR];
+  double rho[ORC_MAXM] = { 0 }, alpha[ORC_MAXM];
+  int act[ORC_MAXVAR];
+  for (int i = 0; i < 3 * n; ++i) {
+    const int k = i % 3;
+    const double bmin = g->box_mind[k] + 0.1, bmax = g->box_maxd[k] - 0.1;
+    double c = x[i];
+    c = fmax(fmin(c, bmax), bmin);
+    X[i] = c;
+    lb[i] = fmax(c - 10.0, bmin);
+    ub[i] = fmin(c + 10.0, bmax);
+  }
+  if (opt_time) {
+    X[nv - 1] = x[nv - 1];
+    lb[nv - 1] = 0.0;
+    ub[nv - 1] = 5.0;
+  }
+  double F, FN = 0.0;
+  orc_combine_cost(g, dist_buf, p, tc, n, mask, X, &F, G);
+  int neval = 1;
+  double best = F;
+  memcpy(x, X, sizeof(double) * nv);
+  *f_best = F;
+  if (!(best == best)) best = DBL_MAX;
+  int cnt = 0, head = 0;
+  while (neval < sp->max_eval) {
+    for (int i = 0; i < nv; ++i) {
+      act[i] = (X[i] <= lb[i] && G[i] > 0.0) || (X[i] >= ub[i] && G[i] < 0.0);
+      PG[i] = act[i] ? 0.0 : G[i];
+    }
+    const double pgn2 = vdot(PG, PG, nv);
+    if (!(pgn2 > 1e-24)) break;
+    memcpy(Q, PG, sizeof(double) * nv);
+    for (int j = 0; j < cnt; ++j) {
+      const int slot = (head - 1 - j + 2 * ORC_MAXM * m) % m;
+      alpha[j] = rho[slot] * vdot(S[slot], Q, nv);
+      for (int i = 0; i < nv; ++i) Q[i] -= alpha[j] * Y[slot][i];
+    }
+    if (cnt > 0) {
+      const int slot = (head - 1 + m) % m;
+      const double gamma = vdot(S[slot], Y[slot], nv) / vdot(Y[slot], Y[slot], nv);
+      for (int i = 0; i < nv; ++i) Q[i] *= gamma;
+    }
+    for (int j = cnt - 1; j >= 0; --j) {
+      const int slot = (head - 1 - j + 2 * ORC_MAXM * m) % m;
+      const double beta = rho[slot] * vdot(Y[slot], Q, nv);
+      for (int i = 0; i < nv; ++i) Q[i] += S[slot][i] * (alpha[j] - beta);
+    }
+    for (int i = 0; i < nv; ++i) D[i] = act[i] ? 0.0 : -Q[i];
+    double gd = vdot(G, D, nv);
+    if (!(gd < 0.0)) {
+      for (int i = 0; i < nv; ++i) D[i] = -PG[i];
+      gd = -pgn2;
+      cnt = 0;
+    }
+    double step = cnt == 0 ? fmin(1.0, 1.0 / sqrt(pgn2)) : 1.0;
+    int accepted = 0;
+    while (neval < sp->max_eval) {
+      for (int i = 0; i < nv; ++i) XN[i] = fmax(fmin(X[i] + step * D[i], ub[i]), lb[i]);
+      orc_combine_cost(g, dist_buf, p, tc, n, mask, XN, &FN, GN);
+      ++neval;
+      if (FN < best) {
+        best = FN;
+        memcpy(x, XN, sizeof(double) * nv);
+        *f_best = FN;
+      }
+      for (int i = 0; i < nv; ++i) dx[i] = XN[i] - X[i];
+      const double dec = vdot(G, dx, nv);
+      if (FN <= F + 1e-4 * dec) {
+        accepted = 1;
+        break;
+      }
+      step *= 0.5;
+      if (step < 1e-12) break;
+    }
+    if (!accepted) break;
+    int small = 1;
+    double s_[ORC_MAXVAR], y_[ORC_MAXVAR];
+    for (int i = 0; i < nv; ++i) {
+      s_[i] = XN[i] - X[i];
+      y_[i] = GN[i] - G[i];
+      small = small && (fabs(s_[i]) <= sp->xtol_rel * fabs(XN[i]));
+    }
+    const double sy = vdot(s_, y_, nv), ss = vdot(s_, s_, nv), yy = vdot(y_, y_, nv);
+    if (sy > 1e-10 * sqrt(ss * yy)) {
+      memcpy(S[head], s_, sizeof(double) * nv);
+      memcpy(Y[head], y_, sizeof(double) * nv);
+      rho[head] = 1.0 / sy;
+      head = (head + 1) % m;
+      if (cnt < m) ++cnt;
+    }
+    memcpy(X, XN, sizeof(double) * nv);
+    memcpy(G, GN, sizeof(double) * nv);
+    F = FN;
+    if (small) break;
+  }
+  *n_eval = neval;
+}
+
+void orc_optimize_batch(const OrcGrid* g, const double* dist_buf, const OrcOptParams* p,
+                        const OrcTrajConst* tc, int32_t n_pts, int32_t cost_mask, int32_t B,
+                        const OrcSolveParams* sp, double* x, double* f_best, int32_t* n_eval,
+                        int threads) {
+  const int nv = (cost_mask & ORC_MINTIME) ? 3 * n_pts + 1 : 3 * n_pts;
+  if (threads < 1) threads = 1;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 8)
+  for (int b = 0; b < B; ++b)
+    optimize_one(g, dist_buf, p, &tc[b], n_pts, cost_mask, sp, x + (int64_t)b * nv, &f_best[b], &n_eval[b]);
+}

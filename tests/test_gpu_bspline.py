@@ -167,3 +167,49 @@ def test_b1_trampoline_and_rejects(fuel, orc, scene):
     check(np.array([f]), g[None, :], fr, gr)
     with pytest.raises(fuel.FuelGpuError):
         opt.combineCostBatch(x[None, :], opt._tc, 20, O.NORMAL_PHASE | O.MINTIME | O.VIEWCONS)
+
+
+def test_optimize_batch_matches_cpu_twin(fuel, orc, scene):
+    """Device-side projected L-BFGS (replaces the NLopt loop of optimize(), :165-253) vs its CPU
+    twin oracle.orc_optimize_batch.  Iterates diverge in the last bits (warp-reduction order), so
+    the check is on the result: the returned x re-evaluates to the returned cost on the oracle,
+    the cost never exceeds the start, the eval budget is respected, and the batch statistics
+    agree with the twin."""
+    B, N, K = 256, 20, 64
+    O = fuel.BsplineOptimizer
+    tr = W.make_trajectories(scene["g"], scene["inflate"], B=B, n_pts=N, seed=77)
+    mask = O.NORMAL_PHASE | O.MINTIME
+    x0 = W.pack_x(tr["ctrl"], tr["dt"])
+    og = orc_grid(orc, scene["g"])
+    to = orc_consts(orc, tr, B)
+    f0, _ = orc.combine_cost_batch(og, scene["d64"], orc.opt_params(), to, N, mask, x0)
+    xg, fg, ng = scene["opt"].optimizeBatch(x0, gpu_consts(fuel, tr, B), N, mask, K)
+    xc, fc, nc = orc.optimize_batch(og, scene["d64"], orc.opt_params(), to, N, mask, x0, max_eval=K, threads=8)
+    assert np.all(ng <= K) and np.all(ng >= 1)
+    assert np.all(fg <= f0 * (1 + 1e-9))
+    # returned variables are inside the bounds of :196-217
+    pts = xg[:, :3 * N].reshape(B, N, 3)
+    assert np.all(pts >= scene["g"].box_min + 0.1 - 1e-12) and np.all(pts <= scene["g"].box_max - 0.1 + 1e-12)
+    assert np.all(xg[:, -1] >= 0.0) and np.all(xg[:, -1] <= 5.0)
+    # best_variable_ re-evaluates to min_cost_ (fp32 ESDF samples vs the oracle's fp64 field: 1e-4)
+    fchk, _ = orc.combine_cost_batch(og, scene["d64"], orc.opt_params(), to, N, mask, xg)
+    assert np.all(np.abs(fchk - fg) <= 1e-4 * np.abs(fg) + 1e-9)
+    # same algorithm, same budget: the final costs agree for almost all trajectories
+    rel = np.abs(fg - fc) / np.abs(fc)
+    assert np.median(rel) < 1e-3, np.median(rel)
+    assert abs(np.mean(fg) - np.mean(fc)) < 0.02 * np.mean(fc)
+    assert np.mean(fg) < 0.01 * np.mean(f0)
+
+
+def test_optimize_single_and_small_budget(fuel, orc, scene):
+    """optimize() through the mirror for one trajectory; max_eval=1 returns the clamped start."""
+    O = fuel.BsplineOptimizer
+    tr = W.make_trajectories(scene["g"], scene["inflate"], B=2, n_pts=20, seed=4)
+    opt = scene["opt"]
+    opt.setBoundaryStates(list(tr["start"][0]), [tr["end_pos"][0]])
+    pts, dt = opt.optimize(tr["ctrl"][0], tr["dt"][0], O.NORMAL_PHASE | O.MINTIME, 1)
+    assert pts.shape == (20, 3) and 0 < dt <= 5.0 and opt.iter_num_ <= 2000 and opt.start_state_ == []
+    x0 = W.pack_x(tr["ctrl"], tr["dt"])
+    xg, fg, ng = opt.optimizeBatch(x0, gpu_consts(fuel, tr, 2), 20, O.NORMAL_PHASE | O.MINTIME, 1)
+    assert np.all(ng == 1)
+    assert np.allclose(xg, x0)  # the workload's control points are already inside the shrunk box
