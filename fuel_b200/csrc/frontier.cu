@@ -449,8 +449,9 @@ __global__ void cov_kernel(const int* __restrict__ k_cl, const int* __restrict__
   fx_add(&st[c].cyy_hi, &st[c].cyy_lo, dy * dy);
 }
 
-// Eigen 3.3 EigenSolver<Matrix2d> restated for a symmetric matrix (same procedure as
-// oracle/fuel_oracle.c orc_principal_axis_2x2; third-party convention, unpinned).
+// Eigen 3.3 EigenSolver<Matrix2d> restated for a symmetric matrix: RealSchur (findSmallSubdiagEntry,
+// splitOffTwoRows, JacobiRotation::makeGivens) + doComputeEigenvectors back-substitution
+// (third-party convention reconstructed from the published algorithm; unpinned).
 __device__ void make_givens(double p, double q, double* c, double* s) {
   if (q == 0.0) {
     *c = p < 0 ? -1.0 : 1.0;
