@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     # the B-spline cost and the PCA follow the reference's fp64 rounding sequence: no FMA contraction
     "-fmad=false",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + (["-DFUEL_PROF"] if os.environ.get("FUEL_PROF") else [])
 
 
 def _nvcc():

@@ -304,6 +304,11 @@ __device__ __forceinline__ void load_traj(const FuelTrajConst* __restrict__ tc, 
 
 // q[3]: this lane's control point (lanes >= n hold anything finite).  Returns f in every
 // lane, this lane's gradient row in gr[3] (zero for lanes >= n) and the dt-gradient in gdt.
+// FAST (the solver kernel): divisions by loop-invariant scalars become multiplications by
+// reciprocals computed once per evaluation, the ESDF gradient is normalised with rsqrt, and
+// the per-term warp reductions are merged into one (cost) + one (dt-gradient).  Same
+// mathematics, rounding differs in the last bits; the faithful variant backs cost_batch.
+template <bool FAST>
 __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict__ dist,
                                           const FuelOptParams& p, const TrajRegs& t,
                                           const FuelTrajConst* __restrict__ tc, int n, int mask,
@@ -314,6 +319,10 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
   double f = 0.0;
   gr[0] = gr[1] = gr[2] = 0.0;
   gdt = 0.0;
+  double f_lane = 0.0, gdt_lane = 0.0;  // FAST: per-lane partial sums, reduced once at the end
+  const double inv_pt = FAST ? 1.0 / t.pt_dist : 0.0;
+  const double dt_inv_f = FAST ? 1.0 / dt : 0.0;
+  const double inv2dt = 0.5 * dt_inv_f, invdt2 = dt_inv_f * dt_inv_f;
 
   // neighbours i+1..i+3
   double q1[3], q2[3], q3[3];
@@ -330,14 +339,19 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
     {
       double ji[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) ji[k] = (q3[k] - 3 * q2[k] + 3 * q1[k] - q[k]) / t.pt_dist;
+      for (int k = 0; k < 3; ++k) {
+        const double num = q3[k] - 3 * q2[k] + 3 * q1[k] - q[k];
+        ji[k] = FAST ? num * inv_pt : num / t.pt_dist;
+      }
       c = ji[0] * ji[0] + ji[1] * ji[1] + ji[2] * ji[2];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) tj[k] = v ? 2 * ji[k] / t.pt_dist : 0.0;
+      for (int k = 0; k < 3; ++k) tj[k] = v ? (FAST ? 2 * ji[k] * inv_pt : 2 * ji[k] / t.pt_dist) : 0.0;
       if (!v) c = 0.0;
     }
-    const double cost = wsum(c);
-    f += p.ld_smooth * cost;
+    if (FAST)
+      f_lane += p.ld_smooth * c;
+    else
+      f += p.ld_smooth * wsum(c);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const double t1 = up(tj[k], 1, lane), t2 = up(tj[k], 2, lane), t3 = up(tj[k], 3, lane);
@@ -354,11 +368,21 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
     if (act) {
       double dg[3];
       const double d = dev_dist_with_grad(g, dist, q, dg);
-      const double nrm = sqrt(dg[0] * dg[0] + dg[1] * dg[1] + dg[2] * dg[2]);
-      if (nrm > 1e-4) {
-        dg[0] /= nrm;
-        dg[1] /= nrm;
-        dg[2] /= nrm;
+      if (FAST) {
+        const double n2 = dg[0] * dg[0] + dg[1] * dg[1] + dg[2] * dg[2];
+        if (n2 > 1e-8) {
+          const double rn = rsqrt(n2);
+          dg[0] *= rn;
+          dg[1] *= rn;
+          dg[2] *= rn;
+        }
+      } else {
+        const double nrm = sqrt(dg[0] * dg[0] + dg[1] * dg[1] + dg[2] * dg[2]);
+        if (nrm > 1e-4) {
+          dg[0] /= nrm;
+          dg[1] /= nrm;
+          dg[2] /= nrm;
+        }
       }
       if (d < p.dist0) {
         c = (d - p.dist0) * (d - p.dist0);
@@ -366,12 +390,15 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
         for (int k = 0; k < 3; ++k) gq[k] += 2.0 * (d - p.dist0) * dg[k];
       }
     }
-    f += p.ld_dist * wsum(c);
+    if (FAST)
+      f_lane += p.ld_dist * c;
+    else
+      f += p.ld_dist * wsum(c);
 #pragma unroll
     for (int k = 0; k < 3; ++k) gr[k] += p.ld_dist * gq[k];
   }
   if (mask & FUELGPU_FEASIBILITY) {  // calcFeasibilityCost :308-353
-    const double dt_inv = 1 / dt;
+    const double dt_inv = FAST ? dt_inv_f : 1 / dt;
     const double dt_inv2 = dt_inv * dt_inv;
     double c = 0.0, gtl = 0.0;
     double tv[3], ta[3];
@@ -400,8 +427,14 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
         if (opt_time) gtl += ta[k] * ai * (-2) * dt;
       }
     }
-    f += p.ld_feasi * wsum(c);
-    const double gt = wsum(gtl);
+    double gt = 0.0;
+    if (FAST) {
+      f_lane += p.ld_feasi * c;
+      gdt_lane += p.ld_feasi * gtl;
+    } else {
+      f += p.ld_feasi * wsum(c);
+      gt = wsum(gtl);
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const double v1 = up(tv[k], 1, lane);
@@ -414,7 +447,7 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
       gq += ta[k];       //                    i = p  : gq[i]   += tmp
       gr[k] += p.ld_feasi * gq;
     }
-    if (opt_time) gdt += p.ld_feasi * gt;
+    if (opt_time && !FAST) gdt += p.ld_feasi * gt;
   }
   if (mask & FUELGPU_START) {  // calcStartCost :355-391
     double a[3], b[3], c3[3];
@@ -437,33 +470,33 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
       if (lane == 2) row[k] += w_pos * 2 * dq[k] * (1 / 6.0);
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) dq[k] = 1 / (2 * dt) * (c3[k] - a[k]) - t.start[1][k];
+    for (int k = 0; k < 3; ++k) dq[k] = (FAST ? inv2dt * (c3[k] - a[k]) : 1 / (2 * dt) * (c3[k] - a[k])) - t.start[1][k];
     cost += dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (lane == 0) row[k] += 2 * dq[k] * (-1.0) / (2 * dt);
-      if (lane == 2) row[k] += 2 * dq[k] * 1.0 / (2 * dt);
+      if (lane == 0) row[k] += (FAST ? 2 * dq[k] * (-1.0) * inv2dt : 2 * dq[k] * (-1.0) / (2 * dt));
+      if (lane == 2) row[k] += (FAST ? 2 * dq[k] * inv2dt : 2 * dq[k] * 1.0 / (2 * dt));
     }
     if (opt_time) {
       double d = 0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) d += dq[k] * (c3[k] - a[k]);
-      gt += d / (-dt * dt);
+      gt += FAST ? -d * invdt2 : d / (-dt * dt);
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) dq[k] = 1 / (dt * dt) * (a[k] - 2 * b[k] + c3[k]) - t.start[2][k];
+    for (int k = 0; k < 3; ++k) dq[k] = (FAST ? invdt2 * (a[k] - 2 * b[k] + c3[k]) : 1 / (dt * dt) * (a[k] - 2 * b[k] + c3[k])) - t.start[2][k];
     cost += dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (lane == 0) row[k] += 2 * dq[k] * 1.0 / (dt * dt);
-      if (lane == 1) row[k] += 2 * dq[k] * (-2.0) / (dt * dt);
-      if (lane == 2) row[k] += 2 * dq[k] * 1.0 / (dt * dt);
+      if (lane == 0) row[k] += (FAST ? 2 * dq[k] * invdt2 : 2 * dq[k] * 1.0 / (dt * dt));
+      if (lane == 1) row[k] += (FAST ? 2 * dq[k] * (-2.0) * invdt2 : 2 * dq[k] * (-2.0) / (dt * dt));
+      if (lane == 2) row[k] += (FAST ? 2 * dq[k] * invdt2 : 2 * dq[k] * 1.0 / (dt * dt));
     }
     if (opt_time) {
       double d = 0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) d += dq[k] * (a[k] - 2 * b[k] + c3[k]);
-      gt += d / (-dt * dt * dt);
+      gt += FAST ? -d * invdt2 * dt_inv_f : d / (-dt * dt * dt);
     }
     f += p.ld_start * cost;
     if (lane < 3) {
@@ -493,35 +526,35 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
     }
     if (t.n_end >= 2) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) dq[k] = 1 / (2 * dt) * (q_1[k] - q_3[k]) - t.end[1][k];
+      for (int k = 0; k < 3; ++k) dq[k] = (FAST ? inv2dt * (q_1[k] - q_3[k]) : 1 / (2 * dt) * (q_1[k] - q_3[k])) - t.end[1][k];
       cost += dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        if (lane == n - 1) row[k] += 2 * dq[k] * 1.0 / (2 * dt);
-        if (lane == n - 3) row[k] += 2 * dq[k] * (-1.0) / (2 * dt);
+        if (lane == n - 1) row[k] += (FAST ? 2 * dq[k] * inv2dt : 2 * dq[k] * 1.0 / (2 * dt));
+        if (lane == n - 3) row[k] += (FAST ? 2 * dq[k] * (-1.0) * inv2dt : 2 * dq[k] * (-1.0) / (2 * dt));
       }
       if (opt_time) {
         double d = 0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) d += dq[k] * (q_1[k] - q_3[k]);
-        gt += d / (-dt * dt);
+        gt += FAST ? -d * invdt2 : d / (-dt * dt);
       }
     }
     if (t.n_end == 3) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) dq[k] = 1 / (dt * dt) * (q_1[k] - 2 * q_2[k] + q_3[k]) - t.end[2][k];
+      for (int k = 0; k < 3; ++k) dq[k] = (FAST ? invdt2 * (q_1[k] - 2 * q_2[k] + q_3[k]) : 1 / (dt * dt) * (q_1[k] - 2 * q_2[k] + q_3[k])) - t.end[2][k];
       cost += dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        if (lane == n - 1) row[k] += 2 * dq[k] * 1.0 / (dt * dt);
-        if (lane == n - 2) row[k] += 2 * dq[k] * (-2.0) / (dt * dt);
-        if (lane == n - 3) row[k] += 2 * dq[k] * 1.0 / (dt * dt);
+        if (lane == n - 1) row[k] += (FAST ? 2 * dq[k] * invdt2 : 2 * dq[k] * 1.0 / (dt * dt));
+        if (lane == n - 2) row[k] += (FAST ? 2 * dq[k] * (-2.0) * invdt2 : 2 * dq[k] * (-2.0) / (dt * dt));
+        if (lane == n - 3) row[k] += (FAST ? 2 * dq[k] * invdt2 : 2 * dq[k] * 1.0 / (dt * dt));
       }
       if (opt_time) {
         double d = 0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) d += dq[k] * (q_1[k] - 2 * q_2[k] + q_3[k]);
-        gt += d / (-dt * dt * dt);
+        gt += FAST ? -d * invdt2 * dt_inv_f : d / (-dt * dt * dt);
       }
     }
     f += p.ld_end * cost;
@@ -541,7 +574,10 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
 #pragma unroll
       for (int k = 0; k < 3; ++k) gq[k] += 2 * d[k];
     }
-    f += p.ld_guide * wsum(c);
+    if (FAST)
+      f_lane += p.ld_guide * c;
+    else
+      f += p.ld_guide * wsum(c);
 #pragma unroll
     for (int k = 0; k < 3; ++k) gr[k] += p.ld_guide * gq[k];
   }
@@ -581,6 +617,16 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
     f += p.ld_time * cost;
     gdt += p.ld_time * gt;
   }
+  if (FAST) {
+    // one butterfly for both scalars (the two chains interleave)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      f_lane += __shfl_down_sync(0xffffffffu, f_lane, o);
+      gdt_lane += __shfl_down_sync(0xffffffffu, gdt_lane, o);
+    }
+    f += __shfl_sync(0xffffffffu, f_lane, 0);
+    if (opt_time) gdt += __shfl_sync(0xffffffffu, gdt_lane, 0);
+  }
   if (!act) gr[0] = gr[1] = gr[2] = 0.0;
   f_out = f;
 }
@@ -606,7 +652,7 @@ __global__ void __launch_bounds__(WPB * 32) cost_batch_warp_kernel(
   }
   const double dt = opt_time ? xb[nvar - 1] : t.knot_span;
   double fo, gr[3], gdt;
-  eval_warp(g, dist, p, t, tc + b, n, mask, q, dt, lane, fo, gr, gdt);
+  eval_warp<false>(g, dist, p, t, tc + b, n, mask, q, dt, lane, fo, gr, gdt);
   double* gb = grad + (int64_t)b * nvar;
   if (lane < n) {
     gb[3 * lane] = gr[0];
@@ -682,7 +728,7 @@ __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
   auto evaluate = [&](const V3& xx, double& fo, V3& go) {
     const double dtv = opt_time ? __shfl_sync(0xffffffffu, xx.v[0], n) : t.knot_span;
     double gr[3], gdt;
-    eval_warp(g, dist, p, t, tc + b, n, mask, xx.v, dtv, lane, fo, gr, gdt);
+    eval_warp<true>(g, dist, p, t, tc + b, n, mask, xx.v, dtv, lane, fo, gr, gdt);
     go.v[0] = is_pt ? gr[0] : (is_dt ? gdt : 0.0);
     go.v[1] = is_pt ? gr[1] : 0.0;
     go.v[2] = is_pt ? gr[2] : 0.0;

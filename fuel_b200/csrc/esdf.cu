@@ -30,13 +30,17 @@ __device__ __forceinline__ bool is_site(uint8_t o, int mode) {
 }
 
 // ---------------------------------------------------------------------------------------
-// z sweep: one warp per (x,y) line, <= 1024 voxels.  The line's site bits are gathered with
-// warp ballots (lane j keeps the 32-bit mask of chunk j), then every voxel finds its nearest
-// set bit on both sides with clz/ffs -- no per-voxel loop, fully coalesced byte loads.
-// out = squared distance along z (int32) or INF.
+// z sweep.  out = distance (in voxels, uint16) to the nearest site on the (x,y) line, 0xFFFF
+// if the line has none.  The 1-D pass needs no envelope: nearest set bit on each side.
 // ---------------------------------------------------------------------------------------
+constexpr unsigned short INF16 = 0xffffu;
+constexpr int BIG = 1 << 20;
+
+// generic box variant: one warp per line, <= 1024 voxels, any z range.  The line's site bits are
+// gathered with warp ballots (lane j keeps the 32-bit mask of chunk j), then every voxel finds
+// its nearest set bit on both sides with clz/ffs.
 __global__ void __launch_bounds__(256) zsweep_warp_kernel(const uint8_t* __restrict__ occ,
-                                                          int32_t* __restrict__ out, int ny, int nz,
+                                                          uint16_t* __restrict__ out, int ny, int nz,
                                                           Box b, int mode, int nlines) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -64,7 +68,6 @@ __global__ void __launch_bounds__(256) zsweep_warp_kernel(const uint8_t* __restr
   for (int i = 0; i < nchunks; ++i) {
     const unsigned m = __shfl_sync(0xffffffffu, mymask, i);
     const int pos = (i << 5) + lane;
-    // nearest site at or below pos
     const unsigned prev = nzb & ((1u << i) - 1u);
     const int pc = prev ? 31 - __clz(prev) : 0;
     const int plast = __shfl_sync(0xffffffffu, mylast, pc);
@@ -72,20 +75,95 @@ __global__ void __launch_bounds__(256) zsweep_warp_kernel(const uint8_t* __restr
     const int nc = next ? __ffs(next) - 1 : 0;
     const int nfirst = __shfl_sync(0xffffffffu, myfirst, nc);
 
-    int d = INF_I;
+    int d = BIG;
     const unsigned ml = m & (0xffffffffu >> (31 - lane));
     if (ml)
       d = lane - (31 - __clz(ml));
     else if (prev)
       d = pos - ((pc << 5) + plast);
     const unsigned mr = m & (0xffffffffu << lane);
-    int dr = INF_I;
+    int dr = BIG;
     if (mr)
       dr = (__ffs(mr) - 1) - lane;
     else if (next)
       dr = ((nc << 5) + nfirst) - pos;
     d = min(d, dr);
-    if (pos < n) out[base + pos] = (d == INF_I) ? INF_I : d * d;
+    if (pos < n) out[base + pos] = (d >= BIG) ? INF16 : (uint16_t)d;
+  }
+}
+
+// full-line variant (box spans the whole z axis, nz % VPL == 0, nz <= 32*VPL): one warp per
+// line, lane L owns VPL consecutive voxels, loaded with ONE vector load per lane (the whole line
+// is one coalesced request) and written with vector stores.  Nearest site outside the lane's
+// own voxels comes from a ballot over "lane has a site" + two shuffles.
+template <int VPL>
+struct VecT;
+template <>
+struct VecT<16> { using T = uint4; };
+template <>
+struct VecT<8> { using T = uint2; };
+template <>
+struct VecT<4> { using T = uint32_t; };
+
+template <int VPL>
+__global__ void __launch_bounds__(256) zsweep_vec_kernel(const uint8_t* __restrict__ occ,
+                                                         uint16_t* __restrict__ out, int ny, int nz,
+                                                         Box b, int mode, int nlines) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= nlines) return;
+  const int nyb = b.hi[1] - b.lo[1] + 1;
+  const int x = b.lo[0] + warp / nyb;
+  const int y = b.lo[1] + warp % nyb;
+  const int64_t base = ((int64_t)x * ny + y) * nz;
+  const bool have = lane * VPL < nz;
+  using V = typename VecT<VPL>::T;
+  union {
+    V v;
+    uint8_t b8[VPL];
+  } u;
+  unsigned mask = 0;
+  if (have) {
+    u.v = __ldg(reinterpret_cast<const V*>(occ + base + lane * VPL));
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) mask |= is_site(u.b8[i], mode) ? (1u << i) : 0u;
+  }
+  const unsigned ball = __ballot_sync(0xffffffffu, mask != 0);
+  const int mylast = mask ? 31 - __clz(mask) : 0;
+  const int myfirst = mask ? __ffs(mask) - 1 : 0;
+  const unsigned pm = ball & ((1u << lane) - 1u);
+  const int pl = pm ? 31 - __clz(pm) : 0;
+  const int plast = __shfl_sync(0xffffffffu, mylast, pl);
+  const unsigned nm = ball & ~((2u << lane) - 1u);
+  const int nl = nm ? __ffs(nm) - 1 : 0;
+  const int nfirst = __shfl_sync(0xffffffffu, myfirst, nl);
+  if (!have) return;
+  // distance from "one before my first voxel" to the nearest site on the left, and from "one
+  // past my last voxel" to the nearest on the right
+  int dl = pm ? (VPL * lane - 1) - (VPL * pl + plast) : BIG;
+  int dr = nm ? (VPL * nl + nfirst) - (VPL * lane + VPL) : BIG;
+  int dleft[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    dl = ((mask >> i) & 1u) ? 0 : dl + 1;
+    dleft[i] = dl;
+  }
+  union {
+    uint4 q[VPL / 8 > 0 ? VPL / 8 : 1];
+    uint16_t h[VPL < 8 ? 8 : VPL];
+  } o;
+#pragma unroll
+  for (int i = VPL - 1; i >= 0; --i) {
+    dr = ((mask >> i) & 1u) ? 0 : dr + 1;
+    const int d = min(dleft[i], dr);
+    o.h[i] = d >= BIG ? INF16 : (uint16_t)d;
+  }
+  uint16_t* dst = out + base + lane * VPL;
+  if (VPL >= 8) {
+#pragma unroll
+    for (int j = 0; j < VPL / 8; ++j) reinterpret_cast<uint4*>(dst)[j] = o.q[j];
+  } else {
+    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(o.h);
   }
 }
 
@@ -94,11 +172,14 @@ __global__ void __launch_bounds__(256) zsweep_warp_kernel(const uint8_t* __restr
 // access of a warp is a contiguous run.  Felzenszwalb-Huttenlocher lower envelope restated
 // in exact integers: parabola of site v has height h(v) = f(v) + v^2; the abscissa where w
 // overtakes u is (h(w)-h(u)) / (2(w-u)); all comparisons are cross-multiplied, no division.
-// The hull stack lives in `stk` (same layout as the volume, slot k of a line at the line's
-// k-th element); the two topmost entries are cached in registers.
+// Loads of the line are issued U at a time before any of them is consumed, so each thread
+// keeps U requests in flight (a single dependent load per warp is latency-, not
+// bandwidth-bound).  The hull stack (slot k of a line at the line's k-th element) lives in
+// `stk`; the x sweep aliases it on its own input, whose slots <= q are dead once read.
+// The two topmost entries are cached in registers.
 // Stack entry = v (10 bits) | h (22 bits): requires n <= 1024 per axis.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_vh(int v, int h) { return ((uint32_t)v << 22) | (uint32_t)h; }
+__device__ __forceinline__ uint32_t pack_vh(int v, int h) { return ((uint32_t)v << 22) + (uint32_t)h; }  // one LEA
 __device__ __forceinline__ int unpack_v(uint32_t e) { return (int)(e >> 22); }
 __device__ __forceinline__ int unpack_h(uint32_t e) { return (int)(e & 0x3fffffu); }
 
@@ -111,85 +192,155 @@ struct LineMap {
   int64_t base;     // element offset of line (0,0), sample 0
 };
 
-template <bool FINAL>
-__global__ void __launch_bounds__(128) envelope_kernel(const int32_t* __restrict__ in,
-                                                       void* __restrict__ outv,
-                                                       uint32_t* __restrict__ stk, LineMap lm,
-                                                       float res) {
+constexpr int ENV_U = 8;
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));  // <= 1 ulp-ish; the bar is 1e-4 relative
+  return r;
+}
+
+// IN16: input is the uint16 1-D distance of the z sweep (squared on load); else int32 squared.
+// All addressing is by running byte pointers (one 64-bit add per step) -- the kernel is
+// issue-bound, so index*stride multiplies in the inner loops are what it cannot afford.
+template <bool IN16, bool FINAL>
+__global__ void __launch_bounds__(128) envelope_kernel(const void* inv, void* outv, uint32_t* stk,
+                                                       LineMap lm, float res) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)lm.nz_run * lm.n_outer) return;
   const int zi = (int)(t % lm.nz_run);
   const int oi = (int)(t / lm.nz_run);
   const int64_t off0 = lm.base + (int64_t)oi * lm.outer_stride + zi;
   const int n = lm.n;
-  const int64_t S = lm.stride;
+  constexpr int ISZ = IN16 ? 2 : 4;
+  const int64_t SBi = lm.stride * ISZ;  // byte strides
+  const int64_t SB = lm.stride * 4;
+  const char* pin = (const char*)inv + off0 * ISZ;
+  char* const stk0 = (char*)(stk + off0);  // slot 0
+  char* ptop = stk0 - SB;                  // slot k (k = -1: empty)
 
   int k = -1;
-  int v1 = 0, h1 = 0, v0 = 0, h0 = 0;
-  for (int q = 0; q < n; ++q) {
-    const int f = in[off0 + q * S];
-    if (f >= INF_I) continue;
-    const int h = f + q * q;
-    while (k >= 1) {
-      // pop while  s(top,q) <= s(second,top)
-      const long long lhs = (long long)(h - h1) * (long long)(v1 - v0);
-      const long long rhs = (long long)(h1 - h0) * (long long)(q - v1);
-      if (lhs > rhs) break;
-      --k;
-      v1 = v0;
-      h1 = h0;
-      if (k >= 1) {
-        const uint32_t e = stk[off0 + (int64_t)(k - 1) * S];
-        v0 = unpack_v(e);
-        h0 = unpack_h(e);
+  // top (v1,h1) and the differences to the entry below it: dv = v1-v0, dh = h1-h0
+  int v1 = 0, h1 = 0, dv = 0, dh = 0;
+  for (int q0 = 0; q0 < n; q0 += ENV_U) {
+    int fb[ENV_U];
+    {
+      const char* pl = pin;
+#pragma unroll
+      for (int u = 0; u < ENV_U; ++u) {
+        int f = INF_I;
+        if (q0 + u < n) {
+          if (IN16) {
+            const int d = *(const uint16_t*)pl;
+            f = d == INF16 ? INF_I : d * d;
+          } else {
+            f = *(const int32_t*)pl;
+          }
+        }
+        fb[u] = f;
+        pl += SBi;
+      }
+      pin = pl;
+    }
+#pragma unroll
+    for (int u = 0; u < ENV_U; ++u) {
+      const int q = q0 + u;
+      const int f = fb[u];
+      if (f < INF_I) {
+        const int h = f + q * q;
+        while (k >= 1) {
+          // pop while  s(top,q) <= s(second,top):  (h-h1)*(v1-v0) <= (h1-h0)*(q-v1)
+          const long long lhs = (long long)(h - h1) * (long long)dv;
+          const long long rhs = (long long)dh * (long long)(q - v1);
+          if (lhs > rhs) break;
+          --k;
+          v1 -= dv;  // = v0
+          h1 -= dh;  // = h0
+          ptop -= SB;
+          if (k >= 1) {
+            const uint32_t e = *(const uint32_t*)(ptop - SB);
+            dv = v1 - unpack_v(e);
+            dh = h1 - unpack_h(e);
+          }
+        }
+        ++k;
+        ptop += SB;
+        *(uint32_t*)ptop = pack_vh(q, h);
+        dv = q - v1;
+        dh = h - h1;
+        v1 = q;
+        h1 = h;
       }
     }
-    ++k;
-    stk[off0 + (int64_t)k * S] = pack_vh(q, h);
-    v0 = v1;
-    h0 = h1;
-    v1 = q;
-    h1 = h;
   }
   const int kmax = k;
 
-  int32_t* outi = (int32_t*)outv;
-  float* outf = (float*)outv;
+  char* pout = (char*)outv + off0 * 4;
   if (kmax < 0) {
     for (int q = 0; q < n; ++q) {
       if (FINAL)
-        outf[off0 + q * S] = __int_as_float(0x7f800000);
+        *(float*)pout = __int_as_float(0x7f800000);
       else
-        outi[off0 + q * S] = INF_I;
+        *(int32_t*)pout = INF_I;
+      pout += SB;
     }
     return;
   }
-  int kc = 0;
-  uint32_t e = stk[off0];
+  // Query, driven by the hull instead of by q: entries are read ENV_U at a time (independent
+  // loads), and each entry emits every q it owns before the next one takes over.  Parabola
+  // `nxt` takes over from `cur` at the first integer q with (hn-hc) < 2q(vn-vc).
+  // val(q) = (q-vc)^2 + f(vc) is carried incrementally: val(q+1) = val(q) + 2(q-vc) + 1.
+  uint32_t e = *(const uint32_t*)stk0;
   int vc = unpack_v(e), hc = unpack_h(e);
-  int vn = 0, hn = 0;
-  if (kmax >= 1) {
-    e = stk[off0 + S];
-    vn = unpack_v(e);
-    hn = unpack_h(e);
-  }
-  for (int q = 0; q < n; ++q) {
-    // advance while the next parabola's take-over abscissa is < q
-    while (kc < kmax && (hn - hc) < 2 * q * (vn - vc)) {
-      ++kc;
-      vc = vn;
-      hc = hn;
-      if (kc < kmax) {
-        e = stk[off0 + (int64_t)(kc + 1) * S];
-        vn = unpack_v(e);
-        hn = unpack_h(e);
+  int q = 0;
+  const char* ps = stk0 + SB;  // slot 1
+  for (int kb = 1; kb <= kmax; kb += ENV_U) {
+    uint32_t eb[ENV_U];
+    {
+      const char* pl = ps;
+#pragma unroll
+      for (int u = 0; u < ENV_U; ++u) {
+        eb[u] = (kb + u <= kmax) ? *(const uint32_t*)pl : 0u;
+        pl += SB;
+      }
+      ps = pl;
+    }
+#pragma unroll
+    for (int u = 0; u < ENV_U; ++u) {
+      if (kb + u <= kmax) {
+        const int vn = unpack_v(eb[u]), hn = unpack_h(eb[u]);
+        const int dh = hn - hc, dv2 = 2 * (vn - vc);
+        int val = hc + q * (q - 2 * vc);
+        int inc = 2 * (q - vc) + 1;
+        int lim = q * dv2;
+        while (q < n && dh >= lim) {
+          if (FINAL)
+            *(float*)pout = res * fast_sqrt((float)val);
+          else
+            *(int32_t*)pout = val;
+          pout += SB;
+          val += inc;
+          inc += 2;
+          lim += dv2;
+          ++q;
+        }
+        vc = vn;
+        hc = hn;
       }
     }
-    const int val = hc + q * q - 2 * q * vc;  // (q-vc)^2 + f(vc)
-    if (FINAL)
-      outf[off0 + q * S] = res * sqrtf((float)val);
-    else
-      outi[off0 + q * S] = val;
+  }
+  {
+    int val = hc + q * (q - 2 * vc);
+    int inc = 2 * (q - vc) + 1;
+    for (; q < n; ++q) {
+      if (FINAL)
+        *(float*)pout = res * fast_sqrt((float)val);
+      else
+        *(int32_t*)pout = val;
+      pout += SB;
+      val += inc;
+      inc += 2;
+    }
   }
 }
 
@@ -224,13 +375,23 @@ int run_three_pass(cudaStream_t s, const uint8_t* occ, int32_t* g1, int32_t* g2,
                    float* out, int nx, int ny, int nz, const Box& b, int mode, float res) {
   (void)nx;
   const int nxb = b.hi[0] - b.lo[0] + 1, nyb = b.hi[1] - b.lo[1] + 1, nzb = b.hi[2] - b.lo[2] + 1;
+  uint16_t* g1h = (uint16_t*)g1;
   // z sweep
   {
     const int nlines = nxb * nyb;
     const int wpb = 8;
-    zsweep_warp_kernel<<<(nlines + wpb - 1) / wpb, wpb * 32, 0, s>>>(occ, g1, ny, nz, b, mode, nlines);
+    const unsigned grid = (nlines + wpb - 1) / wpb;
+    const bool full = b.lo[2] == 0 && nzb == nz;
+    if (full && nz % 16 == 0 && nz <= 512 && nz > 128)
+      zsweep_vec_kernel<16><<<grid, wpb * 32, 0, s>>>(occ, g1h, ny, nz, b, mode, nlines);
+    else if (full && nz % 8 == 0 && nz <= 256 && nz > 64)
+      zsweep_vec_kernel<8><<<grid, wpb * 32, 0, s>>>(occ, g1h, ny, nz, b, mode, nlines);
+    else if (full && nz % 4 == 0 && nz <= 128)
+      zsweep_vec_kernel<4><<<grid, wpb * 32, 0, s>>>(occ, g1h, ny, nz, b, mode, nlines);
+    else
+      zsweep_warp_kernel<<<grid, wpb * 32, 0, s>>>(occ, g1h, ny, nz, b, mode, nlines);
   }
-  // y sweep: lines (x,z)
+  // y sweep: lines (x,z); uint16 distances in, int32 squared 2-D distances out
   {
     LineMap lm;
     lm.n = nyb;
@@ -240,9 +401,9 @@ int run_three_pass(cudaStream_t s, const uint8_t* occ, int32_t* g1, int32_t* g2,
     lm.outer_stride = (int64_t)ny * nz;
     lm.base = ((int64_t)b.lo[0] * ny + b.lo[1]) * nz + b.lo[2];
     const int64_t nl = (int64_t)nzb * nxb;
-    envelope_kernel<false><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g1, g2, stk, lm, res);
+    envelope_kernel<true, false><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g1h, g2, stk, lm, res);
   }
-  // x sweep: lines (y,z), writes metres
+  // x sweep: lines (y,z), writes metres; the hull stack reuses the dead slots of its own input
   {
     LineMap lm;
     lm.n = nxb;
@@ -252,7 +413,7 @@ int run_three_pass(cudaStream_t s, const uint8_t* occ, int32_t* g1, int32_t* g2,
     lm.outer_stride = nz;
     lm.base = ((int64_t)b.lo[0] * ny + b.lo[1]) * nz + b.lo[2];
     const int64_t nl = (int64_t)nzb * nyb;
-    envelope_kernel<true><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g2, out, stk, lm, res);
+    envelope_kernel<false, true><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g2, out, (uint32_t*)g2, lm, res);
   }
   return 0;
 }
@@ -409,7 +570,7 @@ int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl,
   lm.outer_stride = nzl;
   lm.base = 0;
   const int64_t nl2 = (int64_t)nzl * ny;
-  envelope_kernel<false><<<(unsigned)((nl2 + 127) / 128), 128, 0, s>>>(g1, g2, stk, lm, 0.f);
+  envelope_kernel<false, false><<<(unsigned)((nl2 + 127) / 128), 128, 0, s>>>(g1, g2, stk, lm, 0.f);
   return cudaGetLastError() == cudaSuccess ? 0 : FUELGPU_ECUDA;
 }
 

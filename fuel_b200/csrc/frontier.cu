@@ -21,8 +21,12 @@
 //   5. level-synchronous PCA split of all clusters at once.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -99,8 +103,8 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_kernel(Geom g, FParams fp,
 }
 
 // exclusive scan of n ints by one CTA of 1024 threads (n up to a few million)
-__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int* __restrict__ out,
-                                                    int n, int* __restrict__ total) {
+__device__ void block_scan(const int* __restrict__ in, int* __restrict__ out, int n,
+                           int* __restrict__ total) {
   __shared__ int sh[1024];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -122,6 +126,93 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, 
     __syncthreads();
   }
   if (threadIdx.x == 0 && total) *total = carry;
+  __syncthreads();
+}
+__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                    int n, int* __restrict__ total) {
+  block_scan(in, out, n, total);
+}
+
+// two exclusive scans at once (both sums < 2^16 are packed in one int): n <= 32768
+__device__ void block_scan_small(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ total);
+__device__ void block_scan_small2(const int* __restrict__ ina, const int* __restrict__ inb, int* __restrict__ outa,
+                                  int* __restrict__ outb, int n, int* __restrict__ tota, int* __restrict__ totb) {
+  __shared__ unsigned wtot[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int chunk = (n + 1023) / 1024;
+  const int b0 = t * chunk, b1 = min(b0 + chunk, n);
+  unsigned s = 0;
+  for (int i = b0; i < b1; ++i) s += ((unsigned)ina[i] << 16) + (unsigned)inb[i];
+  unsigned inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) wtot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    const unsigned v = wtot[lane];
+    unsigned vi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, vi, o);
+      if (lane >= o) vi += u;
+    }
+    wtot[lane] = vi - v;
+    if (lane == 31) {
+      *tota = (int)(vi >> 16);
+      *totb = (int)(vi & 0xffffu);
+    }
+  }
+  __syncthreads();
+  unsigned run = wtot[w] + inc - s;
+  for (int i = b0; i < b1; ++i) {
+    const unsigned v = ((unsigned)ina[i] << 16) + (unsigned)inb[i];
+    outa[i] = (int)(run >> 16);
+    outb[i] = (int)(run & 0xffffu);
+    run += v;
+  }
+  __syncthreads();
+}
+
+// exclusive scan of a short array (n <= 32 * 1024) by one CTA: every thread owns a contiguous
+// chunk, chunk sums are scanned with two levels of warp shuffles.
+__device__ void block_scan_small(const int* __restrict__ in, int* __restrict__ out, int n,
+                                 int* __restrict__ total) {
+  __shared__ int wtot[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int chunk = (n + 1023) / 1024;
+  const int b0 = t * chunk, b1 = min(b0 + chunk, n);
+  int s = 0;
+  for (int i = b0; i < b1; ++i) s += in[i];
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) wtot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int v = wtot[lane];
+    int vi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, vi, o);
+      if (lane >= o) vi += u;
+    }
+    wtot[lane] = vi - v;  // exclusive warp offsets
+    if (lane == 31 && total) *total = vi;
+  }
+  __syncthreads();
+  int run = wtot[w] + inc - s;
+  for (int i = b0; i < b1; ++i) {
+    const int v = in[i];
+    out[i] = run;
+    run += v;
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(CLS_BLOCK) compact_kernel(Geom g, FParams fp,
@@ -130,7 +221,7 @@ __global__ void __launch_bounds__(CLS_BLOCK) compact_kernel(Geom g, FParams fp,
                                                             const int* __restrict__ blockoff,
                                                             int* __restrict__ cell_addr,
                                                             uint8_t* __restrict__ cell_cls,
-                                                            int* __restrict__ cellidx, int64_t ndom) {
+                                                            int* __restrict__ cellidx, int64_t ndom, int cap) {
   const int64_t L = (int64_t)blockIdx.x * CLS_BLOCK + threadIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned mE = 0, mS = 0;
@@ -146,6 +237,7 @@ __global__ void __launch_bounds__(CLS_BLOCK) compact_kernel(Geom g, FParams fp,
   for (int i = 0; i < w; ++i) woff += wsum[i];
   if ((m >> lane) & 1u) {
     const int idx = blockoff[blockIdx.x] + woff + __popc(m & ((1u << lane) - 1u));
+    if (idx >= cap) return;  // small-path capacity exceeded: the caller falls back and recompacts
     const int z = fp.dom_lo[2] + (int)(L % fp.dom_n[2]);
     const int y = fp.dom_lo[1] + (int)((L / fp.dom_n[2]) % fp.dom_n[1]);
     const int x = fp.dom_lo[0] + (int)(L / ((int64_t)fp.dom_n[2] * fp.dom_n[1]));
@@ -157,7 +249,20 @@ __global__ void __launch_bounds__(CLS_BLOCK) compact_kernel(Geom g, FParams fp,
 }
 
 // ---- 2. union-find over E cells, 26-connectivity -----------------------------------------
-__device__ __forceinline__ int uf_find(const int* parent, int i) {
+// find with path halving.  The plain stores race benignly with the atomicMin hooks: a parent
+// entry is only ever replaced by another member of the same set with a smaller index, so the
+// pointers stay acyclic and the component minimum stays the root.
+__device__ __forceinline__ int uf_find(int* parent, int i) {
+  int p = parent[i];
+  while (p != i) {
+    const int gp = parent[p];
+    if (gp != p) parent[i] = gp;
+    i = p;
+    p = gp;
+  }
+  return i;
+}
+__device__ __forceinline__ int uf_find_ro(const int* parent, int i) {
   int p = parent[i];
   while (p != i) {
     i = p;
@@ -181,8 +286,8 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-__global__ void init_parent_kernel(int* parent, int* claim, int* csize, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void init_parent_item(int* parent, int* claim, int* csize, int n, int _tid) {
+  const int i = _tid;
   if (i < n) {
     parent[i] = i;
     claim[i] = NONE;
@@ -197,36 +302,47 @@ __device__ __forceinline__ void addr_to_idx(const Geom& g, int a, int& x, int& y
   x = r / g.ny;
 }
 
-__global__ void union_kernel(Geom g, const int* __restrict__ cell_addr,
+__device__ __forceinline__ void union_item(Geom g, const int* __restrict__ cell_addr,
                              const uint8_t* __restrict__ cell_cls, const int* __restrict__ cellidx,
-                             int* parent, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                             int* parent, int n, int _tid) {
+  const int i = _tid;
   if (i >= n || cell_cls[i] != 1) return;
   int x, y, z;
   addr_to_idx(g, cell_addr[i], x, y, z);
-  // the 13 neighbours with smaller address
+  // the 13 neighbours with smaller address: all lookups are issued before any is consumed
+  int jn[13];
+  int t = 0;
+#pragma unroll
   for (int dx = -1; dx <= 0; ++dx)
+#pragma unroll
     for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
       for (int dz = -1; dz <= 1; ++dz) {
         if (dx == 0 && (dy > 0 || (dy == 0 && dz >= 0))) continue;
         const int X = x + dx, Y = y + dy, Z = z + dz;
-        if (X < 0 || Y < 0 || Z < 0 || Y >= g.ny || Z >= g.nz) continue;
-        const int j = cellidx[addr_of(g, X, Y, Z)];
-        if (j >= 0 && cell_cls[j] == 1) uf_union(parent, i, j);
+        const bool ok = !(X < 0 || Y < 0 || Z < 0 || Y >= g.ny || Z >= g.nz);
+        jn[t++] = ok ? cellidx[addr_of(g, X, Y, Z)] : -1;
       }
+#pragma unroll
+  for (int q = 0; q < 13; ++q) {
+    const int j = jn[q];
+    jn[q] = (j >= 0 && cell_cls[j] == 1) ? j : -1;
+  }
+#pragma unroll
+  for (int q = 0; q < 13; ++q)
+    if (jn[q] >= 0) uf_union(parent, i, jn[q]);
 }
-
-__global__ void flatten_kernel(int* parent, const uint8_t* __restrict__ cell_cls, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void flatten_item(int* parent, const uint8_t* __restrict__ cell_cls, int n, int _tid) {
+  const int i = _tid;
   if (i >= n || cell_cls[i] != 1) return;
-  parent[i] = uf_find(parent, i);
+  parent[i] = uf_find_ro(parent, i);
 }
 
 // ---- 3. claimers ----------------------------------------------------------------------------
-__global__ void claim_kernel(Geom g, FParams fp, const int* __restrict__ cell_addr,
+__device__ __forceinline__ void claim_item(Geom g, FParams fp, const int* __restrict__ cell_addr,
                              const uint8_t* __restrict__ cell_cls, const int* __restrict__ cellidx,
-                             const int* __restrict__ label, int* claim, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                             const int* __restrict__ label, int* claim, int n, int _tid) {
+  const int i = _tid;
   if (i >= n) return;
   int x, y, z;
   addr_to_idx(g, cell_addr[i], x, y, z);
@@ -248,10 +364,10 @@ __global__ void claim_kernel(Geom g, FParams fp, const int* __restrict__ cell_ad
 }
 
 // ---- 4. cluster id (= seed cell index) per cell, sizes, flags --------------------------------
-__global__ void assign_kernel(const int* __restrict__ cell_addr, const uint8_t* __restrict__ cell_cls,
+__device__ __forceinline__ void assign_item(const int* __restrict__ cell_addr, const uint8_t* __restrict__ cell_cls,
                               const int* __restrict__ label, const int* __restrict__ claim,
-                              int* __restrict__ seed, int* csize, int8_t* __restrict__ flag, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                              int* __restrict__ seed, int* csize, int8_t* __restrict__ flag, int n, int _tid) {
+  const int i = _tid;
   if (i >= n) return;
   const int s = cell_cls[i] == 1 ? claim[label[i]] : i;
   seed[i] = s;
@@ -262,9 +378,9 @@ __global__ void assign_kernel(const int* __restrict__ cell_addr, const uint8_t* 
 }
 
 // per cell: 1 if it is the seed of a kept cluster (for the rank scan), and kept-cell marks
-__global__ void mark_kernel(const int* __restrict__ seed, const int* __restrict__ csize, int cluster_min,
-                            int* __restrict__ is_root, int* __restrict__ is_kept, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void mark_item(const int* __restrict__ seed, const int* __restrict__ csize, int cluster_min,
+                            int* __restrict__ is_root, int* __restrict__ is_kept, int n, int _tid) {
+  const int i = _tid;
   if (i >= n) return;
   const int s = seed[i];
   const bool kept = s != NONE && csize[s] > cluster_min;  // expanded.size() > cluster_min_ (:157)
@@ -272,17 +388,17 @@ __global__ void mark_kernel(const int* __restrict__ seed, const int* __restrict_
   is_root[i] = (kept && s == i) ? 1 : 0;
 }
 
-__global__ void reset_cellidx_kernel(const int* __restrict__ cell_addr, int* __restrict__ cellidx, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void reset_cellidx_item(const int* __restrict__ cell_addr, int* __restrict__ cellidx, int n, int _tid) {
+  const int i = _tid;
   if (i < n) cellidx[cell_addr[i]] = -1;
 }
 
 // kept cells -> dense arrays; cellidx now maps voxel -> kept index
-__global__ void gather_kept_kernel(const int* __restrict__ cell_addr, const int* __restrict__ seed,
+__device__ __forceinline__ void gather_kept_item(const int* __restrict__ cell_addr, const int* __restrict__ seed,
                                    const int* __restrict__ is_kept, const int* __restrict__ kept_off,
                                    const int* __restrict__ root_rank, int* __restrict__ k_addr,
-                                   int* __restrict__ k_cl, int* __restrict__ cellidx, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                   int* __restrict__ k_cl, int* __restrict__ cellidx, int n, int _tid) {
+  const int i = _tid;
   if (i >= n) return;
   if (is_kept[i]) {
     const int k = kept_off[i];
@@ -318,8 +434,8 @@ struct ClusterStat {  // per cluster, rebuilt every level while the cluster is a
 };
 
 
-__global__ void stat_reset_kernel(ClusterStat* st, const ClusterMeta* __restrict__ meta, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void stat_reset_item(ClusterStat* st, const ClusterMeta* __restrict__ meta, int C, int _tid) {
+  const int c = _tid;
   if (c >= C || !meta[c].active) return;  // finished clusters keep their last statistics
   ClusterStat s;
   memset(&s, 0, sizeof(s));
@@ -328,32 +444,45 @@ __global__ void stat_reset_kernel(ClusterStat* st, const ClusterMeta* __restrict
   st[c] = s;
 }
 
-__global__ void stat_accum_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
-                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  const int c = k_cl[k];
-  if (!meta[c].active) return;
-  int x, y, z;
-  addr_to_idx(g, k_addr[k], x, y, z);
+__device__ __forceinline__ void stat_accum_item(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K, int _tid) {
+  // Cells arrive in address order, so the lanes of a warp mostly share a cluster: lanes with the
+  // same cluster id are reduced in-warp (match_any + reduce_sync) and ONE lane issues the atomics.
+  // All sums are exact integers -> the result does not depend on the grouping.
+  const int k = _tid;
+  int c = -1, x = 0, y = 0, z = 0;
+  if (k < K) {
+    c = k_cl[k];
+    if (!meta[c].active)
+      c = -1;
+    else
+      addr_to_idx(g, k_addr[k], x, y, z);
+  }
+  const unsigned act = __activemask();
+  const unsigned grp = __match_any_sync(act, c);
+  if (c < 0) return;
+  const int sx = __reduce_add_sync(grp, x), sy = __reduce_add_sync(grp, y), sz = __reduce_add_sync(grp, z);
+  const int lx = __reduce_min_sync(grp, x), ly = __reduce_min_sync(grp, y), lz = __reduce_min_sync(grp, z);
+  const int hx = __reduce_max_sync(grp, x), hy = __reduce_max_sync(grp, y), hz = __reduce_max_sync(grp, z);
+  if ((int)(threadIdx.x & 31) != __ffs(grp) - 1) return;
   ClusterStat* s = &st[c];
-  atomicAdd((unsigned long long*)&s->sx, (unsigned long long)x);
-  atomicAdd((unsigned long long*)&s->sy, (unsigned long long)y);
-  atomicAdd((unsigned long long*)&s->sz, (unsigned long long)z);
-  atomicAdd(&s->n, 1);
-  atomicMin(&s->lo[0], x);
-  atomicMin(&s->lo[1], y);
-  atomicMin(&s->lo[2], z);
-  atomicMax(&s->hi[0], x);
-  atomicMax(&s->hi[1], y);
-  atomicMax(&s->hi[2], z);
+  atomicAdd((unsigned long long*)&s->sx, (unsigned long long)sx);
+  atomicAdd((unsigned long long*)&s->sy, (unsigned long long)sy);
+  atomicAdd((unsigned long long*)&s->sz, (unsigned long long)sz);
+  atomicAdd(&s->n, __popc(grp));
+  atomicMin(&s->lo[0], lx);
+  atomicMin(&s->lo[1], ly);
+  atomicMin(&s->lo[2], lz);
+  atomicMax(&s->hi[0], hx);
+  atomicMax(&s->hi[1], hy);
+  atomicMax(&s->hi[2], hz);
 }
 
 // average_ of computeFrontierInfo (:376-386).  The reference sums positions sequentially in
 // fp64; here the index sums are exact integers and the mean is formed once (differs from
 // the sequential sum by rounding only, ~1e-16 relative).
-__global__ void mean_kernel(Geom g, ClusterMeta* meta, const ClusterStat* __restrict__ st, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void mean_item(Geom g, ClusterMeta* meta, const ClusterStat* __restrict__ st, int C, int _tid) {
+  const int c = _tid;
   if (c >= C || !meta[c].active) return;
   const ClusterStat& s = st[c];
   const double inv = 1.0 / (double)s.n;
@@ -374,11 +503,11 @@ __device__ __forceinline__ int leaf_coord(const Geom& g, const FParams& fp, int 
 // PCL VoxelGrid restated per cell: the min-address cell of every occupied leaf computes the
 // leaf centroid (float accumulation in ascending address order) and contributes to the split
 // test (:183-189) and the covariance (:194-200).
-__global__ void downsample_kernel(Geom g, FParams fp, const int* __restrict__ k_addr,
+__device__ __forceinline__ void downsample_item(Geom g, FParams fp, const int* __restrict__ k_addr,
                                   const int* __restrict__ k_cl, const int* __restrict__ cellidx,
                                   const ClusterMeta* __restrict__ meta, ClusterStat* st,
-                                  float* __restrict__ k_cent, int* __restrict__ k_leaf, int K) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+                                  float* __restrict__ k_cent, int* __restrict__ k_leaf, int K, int _tid) {
+  const int k = _tid;
   if (k >= K) return;
   const int c = k_cl[k];
   if (!meta[c].active) return;
@@ -399,20 +528,40 @@ __global__ void downsample_kernel(Geom g, FParams fp, const int* __restrict__ k_
     while (lo[a] - 1 >= 0 && lo[a] - 1 >= s.lo[a] && leaf_coord(g, fp, lo[a] - 1, a, min_b[a]) == lc[a]) --lo[a];
     while (hi[a] + 1 < nmax[a] && hi[a] + 1 <= s.hi[a] && leaf_coord(g, fp, hi[a] + 1, a, min_b[a]) == lc[a]) ++hi[a];
   }
-  // ascending address order over the leaf's voxels
+  // The leaf's voxels in ascending address order (a leaf spans at most 4 voxels per axis).  All
+  // cellidx lookups are issued first, then all cluster-id lookups (two memory round trips
+  // instead of one per voxel), then the float accumulation runs in the reference order.
+  int jj[64];
+#pragma unroll
+  for (int dx = 0; dx < 4; ++dx)
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+      for (int dz = 0; dz < 4; ++dz) {
+        const int x = lo[0] + dx, y = lo[1] + dy, z = lo[2] + dz;
+        const bool ok = x <= hi[0] && y <= hi[1] && z <= hi[2];
+        jj[(dx * 4 + dy) * 4 + dz] = ok ? cellidx[addr_of(g, x, y, z)] : -1;
+      }
+#pragma unroll
+  for (int v = 0; v < 64; ++v) {
+    const int j = jj[v];
+    jj[v] = (j >= 0 && k_cl[j] == c) ? j : -1;
+  }
   float sum[3] = { 0.f, 0.f, 0.f };
   int cnt = 0;
-  for (int x = lo[0]; x <= hi[0]; ++x)
-    for (int y = lo[1]; y <= hi[1]; ++y)
-      for (int z = lo[2]; z <= hi[2]; ++z) {
-        const int j = cellidx[addr_of(g, x, y, z)];
-        if (j < 0 || k_cl[j] != c) continue;
-        if (cnt == 0 && j != k) return;  // a smaller-address cell owns this leaf
-        sum[0] += cell_posf(g, x, 0);
-        sum[1] += cell_posf(g, y, 1);
-        sum[2] += cell_posf(g, z, 2);
-        ++cnt;
-      }
+  bool owner = true;
+#pragma unroll
+  for (int v = 0; v < 64; ++v) {
+    const int j = jj[v];
+    if (j >= 0 && owner) {
+      if (cnt == 0 && j != k) owner = false;  // a smaller-address cell owns this leaf
+      sum[0] += cell_posf(g, lo[0] + v / 16, 0);
+      sum[1] += cell_posf(g, lo[1] + (v / 4) % 4, 1);
+      sum[2] += cell_posf(g, lo[2] + v % 4, 2);
+      ++cnt;
+    }
+  }
+  if (!owner) return;
   const float fc = (float)cnt;
   const float cx = sum[0] / fc, cy = sum[1] / fc, cz = sum[2] / fc;
   k_cent[3 * k] = cx;
@@ -435,10 +584,10 @@ __device__ __forceinline__ double fx_get(long long hi, long long lo) {
   return (double)hi * (1.0 / 1048576.0) + (double)lo * (1.0 / 4835703278458516698824704.0);
 }
 
-__global__ void cov_kernel(const int* __restrict__ k_cl, const int* __restrict__ k_leaf,
+__device__ __forceinline__ void cov_item(const int* __restrict__ k_cl, const int* __restrict__ k_leaf,
                            const float* __restrict__ k_cent, const ClusterMeta* __restrict__ meta,
-                           ClusterStat* st, int K) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+                           ClusterStat* st, int K, int _tid) {
+  const int k = _tid;
   if (k >= K) return;
   const int c = k_cl[k];
   if (!meta[c].active || k_leaf[k] < 0 || !st[c].need_split) return;
@@ -533,8 +682,8 @@ __device__ void principal_axis_2x2(double a, double b, double d, double pc[2]) {
   pc[1] = max_idx == 0 ? v0[1] : v1[1];
 }
 
-__global__ void pca_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pca_item(ClusterMeta* meta, const ClusterStat* __restrict__ st, int C, int _tid) {
+  const int c = _tid;
   if (c >= C || !meta[c].active) return;
   const ClusterStat& s = st[c];
   meta[c].do_split = 0;
@@ -555,9 +704,9 @@ __device__ __forceinline__ int cell_side(const Geom& g, const ClusterMeta& mt, i
   return d >= 0 ? 0 : 1;
 }
 
-__global__ void side_count_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
-                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void side_count_item(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K, int _tid) {
+  const int k = _tid;
   if (k >= K) return;
   const int c = k_cl[k];
   if (!meta[c].active || !meta[c].do_split) return;
@@ -569,8 +718,8 @@ __global__ void side_count_kernel(Geom g, const int* __restrict__ k_addr, const 
 
 // decide splits, allocate ids for the ftr2 halves, update metadata.  Single thread block
 // scan over clusters keeps ids deterministic.
-__global__ void __launch_bounds__(1024) split_alloc_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st,
-                                                           int C, int* __restrict__ n_new) {
+__device__ void split_alloc(ClusterMeta* meta, const ClusterStat* __restrict__ st, int C,
+                            int* __restrict__ n_new) {
   __shared__ int sh[1024];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -613,29 +762,244 @@ __global__ void __launch_bounds__(1024) split_alloc_kernel(ClusterMeta* meta, co
   }
   if (threadIdx.x == 0) *n_new = carry;
 }
+__global__ void __launch_bounds__(1024) split_alloc_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st,
+                                                           int C, int* __restrict__ n_new) {
+  split_alloc(meta, st, C, n_new);
+}
 
-__global__ void relabel_kernel(Geom g, const int* __restrict__ k_addr, int* __restrict__ k_cl,
-                               const ClusterMeta* __restrict__ meta, int K, int C_old) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void relabel_item(Geom g, const int* __restrict__ k_addr, int* __restrict__ k_cl,
+                               const ClusterMeta* __restrict__ meta, int K, int C_old, int _tid) {
+  const int k = _tid;
   if (k >= K) return;
   const int c = k_cl[k];
   if (c >= C_old || !meta[c].do_split) return;
   if (cell_side(g, meta[c], k_addr[k]) == 1) k_cl[k] = meta[c].new_id;
 }
 
-__global__ void clear_do_split_kernel(ClusterMeta* meta, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void clear_do_split_item(ClusterMeta* meta, int C, int _tid) {
+  const int c = _tid;
   if (c < C) meta[c].do_split = 0;
 }
 
-__global__ void init_meta_kernel(ClusterMeta* meta, int R) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void init_meta_item(ClusterMeta* meta, int R, int _tid) {
+  const int c = _tid;
   if (c >= R) return;
   ClusterMeta m;
   memset(&m, 0, sizeof(m));
   m.root = c;
   m.active = 1;
   meta[c] = m;
+}
+
+// ---- grid-stride wrappers of the per-item functions (large inputs) ----
+__global__ void init_parent_kernel(int* parent, int* claim, int* csize, int n) {
+  init_parent_item(parent, claim, csize, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void union_kernel(Geom g, const int* __restrict__ cell_addr,
+                             const uint8_t* __restrict__ cell_cls, const int* __restrict__ cellidx,
+                             int* parent, int n) {
+  union_item(g, cell_addr, cell_cls, cellidx, parent, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void flatten_kernel(int* parent, const uint8_t* __restrict__ cell_cls, int n) {
+  flatten_item(parent, cell_cls, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void claim_kernel(Geom g, FParams fp, const int* __restrict__ cell_addr,
+                             const uint8_t* __restrict__ cell_cls, const int* __restrict__ cellidx,
+                             const int* __restrict__ label, int* claim, int n) {
+  claim_item(g, fp, cell_addr, cell_cls, cellidx, label, claim, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void assign_kernel(const int* __restrict__ cell_addr, const uint8_t* __restrict__ cell_cls,
+                              const int* __restrict__ label, const int* __restrict__ claim,
+                              int* __restrict__ seed, int* csize, int8_t* __restrict__ flag, int n) {
+  assign_item(cell_addr, cell_cls, label, claim, seed, csize, flag, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void mark_kernel(const int* __restrict__ seed, const int* __restrict__ csize, int cluster_min,
+                            int* __restrict__ is_root, int* __restrict__ is_kept, int n) {
+  mark_item(seed, csize, cluster_min, is_root, is_kept, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void reset_cellidx_kernel(const int* __restrict__ cell_addr, int* __restrict__ cellidx, int n) {
+  reset_cellidx_item(cell_addr, cellidx, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void gather_kept_kernel(const int* __restrict__ cell_addr, const int* __restrict__ seed,
+                                   const int* __restrict__ is_kept, const int* __restrict__ kept_off,
+                                   const int* __restrict__ root_rank, int* __restrict__ k_addr,
+                                   int* __restrict__ k_cl, int* __restrict__ cellidx, int n) {
+  gather_kept_item(cell_addr, seed, is_kept, kept_off, root_rank, k_addr, k_cl, cellidx, n, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void stat_reset_kernel(ClusterStat* st, const ClusterMeta* __restrict__ meta, int C) {
+  stat_reset_item(st, meta, C, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void stat_accum_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K) {
+  stat_accum_item(g, k_addr, k_cl, meta, st, K, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void mean_kernel(Geom g, ClusterMeta* meta, const ClusterStat* __restrict__ st, int C) {
+  mean_item(g, meta, st, C, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void downsample_kernel(Geom g, FParams fp, const int* __restrict__ k_addr,
+                                  const int* __restrict__ k_cl, const int* __restrict__ cellidx,
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st,
+                                  float* __restrict__ k_cent, int* __restrict__ k_leaf, int K) {
+  downsample_item(g, fp, k_addr, k_cl, cellidx, meta, st, k_cent, k_leaf, K, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void cov_kernel(const int* __restrict__ k_cl, const int* __restrict__ k_leaf,
+                           const float* __restrict__ k_cent, const ClusterMeta* __restrict__ meta,
+                           ClusterStat* st, int K) {
+  cov_item(k_cl, k_leaf, k_cent, meta, st, K, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void pca_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st, int C) {
+  pca_item(meta, st, C, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void side_count_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K) {
+  side_count_item(g, k_addr, k_cl, meta, st, K, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void relabel_kernel(Geom g, const int* __restrict__ k_addr, int* __restrict__ k_cl,
+                               const ClusterMeta* __restrict__ meta, int K, int C_old) {
+  relabel_item(g, k_addr, k_cl, meta, K, C_old, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void clear_do_split_kernel(ClusterMeta* meta, int C) {
+  clear_do_split_item(meta, C, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void init_meta_kernel(ClusterMeta* meta, int R) {
+  init_meta_item(meta, R, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+
+// ---- small inputs: the whole clustering + split in ONE single-CTA launch --------------------
+// Per-search work on a room-sized map is a few thousand frontier cells: every phase is far
+// below one launch latency, so the multi-kernel pipeline is pure launch + host-sync overhead.
+// Here one CTA of 1024 threads runs all phases back to back with __syncthreads() in between
+// and iterates the split levels on the device.  Same per-item functions as the large path.
+constexpr int SMALL_CTAS = 8;      // one thread-block cluster (portable maximum)
+constexpr int SMALL_CAP = 32768;   // candidate cells
+constexpr int SMALL_CCAP = 8192;   // clusters (incl. split products)
+
+struct SmallBufs {
+  int *cell_addr, *parent, *claim, *csize, *seed, *is_root, *is_kept, *root_rank, *kept_off;
+  uint8_t* cell_cls;
+  int *k_addr, *k_cl, *k_leaf;
+  float* k_cent;
+  ClusterMeta* meta;
+  ClusterStat* stat;
+  int* counters;  // [0] n_cand (in) [1] R [2] K [3] n_new [4] status [5] C
+};
+
+__global__ void __cluster_dims__(SMALL_CTAS, 1, 1) __launch_bounds__(1024) cluster_small_kernel(Geom g, FParams fp, int8_t* __restrict__ flag,
+                                                             int* __restrict__ cellidx, SmallBufs b) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = rank * 1024 + threadIdx.x;
+  constexpr int NT = 1024 * SMALL_CTAS;
+  const int n = b.counters[0];
+#ifdef FUEL_PROF
+  long long* prof = (long long*)(b.counters + 8);
+  int pi = 0;
+#define STAMP() do { if (tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); prof[pi++] = t_; } } while (0)
+#else
+#define STAMP() do {} while (0)
+#endif
+  STAMP();
+  if (n > SMALL_CAP) {
+    if (tid == 0) b.counters[4] = 1;
+    return;  // uniform over the whole cluster
+  }
+#define FOR_ITEMS(i, N) for (int i = tid; i - tid < (N); i += NT)  // uniform trip count per warp
+  FOR_ITEMS(i, n) init_parent_item(b.parent, b.claim, b.csize, n, i);
+  cluster.sync();
+  STAMP();
+  FOR_ITEMS(i, n) union_item(g, b.cell_addr, b.cell_cls, cellidx, b.parent, n, i);
+  cluster.sync();
+  STAMP();
+  FOR_ITEMS(i, n) flatten_item(b.parent, b.cell_cls, n, i);
+  cluster.sync();
+  STAMP();
+  FOR_ITEMS(i, n) claim_item(g, fp, b.cell_addr, b.cell_cls, cellidx, b.parent, b.claim, n, i);
+  cluster.sync();
+  STAMP();
+  FOR_ITEMS(i, n) assign_item(b.cell_addr, b.cell_cls, b.parent, b.claim, b.seed, b.csize, flag, n, i);
+  cluster.sync();
+  STAMP();
+  FOR_ITEMS(i, n) mark_item(b.seed, b.csize, fp.cluster_min, b.is_root, b.is_kept, n, i);
+  cluster.sync();
+  STAMP();
+  if (rank == 0) {
+    block_scan_small2(b.is_root, b.is_kept, b.root_rank, b.kept_off, n, b.counters + 1, b.counters + 2);
+  }
+  cluster.sync();
+  STAMP();
+  const int R = b.counters[1], K = b.counters[2];
+  int C = R;
+  int status = 0;
+  if (R > 0 && K > 0) {
+    FOR_ITEMS(i, n) gather_kept_item(b.cell_addr, b.seed, b.is_kept, b.kept_off, b.root_rank, b.k_addr, b.k_cl,
+                                     cellidx, n, i);
+    FOR_ITEMS(c, R) init_meta_item(b.meta, R, c);
+    cluster.sync();
+  STAMP();
+    for (int level = 0; level < 40; ++level) {
+      if (2 * C > SMALL_CCAP) {
+        status = 2;
+        break;
+      }
+      FOR_ITEMS(c, C) stat_reset_item(b.stat, b.meta, C, c);
+      cluster.sync();
+  STAMP();
+      FOR_ITEMS(k, K) stat_accum_item(g, b.k_addr, b.k_cl, b.meta, b.stat, K, k);
+      cluster.sync();
+  STAMP();
+      FOR_ITEMS(c, C) mean_item(g, b.meta, b.stat, C, c);
+      cluster.sync();
+  STAMP();
+      FOR_ITEMS(k, K) downsample_item(g, fp, b.k_addr, b.k_cl, cellidx, b.meta, b.stat, b.k_cent, b.k_leaf, K, k);
+      cluster.sync();
+  STAMP();
+      FOR_ITEMS(k, K) cov_item(b.k_cl, b.k_leaf, b.k_cent, b.meta, b.stat, K, k);
+      cluster.sync();
+  STAMP();
+      FOR_ITEMS(c, C) pca_item(b.meta, b.stat, C, c);
+      cluster.sync();
+  STAMP();
+      FOR_ITEMS(k, K) side_count_item(g, b.k_addr, b.k_cl, b.meta, b.stat, K, k);
+      cluster.sync();
+  STAMP();
+      if (rank == 0) split_alloc(b.meta, b.stat, C, b.counters + 3);
+      cluster.sync();
+  STAMP();
+      FOR_ITEMS(k, K) relabel_item(g, b.k_addr, b.k_cl, b.meta, K, C, k);
+      cluster.sync();
+  STAMP();
+      const int n_new = b.counters[3];
+      if (n_new == 0) break;
+      FOR_ITEMS(c, C) clear_do_split_item(b.meta, C, c);
+      C += n_new;
+      cluster.sync();
+  STAMP();
+    }
+  }
+  FOR_ITEMS(i, n) reset_cellidx_item(b.cell_addr, cellidx, n, i);
+  if (tid == 0) {
+    b.counters[4] = status;
+    b.counters[5] = C;
+  }
+#undef FOR_ITEMS
 }
 
 __global__ void is_changed_kernel(Geom g, const uint8_t* __restrict__ occ, const int* __restrict__ offs,
@@ -703,7 +1067,8 @@ struct FrontierState {
   DevBuf<float> k_cent;
   DevBuf<ClusterStat> stat;
   DevBuf<ClusterMeta> meta;
-  int* d_counters = nullptr;  // [0] n_cand [1] n_roots [2] n_kept [3] n_new
+  bool small_ready = false;
+  int* d_counters = nullptr;  // [0] n_cand [1] n_roots [2] n_kept [3] n_new [4] small-path status [5] C
   // results of the last search (host side, CSR)
   std::vector<int32_t> h_cell_off, h_cell_addr, h_filt_off;
   std::vector<double> h_filtered, h_avg, h_bmin, h_bmax;
@@ -713,7 +1078,8 @@ int frontier_state_create(FuelMap* m) {
   m->fs = new FrontierState();
   FUEL_CUDA(m, cudaMalloc(&m->fs->cellidx, sizeof(int) * m->nvox));
   FUEL_CUDA(m, cudaMemsetAsync(m->fs->cellidx, 0xff, sizeof(int) * m->nvox, m->stream));
-  FUEL_CUDA(m, cudaMalloc(&m->fs->d_counters, sizeof(int) * 8));
+  FUEL_CUDA(m, cudaMalloc(&m->fs->d_counters, sizeof(int) * 8 + sizeof(long long) * 256));
+  FUEL_CUDA(m, cudaMemsetAsync(m->fs->d_counters, 0, sizeof(int) * 8 + sizeof(long long) * 256, m->stream));
   return 0;
 }
 
@@ -737,6 +1103,82 @@ void frontier_state_destroy(FuelMap* m) {
   } while (0)
 
 static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+static int frontier_marshal(FuelMap* m, int K, int C, int32_t* n_clusters, int32_t* n_cells,
+                            int32_t* n_filtered) {
+  FrontierState* f = m->fs;
+  const Geom& g = m->g;
+  cudaStream_t s = m->stream;
+  // ---- download and marshal into CSR (ordering only; no geometry is decided here) ------
+  std::vector<int> h_addr(K), h_cl(K), h_leaf(K);
+  std::vector<float> h_cent((size_t)3 * K);
+  std::vector<ClusterMeta> h_meta(C);
+  std::vector<ClusterStat> h_stat(C);
+  FUEL_CUDA(m, cudaMemcpyAsync(h_addr.data(), f->k_addr.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_cl.data(), f->k_cl.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_leaf.data(), f->k_leaf.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_cent.data(), f->k_cent.p, sizeof(float) * 3 * K, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_meta.data(), f->meta.p, sizeof(ClusterMeta) * C, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_stat.data(), f->stat.p, sizeof(ClusterStat) * C, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaStreamSynchronize(s));
+
+  // cluster order: (root, path) lexicographic = the reference's in-place list replacement
+  std::vector<int> order(C);
+  for (int c = 0; c < C; ++c) order[c] = c;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    if (h_meta[a].root != h_meta[b].root) return h_meta[a].root < h_meta[b].root;
+    return h_meta[a].path < h_meta[b].path;
+  });
+  std::vector<int> rank(C);
+  for (int i = 0; i < C; ++i) rank[order[i]] = i;
+
+  f->h_cell_off.assign(C + 1, 0);
+  f->h_filt_off.assign(C + 1, 0);
+  for (int k = 0; k < K; ++k) {
+    f->h_cell_off[rank[h_cl[k]] + 1]++;
+    if (h_leaf[k] >= 0) f->h_filt_off[rank[h_cl[k]] + 1]++;
+  }
+  for (int c = 0; c < C; ++c) {
+    f->h_cell_off[c + 1] += f->h_cell_off[c];
+    f->h_filt_off[c + 1] += f->h_filt_off[c];
+  }
+  f->h_cell_addr.resize(K);
+  const int NF = f->h_filt_off[C];
+  std::vector<std::pair<int, int>> filt_keys(NF);  // (leaf, kept index) per slot
+  {
+    std::vector<int> cur(f->h_cell_off.begin(), f->h_cell_off.end() - 1);
+    std::vector<int> curf(f->h_filt_off.begin(), f->h_filt_off.end() - 1);
+    for (int k = 0; k < K; ++k) {  // k ascending = address ascending (stable)
+      const int r = rank[h_cl[k]];
+      f->h_cell_addr[cur[r]++] = h_addr[k];
+      if (h_leaf[k] >= 0) filt_keys[curf[r]++] = std::make_pair(h_leaf[k], k);
+    }
+  }
+  f->h_filtered.resize((size_t)3 * NF);
+  for (int c = 0; c < C; ++c) {
+    // VoxelGrid emits centroids in ascending leaf index
+    std::sort(filt_keys.begin() + f->h_filt_off[c], filt_keys.begin() + f->h_filt_off[c + 1]);
+    for (int i = f->h_filt_off[c]; i < f->h_filt_off[c + 1]; ++i) {
+      const int k = filt_keys[i].second;
+      for (int a = 0; a < 3; ++a) f->h_filtered[(size_t)3 * i + a] = (double)h_cent[(size_t)3 * k + a];
+    }
+  }
+  f->h_avg.resize((size_t)3 * C);
+  f->h_bmin.resize((size_t)3 * C);
+  f->h_bmax.resize((size_t)3 * C);
+  for (int c = 0; c < C; ++c) {
+    const int r = rank[c];
+    for (int a = 0; a < 3; ++a) {
+      f->h_avg[(size_t)3 * r + a] = h_meta[c].mean[a];
+      f->h_bmin[(size_t)3 * r + a] = (h_stat[c].lo[a] + 0.5) * g.res + g.origin[a];
+      f->h_bmax[(size_t)3 * r + a] = (h_stat[c].hi[a] + 0.5) * g.res + g.origin[a];
+    }
+  }
+  *n_clusters = C;
+  *n_cells = K;
+  *n_filtered = NF;
+  return 0;
+}
 
 int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
                          const FuelFrontierParams* p, int32_t* n_clusters, int32_t* n_cells,
@@ -805,9 +1247,42 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   scan_kernel<<<1, 1024, 0, s>>>(f->blockcnt.p, f->blockoff.p, (int)nb, f->d_counters + 0);
   m->launches += 1;
   int n_cand = 0;
-  FUEL_CUDA(m, cudaMemcpyAsync(&n_cand, f->d_counters, sizeof(int), cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaStreamSynchronize(s));
-  if (n_cand == 0) return 0;
+  // ---- small path: one compaction + ONE single-CTA launch, one host sync ------------------------
+  {
+    ENSURE(f->cell_addr, SMALL_CAP); ENSURE(f->cell_cls, SMALL_CAP); ENSURE(f->parent, SMALL_CAP);
+    ENSURE(f->claim, SMALL_CAP); ENSURE(f->csize, SMALL_CAP); ENSURE(f->seed, SMALL_CAP);
+    ENSURE(f->is_root, SMALL_CAP); ENSURE(f->is_kept, SMALL_CAP); ENSURE(f->root_rank, SMALL_CAP);
+    ENSURE(f->kept_off, SMALL_CAP); ENSURE(f->k_addr, SMALL_CAP); ENSURE(f->k_cl, SMALL_CAP);
+    ENSURE(f->k_leaf, SMALL_CAP); ENSURE(f->k_cent, (size_t)3 * SMALL_CAP);
+    ENSURE(f->meta, SMALL_CCAP); ENSURE(f->stat, SMALL_CCAP);
+    compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p,
+                                            f->cell_cls.p, f->cellidx, ndom, SMALL_CAP);
+    SmallBufs sb;
+    sb.cell_addr = f->cell_addr.p; sb.parent = f->parent.p; sb.claim = f->claim.p; sb.csize = f->csize.p;
+    sb.seed = f->seed.p; sb.is_root = f->is_root.p; sb.is_kept = f->is_kept.p; sb.root_rank = f->root_rank.p;
+    sb.kept_off = f->kept_off.p; sb.cell_cls = f->cell_cls.p; sb.k_addr = f->k_addr.p; sb.k_cl = f->k_cl.p;
+    sb.k_leaf = f->k_leaf.p; sb.k_cent = f->k_cent.p; sb.meta = f->meta.p; sb.stat = f->stat.p;
+    sb.counters = f->d_counters;
+    cluster_small_kernel<<<SMALL_CTAS, 1024, 0, s>>>(g, fp, m->flag, f->cellidx, sb);
+    m->launches += 2;
+    int cnt[8];
+    FUEL_CUDA(m, cudaMemcpyAsync(cnt, f->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, s));
+    FUEL_CUDA(m, cudaStreamSynchronize(s));
+    n_cand = cnt[0];
+    if (n_cand == 0) return 0;
+    if (cnt[4] == 0) {
+      const int R = cnt[1], K = cnt[2], C = cnt[5];
+      if (R == 0 || K == 0) return 0;
+      return frontier_marshal(m, K, C, n_clusters, n_cells, n_filtered);
+    }
+    // capacity exceeded (status 1: cells, 2: clusters): fall through to the multi-kernel path.
+    // Flags written so far are the same ones it will write; cellidx was reset by the kernel
+    // (status 2) or never touched beyond the cap (status 1: reset what compaction wrote).
+    if (cnt[4] == 1) {
+      reset_cellidx_kernel<<<nblk(SMALL_CAP, 256), 256, 0, s>>>(f->cell_addr.p, f->cellidx, SMALL_CAP);
+      m->launches += 1;
+    }
+  }
 
   ENSURE(f->cell_addr, n_cand); ENSURE(f->cell_cls, n_cand); ENSURE(f->parent, n_cand);
   ENSURE(f->claim, n_cand); ENSURE(f->csize, n_cand); ENSURE(f->seed, n_cand);
@@ -815,7 +1290,7 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   ENSURE(f->kept_off, n_cand);
 
   compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p,
-                                          f->cell_cls.p, f->cellidx, ndom);
+                                          f->cell_cls.p, f->cellidx, ndom, n_cand);
   m->launches += 1;
   const unsigned cb = nblk(n_cand, 256);
   init_parent_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->claim.p, f->csize.p, n_cand);
@@ -891,78 +1366,10 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
     C += n_new;
   }
 
-  // ---- download and marshal into CSR (ordering only; no geometry is decided here) ------
-  std::vector<int> h_addr(K), h_cl(K), h_leaf(K);
-  std::vector<float> h_cent((size_t)3 * K);
-  std::vector<ClusterMeta> h_meta(C);
-  std::vector<ClusterStat> h_stat(C);
-  FUEL_CUDA(m, cudaMemcpyAsync(h_addr.data(), f->k_addr.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_cl.data(), f->k_cl.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_leaf.data(), f->k_leaf.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_cent.data(), f->k_cent.p, sizeof(float) * 3 * K, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_meta.data(), f->meta.p, sizeof(ClusterMeta) * C, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_stat.data(), f->stat.p, sizeof(ClusterStat) * C, cudaMemcpyDeviceToHost, s));
   reset_cellidx_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cellidx, n_cand);
   m->launches += 1;
   FUEL_CUDA(m, cudaGetLastError());
-  FUEL_CUDA(m, cudaStreamSynchronize(s));
-
-  // cluster order: (root, path) lexicographic = the reference's in-place list replacement
-  std::vector<int> order(C);
-  for (int c = 0; c < C; ++c) order[c] = c;
-  std::sort(order.begin(), order.end(), [&](int a, int b) {
-    if (h_meta[a].root != h_meta[b].root) return h_meta[a].root < h_meta[b].root;
-    return h_meta[a].path < h_meta[b].path;
-  });
-  std::vector<int> rank(C);
-  for (int i = 0; i < C; ++i) rank[order[i]] = i;
-
-  f->h_cell_off.assign(C + 1, 0);
-  f->h_filt_off.assign(C + 1, 0);
-  for (int k = 0; k < K; ++k) {
-    f->h_cell_off[rank[h_cl[k]] + 1]++;
-    if (h_leaf[k] >= 0) f->h_filt_off[rank[h_cl[k]] + 1]++;
-  }
-  for (int c = 0; c < C; ++c) {
-    f->h_cell_off[c + 1] += f->h_cell_off[c];
-    f->h_filt_off[c + 1] += f->h_filt_off[c];
-  }
-  f->h_cell_addr.resize(K);
-  const int NF = f->h_filt_off[C];
-  std::vector<std::pair<int, int>> filt_keys(NF);  // (leaf, kept index) per slot
-  {
-    std::vector<int> cur(f->h_cell_off.begin(), f->h_cell_off.end() - 1);
-    std::vector<int> curf(f->h_filt_off.begin(), f->h_filt_off.end() - 1);
-    for (int k = 0; k < K; ++k) {  // k ascending = address ascending (stable)
-      const int r = rank[h_cl[k]];
-      f->h_cell_addr[cur[r]++] = h_addr[k];
-      if (h_leaf[k] >= 0) filt_keys[curf[r]++] = std::make_pair(h_leaf[k], k);
-    }
-  }
-  f->h_filtered.resize((size_t)3 * NF);
-  for (int c = 0; c < C; ++c) {
-    // VoxelGrid emits centroids in ascending leaf index
-    std::sort(filt_keys.begin() + f->h_filt_off[c], filt_keys.begin() + f->h_filt_off[c + 1]);
-    for (int i = f->h_filt_off[c]; i < f->h_filt_off[c + 1]; ++i) {
-      const int k = filt_keys[i].second;
-      for (int a = 0; a < 3; ++a) f->h_filtered[(size_t)3 * i + a] = (double)h_cent[(size_t)3 * k + a];
-    }
-  }
-  f->h_avg.resize((size_t)3 * C);
-  f->h_bmin.resize((size_t)3 * C);
-  f->h_bmax.resize((size_t)3 * C);
-  for (int c = 0; c < C; ++c) {
-    const int r = rank[c];
-    for (int a = 0; a < 3; ++a) {
-      f->h_avg[(size_t)3 * r + a] = h_meta[c].mean[a];
-      f->h_bmin[(size_t)3 * r + a] = (h_stat[c].lo[a] + 0.5) * g.res + g.origin[a];
-      f->h_bmax[(size_t)3 * r + a] = (h_stat[c].hi[a] + 0.5) * g.res + g.origin[a];
-    }
-  }
-  *n_clusters = C;
-  *n_cells = K;
-  *n_filtered = NF;
-  return 0;
+  return frontier_marshal(m, K, C, n_clusters, n_cells, n_filtered);
 }
 
 int frontier_fetch_impl(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr, int32_t* filt_offsets,
@@ -999,3 +1406,12 @@ int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const
   cudaFree(d_ch);
   return 0;
 }
+
+#ifdef FUEL_PROF
+// debug-only (FUEL_PROF builds): %globaltimer stamps taken after every cluster.sync()
+extern "C" __attribute__((visibility("default"))) int fuelgpu_debug_frontier_prof(FuelMap* m, long long* out,
+                                                                                  int n) {
+  cudaMemcpy(out, (long long*)(m->fs->d_counters + 8), sizeof(long long) * n, cudaMemcpyDeviceToHost);
+  return 0;
+}
+#endif

@@ -179,3 +179,19 @@ def test_empty_and_all_unknown(fuel, orc):
     for tri in (np.zeros(n, dtype=np.uint8), np.full(n, W.FREE, dtype=np.uint8)):
         gpu, gfl = run_gpu(fuel, g, inflate, tri, (0, 0, 0), (2, 2, 2), cluster_min=0)
         assert gpu == [] and not gfl.any()
+
+
+def test_large_scene_uses_multi_kernel_path(fuel, orc):
+    """More than 32768 candidate cells: the single-CTA small path overflows and the multi-kernel
+    path takes over; results must be identical to the oracle either way."""
+    n = (192, 160, 48)
+    origin = np.array([0.0, 0.0, 0.0])
+    g0 = W.Grid(n, origin, 0.1)
+    g = W.Grid(n, origin, 0.1, box_min=origin + 0.3, box_max=g0.map_max - 0.3)
+    inflate, tri = random_scene(n, 99, p_site=0.002, p_unknown=0.5, blobs=90)
+    kw = dict(cluster_min=30, cluster_size_xy=1.5, down_sample=3, min_z=0.4)
+    gpu, gfl = run_gpu(fuel, g, inflate, tri, origin, g0.map_max, **kw)
+    ref, rfl = run_orc(orc, g, tri, origin, g0.map_max, cell_order=1, **kw)
+    assert int(rfl.sum()) > 32768, int(rfl.sum())
+    assert_same(gpu, ref)
+    assert np.array_equal(gfl, rfl)
