@@ -1,0 +1,88 @@
+"""world_size-2 gloo test (CPU) of the z-sharded ESDF orchestration in fuel_b200/dist.py: slab
+shapes, the single z->x exchange, chunk assembly and the final all-gather.  The two CUDA
+entry points are replaced by CPU stand-ins (exact integer EDT passes in numpy) so that the
+N>1 host logic is exercised without a GPU; the result must equal the oracle's full-map ESDF."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+INF = 0x3FFFFFFF
+
+
+def edt1d_sq(f):
+    """exact 1-D squared-distance lower envelope of f (INF = no site) along axis 0, brute force"""
+    n = f.shape[0]
+    q = np.arange(n)
+    d2 = (q[:, None] - q[None, :]) ** 2  # [q, v]
+    fin = f < INF
+    big = np.where(fin, f, np.int64(1) << 40).astype(np.int64)
+    out = (d2[:, :, None] + big[None, :, :].reshape(1, n, -1)).min(axis=1)
+    return np.where(out >= (np.int64(1) << 39), INF, out).reshape(f.shape)
+
+
+def cpu_xy(occ):
+    o = occ.numpy()
+    site = (o & 4) != 0  # optimistic: inflate bit
+    f = np.where(site, 0, INF).astype(np.int64)
+    nx, ny, nz = f.shape
+    g = edt1d_sq(np.moveaxis(f, 1, 0).reshape(ny, -1)).reshape(ny, nx, nz)
+    g = np.moveaxis(g, 0, 1)
+    g = edt1d_sq(g.reshape(nx, -1)).reshape(nx, ny, nz)
+    return torch.from_numpy(g.astype(np.int32))
+
+
+def cpu_z(chunks, res):
+    c = chunks.numpy().astype(np.int64)
+    G, nxl, ny, nzl = c.shape
+    col = np.concatenate([c[s] for s in range(G)], axis=2)  # [nxl, ny, nz]
+    g = edt1d_sq(np.moveaxis(col, 2, 0).reshape(G * nzl, -1)).reshape(G * nzl, nxl, ny)
+    g = np.moveaxis(g, 0, 2)
+    out = np.where(g >= INF, np.inf, res * np.sqrt(g.astype(np.float64)))
+    return torch.from_numpy(out.astype(np.float32))
+
+
+def worker(rank, world, port, n, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fuel_b200.dist import ShardedESDF
+    rng = np.random.default_rng(5)  # same map on every rank
+    inflate = (rng.random(n) < 0.01).astype(np.uint8)
+    occ = torch.from_numpy((inflate << 2) | 1)
+    sh = ShardedESDF(n, 0.1, optimistic=True, xy_fn=cpu_xy, z_fn=lambda ch: cpu_z(ch, 0.1))
+    assert sh.z_range() == (rank * n[2] // world, (rank + 1) * n[2] // world)
+    slab = sh.shard_occupancy(occ)
+    assert slab.shape == (n[0], n[1], n[2] // world) and slab.is_contiguous()
+    part = sh.update(slab)
+    assert part.shape == (n[0] // world, n[1], n[2])
+    full = sh.gather_full(part)
+    ret[rank] = full.numpy()
+    dist.destroy_process_group()
+
+
+def test_z_sharded_esdf_two_ranks(orc):
+    n = (12, 10, 8)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(worker, args=(2, port, n, ret), nprocs=2, join=True)
+    rng = np.random.default_rng(5)
+    inflate = (rng.random(n) < 0.01).astype(np.int8)
+    g = orc.make_grid(n, 0.1, (0, 0, 0))
+    ref = orc.update_esdf3d(g, inflate, None, [0, 0, 0], np.array(n) - 1, True, False)
+    for r in (0, 1):
+        got = ret[r]
+        assert got.shape == n
+        assert np.allclose(got, ref, rtol=1e-6), "rank %d" % r
+    assert np.array_equal(ret[0], ret[1])
