@@ -192,7 +192,6 @@ struct LineMap {
   int64_t base;     // element offset of line (0,0), sample 0
 };
 
-constexpr int ENV_U = 8;
 
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;
@@ -203,7 +202,7 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 // IN16: input is the uint16 1-D distance of the z sweep (squared on load); else int32 squared.
 // All addressing is by running byte pointers (one 64-bit add per step) -- the kernel is
 // issue-bound, so index*stride multiplies in the inner loops are what it cannot afford.
-template <bool IN16, bool FINAL>
+template <bool IN16, bool FINAL, int ENV_U>
 __global__ void __launch_bounds__(128) envelope_kernel(const void* inv, void* outv, uint32_t* stk,
                                                        LineMap lm, float res) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,7 +400,7 @@ int run_three_pass(cudaStream_t s, const uint8_t* occ, int32_t* g1, int32_t* g2,
     lm.outer_stride = (int64_t)ny * nz;
     lm.base = ((int64_t)b.lo[0] * ny + b.lo[1]) * nz + b.lo[2];
     const int64_t nl = (int64_t)nzb * nxb;
-    envelope_kernel<true, false><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g1h, g2, stk, lm, res);
+    envelope_kernel<true, false, 16><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g1h, g2, stk, lm, res);
   }
   // x sweep: lines (y,z), writes metres; the hull stack reuses the dead slots of its own input
   {
@@ -413,7 +412,7 @@ int run_three_pass(cudaStream_t s, const uint8_t* occ, int32_t* g1, int32_t* g2,
     lm.outer_stride = nz;
     lm.base = ((int64_t)b.lo[0] * ny + b.lo[1]) * nz + b.lo[2];
     const int64_t nl = (int64_t)nzb * nyb;
-    envelope_kernel<false, true><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g2, out, (uint32_t*)g2, lm, res);
+    envelope_kernel<false, true, 8><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g2, out, (uint32_t*)g2, lm, res);
   }
   return 0;
 }
@@ -570,7 +569,7 @@ int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl,
   lm.outer_stride = nzl;
   lm.base = 0;
   const int64_t nl2 = (int64_t)nzl * ny;
-  envelope_kernel<false, false><<<(unsigned)((nl2 + 127) / 128), 128, 0, s>>>(g1, g2, stk, lm, 0.f);
+  envelope_kernel<false, false, 8><<<(unsigned)((nl2 + 127) / 128), 128, 0, s>>>(g1, g2, stk, lm, 0.f);
   return cudaGetLastError() == cudaSuccess ? 0 : FUELGPU_ECUDA;
 }
 

@@ -72,9 +72,12 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_kernel(Geom g, FParams fp,
   const int64_t L = (int64_t)blockIdx.x * CLS_BLOCK + threadIdx.x;
   bool isE = false, isS = false;
   if (L < ndom) {
-    const int z = fp.dom_lo[2] + (int)(L % fp.dom_n[2]);
-    const int y = fp.dom_lo[1] + (int)((L / fp.dom_n[2]) % fp.dom_n[1]);
-    const int x = fp.dom_lo[0] + (int)(L / ((int64_t)fp.dom_n[2] * fp.dom_n[1]));
+    const unsigned Lu = (unsigned)L;  // ndom < 2^31 (checked by the host)
+    const unsigned row = Lu / (unsigned)fp.dom_n[2];
+    const int z = fp.dom_lo[2] + (int)(Lu - row * (unsigned)fp.dom_n[2]);
+    const unsigned xr = row / (unsigned)fp.dom_n[1];
+    const int y = fp.dom_lo[1] + (int)(row - xr * (unsigned)fp.dom_n[1]);
+    const int x = fp.dom_lo[0] + (int)xr;
     if (flag[addr_of(g, x, y, z)] == 0 && frontier_pred(g, occ, x, y, z)) {
       const bool inbox = x >= g.box_min[0] && x < g.box_max[0] && y >= g.box_min[1] &&
                          y < g.box_max[1] && z >= g.box_min[2] && z < g.box_max[2];
@@ -131,6 +134,41 @@ __device__ void block_scan(const int* __restrict__ in, int* __restrict__ out, in
 __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int* __restrict__ out,
                                                     int n, int* __restrict__ total) {
   block_scan(in, out, n, total);
+}
+
+// large arrays: (a) every CTA scans its own 1024-element chunk, (b) one CTA scans the chunk totals,
+// (c) the chunk offsets are added back.
+__global__ void __launch_bounds__(1024) scan_chunks_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                           int n, int* __restrict__ chunk_tot) {
+  __shared__ int wtot[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int v = i < n ? in[i] : 0;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) wtot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    const int t = wtot[lane];
+    int ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    wtot[lane] = ti - t;
+    if (lane == 31) chunk_tot[blockIdx.x] = ti;
+  }
+  __syncthreads();
+  if (i < n) out[i] = wtot[w] + inc - v;
+}
+__global__ void __launch_bounds__(1024) scan_add_kernel(int* __restrict__ out, int n, const int* __restrict__ chunk_off) {
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  if (i < n) out[i] += chunk_off[blockIdx.x];
 }
 
 // two exclusive scans at once (both sums < 2^16 are packed in one int): n <= 32768
@@ -238,9 +276,12 @@ __global__ void __launch_bounds__(CLS_BLOCK) compact_kernel(Geom g, FParams fp,
   if ((m >> lane) & 1u) {
     const int idx = blockoff[blockIdx.x] + woff + __popc(m & ((1u << lane) - 1u));
     if (idx >= cap) return;  // small-path capacity exceeded: the caller falls back and recompacts
-    const int z = fp.dom_lo[2] + (int)(L % fp.dom_n[2]);
-    const int y = fp.dom_lo[1] + (int)((L / fp.dom_n[2]) % fp.dom_n[1]);
-    const int x = fp.dom_lo[0] + (int)(L / ((int64_t)fp.dom_n[2] * fp.dom_n[1]));
+    const unsigned Lu = (unsigned)L;  // ndom < 2^31 (checked by the host)
+    const unsigned row = Lu / (unsigned)fp.dom_n[2];
+    const int z = fp.dom_lo[2] + (int)(Lu - row * (unsigned)fp.dom_n[2]);
+    const unsigned xr = row / (unsigned)fp.dom_n[1];
+    const int y = fp.dom_lo[1] + (int)(row - xr * (unsigned)fp.dom_n[1]);
+    const int x = fp.dom_lo[0] + (int)xr;
     const int a = (int)addr_of(g, x, y, z);
     cell_addr[idx] = a;
     cell_cls[idx] = ((mE >> lane) & 1u) ? 1 : 2;  // 1 = E, 2 = S
@@ -707,13 +748,22 @@ __device__ __forceinline__ int cell_side(const Geom& g, const ClusterMeta& mt, i
 __device__ __forceinline__ void side_count_item(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
                                   const ClusterMeta* __restrict__ meta, ClusterStat* st, int K, int _tid) {
   const int k = _tid;
-  if (k >= K) return;
-  const int c = k_cl[k];
-  if (!meta[c].active || !meta[c].do_split) return;
-  if (cell_side(g, meta[c], k_addr[k]) == 0)
-    atomicAdd(&st[c].cnt0, 1);
-  else
-    atomicAdd(&st[c].cnt1, 1);
+  int c = -1, side = 0;
+  if (k < K) {
+    c = k_cl[k];
+    if (!meta[c].active || !meta[c].do_split)
+      c = -1;
+    else
+      side = cell_side(g, meta[c], k_addr[k]);
+  }
+  const unsigned act = __activemask();
+  const unsigned grp = __match_any_sync(act, c);
+  if (c < 0) return;
+  const int n1 = __reduce_add_sync(grp, side);
+  if ((int)(threadIdx.x & 31) != __ffs(grp) - 1) return;
+  const int n0 = __popc(grp) - n1;
+  if (n0) atomicAdd(&st[c].cnt0, n0);
+  if (n1) atomicAdd(&st[c].cnt1, n1);
 }
 
 // decide splits, allocate ids for the ftr2 halves, update metadata.  Single thread block
@@ -1060,7 +1110,7 @@ struct DevBuf {
 struct FrontierState {
   int* cellidx = nullptr;  // voxel -> cell index, -1 elsewhere (persistent, sparse use)
   DevBuf<uint32_t> maskE, maskS;
-  DevBuf<int> blockcnt, blockoff;
+  DevBuf<int> blockcnt, blockoff, scan_tot, scan_off;
   DevBuf<int> cell_addr, parent, claim, csize, seed, is_root, is_kept, root_rank, kept_off;
   DevBuf<uint8_t> cell_cls;
   DevBuf<int> k_addr, k_cl, k_leaf;
@@ -1068,6 +1118,8 @@ struct FrontierState {
   DevBuf<ClusterStat> stat;
   DevBuf<ClusterMeta> meta;
   bool small_ready = false;
+  char* h_pin = nullptr;  // pinned host staging for the result download
+  size_t h_pin_bytes = 0;
   int* d_counters = nullptr;  // [0] n_cand [1] n_roots [2] n_kept [3] n_new [4] small-path status [5] C
   // results of the last search (host side, CSR)
   std::vector<int32_t> h_cell_off, h_cell_addr, h_filt_off;
@@ -1088,7 +1140,9 @@ void frontier_state_destroy(FuelMap* m) {
   FrontierState* f = m->fs;
   if (f->cellidx) cudaFree(f->cellidx);
   if (f->d_counters) cudaFree(f->d_counters);
+  if (f->h_pin) cudaFreeHost(f->h_pin);
   f->maskE.release(); f->maskS.release(); f->blockcnt.release(); f->blockoff.release();
+  f->scan_tot.release(); f->scan_off.release();
   f->cell_addr.release(); f->parent.release(); f->claim.release(); f->csize.release();
   f->seed.release(); f->is_root.release(); f->is_kept.release(); f->root_rank.release();
   f->kept_off.release(); f->cell_cls.release(); f->k_addr.release(); f->k_cl.release();
@@ -1104,24 +1158,93 @@ void frontier_state_destroy(FuelMap* m) {
 
 static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
+// exclusive scan of n ints on the stream; `total` (device) receives the sum
+static int scan_ints(FuelMap* m, const int* in, int* out, int n, int* total) {
+  FrontierState* f = m->fs;
+  cudaStream_t s = m->stream;
+  if (n <= 4096) {
+    scan_kernel<<<1, 1024, 0, s>>>(in, out, n, total);
+    m->launches += 1;
+    return 0;
+  }
+  const int nchunk = (n + 1023) / 1024;
+  if (f->scan_tot.ensure(nchunk) || f->scan_off.ensure(nchunk))
+    return fuel_fail(m, FUELGPU_ENOMEM, "frontier: device allocation failed");
+  scan_chunks_kernel<<<nchunk, 1024, 0, s>>>(in, out, n, f->scan_tot.p);
+  scan_kernel<<<1, 1024, 0, s>>>(f->scan_tot.p, f->scan_off.p, nchunk, total);
+  scan_add_kernel<<<nchunk, 1024, 0, s>>>(out, n, f->scan_off.p);
+  m->launches += 3;
+  return 0;
+}
+
+struct HostView {  // result arrays in pinned host memory
+  const int *addr, *cl, *leaf;
+  const float* cent;
+  const ClusterMeta* meta;
+  const ClusterStat* stat;
+};
+
+static size_t view_bytes(int K, int C) {
+  return (size_t)K * (3 * sizeof(int) + 3 * sizeof(float)) + (size_t)C * (sizeof(ClusterMeta) + sizeof(ClusterStat)) + 64;
+}
+
+static int ensure_pin(FuelMap* m, size_t bytes) {
+  FrontierState* f = m->fs;
+  if (bytes <= f->h_pin_bytes) return 0;
+  if (f->h_pin) cudaFreeHost(f->h_pin);
+  f->h_pin = nullptr;
+  f->h_pin_bytes = 0;
+  FUEL_CUDA(m, cudaMallocHost((void**)&f->h_pin, bytes));
+  f->h_pin_bytes = bytes;
+  return 0;
+}
+
+// enqueue the D2H of K cells / C clusters into the pinned buffer at `base` (no sync)
+static int enqueue_download(FuelMap* m, int K, int C, char* base, HostView* v) {
+  FrontierState* f = m->fs;
+  cudaStream_t s = m->stream;
+  char* p = base;
+  auto put = [&](const void* src, size_t bytes) -> char* {
+    char* dst = p;
+    p += (bytes + 15) & ~(size_t)15;
+    if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+    return dst;
+  };
+  v->meta = (const ClusterMeta*)put(f->meta.p, sizeof(ClusterMeta) * C);
+  v->stat = (const ClusterStat*)put(f->stat.p, sizeof(ClusterStat) * C);
+  v->addr = (const int*)put(f->k_addr.p, sizeof(int) * K);
+  v->cl = (const int*)put(f->k_cl.p, sizeof(int) * K);
+  v->leaf = (const int*)put(f->k_leaf.p, sizeof(int) * K);
+  v->cent = (const float*)put(f->k_cent.p, sizeof(float) * 3 * K);
+  FUEL_CUDA(m, cudaGetLastError());
+  return 0;
+}
+
+static int frontier_build_csr(FuelMap* m, int K, int C, const HostView& hv, int32_t* n_clusters,
+                              int32_t* n_cells, int32_t* n_filtered);
+
 static int frontier_marshal(FuelMap* m, int K, int C, int32_t* n_clusters, int32_t* n_cells,
                             int32_t* n_filtered) {
+  int rc = ensure_pin(m, view_bytes(K, C));
+  if (rc) return rc;
+  HostView hv;
+  rc = enqueue_download(m, K, C, m->fs->h_pin, &hv);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return frontier_build_csr(m, K, C, hv, n_clusters, n_cells, n_filtered);
+}
+
+static int frontier_build_csr(FuelMap* m, int K, int C, const HostView& hv, int32_t* n_clusters,
+                              int32_t* n_cells, int32_t* n_filtered) {
   FrontierState* f = m->fs;
   const Geom& g = m->g;
-  cudaStream_t s = m->stream;
-  // ---- download and marshal into CSR (ordering only; no geometry is decided here) ------
-  std::vector<int> h_addr(K), h_cl(K), h_leaf(K);
-  std::vector<float> h_cent((size_t)3 * K);
-  std::vector<ClusterMeta> h_meta(C);
-  std::vector<ClusterStat> h_stat(C);
-  FUEL_CUDA(m, cudaMemcpyAsync(h_addr.data(), f->k_addr.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_cl.data(), f->k_cl.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_leaf.data(), f->k_leaf.p, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_cent.data(), f->k_cent.p, sizeof(float) * 3 * K, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_meta.data(), f->meta.p, sizeof(ClusterMeta) * C, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(h_stat.data(), f->stat.p, sizeof(ClusterStat) * C, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaStreamSynchronize(s));
-
+  const int* h_addr = hv.addr;
+  const int* h_cl = hv.cl;
+  const int* h_leaf = hv.leaf;
+  const float* h_cent = hv.cent;
+  const ClusterMeta* h_meta = hv.meta;
+  const ClusterStat* h_stat = hv.stat;
+  // ---- marshal into CSR (ordering only; no geometry is decided here) ------
   // cluster order: (root, path) lexicographic = the reference's in-place list replacement
   std::vector<int> order(C);
   for (int c = 0; c < C; ++c) order[c] = c;
@@ -1244,8 +1367,7 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
 
   classify_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, m->occ, m->flag, f->maskE.p, f->maskS.p, f->blockcnt.p, ndom);
   m->launches += 1;
-  scan_kernel<<<1, 1024, 0, s>>>(f->blockcnt.p, f->blockoff.p, (int)nb, f->d_counters + 0);
-  m->launches += 1;
+  if (scan_ints(m, f->blockcnt.p, f->blockoff.p, (int)nb, f->d_counters + 0)) return FUELGPU_ENOMEM;
   int n_cand = 0;
   // ---- small path: one compaction + ONE single-CTA launch, one host sync ------------------------
   {
@@ -1265,14 +1387,23 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
     sb.counters = f->d_counters;
     cluster_small_kernel<<<SMALL_CTAS, 1024, 0, s>>>(g, fp, m->flag, f->cellidx, sb);
     m->launches += 2;
-    int cnt[8];
+    // one host sync in the common case: the counters and a speculative prefix of the results
+    // (K0 cells, C0 clusters) are downloaded together; a second stage only if they did not fit
+    constexpr int K0 = 12288, C0 = 256;
+    int rc0 = ensure_pin(m, 64 + view_bytes(K0, C0));
+    if (rc0) return rc0;
+    int* cnt = (int*)f->h_pin;
     FUEL_CUDA(m, cudaMemcpyAsync(cnt, f->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, s));
+    HostView hv;
+    rc0 = enqueue_download(m, K0, C0, f->h_pin + 64, &hv);
+    if (rc0) return rc0;
     FUEL_CUDA(m, cudaStreamSynchronize(s));
     n_cand = cnt[0];
     if (n_cand == 0) return 0;
     if (cnt[4] == 0) {
       const int R = cnt[1], K = cnt[2], C = cnt[5];
       if (R == 0 || K == 0) return 0;
+      if (K <= K0 && C <= C0) return frontier_build_csr(m, K, C, hv, n_clusters, n_cells, n_filtered);
       return frontier_marshal(m, K, C, n_clusters, n_cells, n_filtered);
     }
     // capacity exceeded (status 1: cells, 2: clusters): fall through to the multi-kernel path.
@@ -1306,10 +1437,8 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   m->launches += 1;
   mark_kernel<<<cb, 256, 0, s>>>(f->seed.p, f->csize.p, fp.cluster_min, f->is_root.p, f->is_kept.p, n_cand);
   m->launches += 1;
-  scan_kernel<<<1, 1024, 0, s>>>(f->is_root.p, f->root_rank.p, n_cand, f->d_counters + 1);
-  m->launches += 1;
-  scan_kernel<<<1, 1024, 0, s>>>(f->is_kept.p, f->kept_off.p, n_cand, f->d_counters + 2);
-  m->launches += 1;
+  if (scan_ints(m, f->is_root.p, f->root_rank.p, n_cand, f->d_counters + 1)) return FUELGPU_ENOMEM;
+  if (scan_ints(m, f->is_kept.p, f->kept_off.p, n_cand, f->d_counters + 2)) return FUELGPU_ENOMEM;
   int cnt[3];
   FUEL_CUDA(m, cudaMemcpyAsync(cnt, f->d_counters, sizeof(int) * 3, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
