@@ -171,14 +171,16 @@ def workload_config(args):
             "batch": args.batch, "ctrl_pts": 20, "evals_per_replan": args.evals,
             "cost_mask": "SMOOTHNESS|DISTANCE|FEASIBILITY|START|END|MINTIME",
             "parallelism": "replica x%d (independent planners, no collective)" % args.gpus,
-            "l2": "256 MB L2 flush between timed steps (flush time excluded: each step has its own event pair)"}
+            "l2": "256 MB L2 flush between timed steps (flush time excluded: each step has its own event pair)",
+            "overlap": "frontier search (own stream, begin/end) runs beside ESDF update + solver"
+                       if not getattr(args, "no_overlap", False) else "stages run back to back"}
 
 
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
 class GpuPlanner:
-    def __init__(self, dev, batch, evals, seed_offset=0):
+    def __init__(self, dev, batch, evals, seed_offset=0, overlap=True):
         import ctypes as C
 
         import torch
@@ -226,6 +228,14 @@ class GpuPlanner:
         self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:%d" % dev)
         m.upload()
         self.n_clusters = 0
+        # the frontier subsystem has its own stream in the library: the search is enqueued first
+        # (fuelgpu_frontier_search_begin), the ESDF update and the solver run beside it on the main
+        # stream, and the result is collected last (fuelgpu_frontier_search_end)
+        self.overlap = overlap
+
+    def _frontier_begin(self):
+        self.ff.reset_flags()
+        self.ff.search_box_begin(self.g.origin, self.g.map_max)
 
     def l2_flush(self):
         self.flush.zero_()
@@ -233,10 +243,10 @@ class GpuPlanner:
     def replan_resident(self):
         """Inputs already in HBM: occupancy byte, x, trajectory constants."""
         L, C = self.fuel.lib(), self.C
+        self._frontier_begin()
+        if not self.overlap:
+            self.n_clusters = len(self.ff.search_box_end())
         self.m.updateESDF3d()
-        self.ff.reset_flags()
-        out = self.ff.search_box(self.g.origin, self.g.map_max)
-        self.n_clusters = len(out)
         h = self.m.handle
         # the solver loop of BsplineOptimizer::optimize() on the device: K = max_eval cost/gradient
         # evaluations per trajectory inside one persistent kernel
@@ -247,6 +257,8 @@ class GpuPlanner:
                                                   C.c_void_p(self.d_n.data_ptr()))
         if rc:
             raise RuntimeError(L.fuelgpu_last_error(h))
+        if self.overlap:
+            self.n_clusters = len(self.ff.search_box_end())
 
     def replan_e2e(self):
         """Through the reference-facing host API with HOST buffers: occupancy H2D, ESDF update,
@@ -255,11 +267,14 @@ class GpuPlanner:
         H2D once, best x / cost / eval count D2H once)."""
         m = self.m
         m.upload()
+        self._frontier_begin()
+        if not self.overlap:
+            out = self.ff.search_box_end()
         m.updateESDF3d()
         m.download()
-        self.ff.reset_flags()
-        out = self.ff.search_box(self.g.origin, self.g.map_max)
         x, f, ne = self.opt.optimizeBatch(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0)
+        if self.overlap:
+            out = self.ff.search_box_end()
         self.last_neval = ne
         return out, f
 
@@ -322,7 +337,7 @@ def run_ours(args):
         __graft_entry__.build()
     if world > 1:
         dist.barrier()
-    P = GpuPlanner(local, args.batch, args.evals, seed_offset=100 * rank)
+    P = GpuPlanner(local, args.batch, args.evals, seed_offset=100 * rank, overlap=not args.no_overlap)
     st = P.stream
 
     def barrier():
@@ -460,6 +475,7 @@ def main():
     ap.add_argument("--evals", type=int, default=64)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--no-esdf512", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the frontier search after the ESDF update instead of beside it")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -68,6 +68,8 @@ SIGNATURES = {
     "fuelgpu_esdf_sample": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "fuelgpu_frontier_search": (C.c_int, [_vp, _vp, _vp, C.POINTER(FuelFrontierParams),
                                           C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "fuelgpu_frontier_search_begin": (C.c_int, [_vp, _vp, _vp, C.POINTER(FuelFrontierParams)]),
+    "fuelgpu_frontier_search_end": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "fuelgpu_frontier_fetch": (C.c_int, [_vp] + [_vp] * 7),
     "fuelgpu_frontier_clear_flags": (C.c_int, [_vp, _i32, _vp]),
     "fuelgpu_frontier_is_changed": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),

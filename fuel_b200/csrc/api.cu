@@ -212,6 +212,7 @@ int fuelgpu_map_set_stream(FuelMap* m, void* cuda_stream) {
 int fuelgpu_map_synchronize(FuelMap* m) {
   if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(frontier_stream_raw(m)));
   return 0;
 }
 
@@ -265,7 +266,7 @@ int fuelgpu_map_upload_occupancy(FuelMap* m, const int8_t* inflate, const double
     FUEL_CUDA(m, cudaMemcpyAsync(d_tri, tristate + off, cnt, cudaMemcpyHostToDevice, m->stream));
     ingest_tri_kernel<<<nb, 256, 0, m->stream>>>(d_inf, d_tri, m->occ + off, cnt);
   }
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
   tend(m, T_UPLOAD);
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));  // host buffers may be reused by the caller
@@ -304,7 +305,7 @@ int fuelgpu_esdf_download(FuelMap* m, const int32_t bmin[3], const int32_t bmax[
     if (rc) return rc;
     f32_to_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, m->stream>>>(
         m->dist + off, (double*)m->stage, cnt, m->g.res * sqrt(1.7976931348623157e308));
-    m->launches += 1;
+    FUEL_LAUNCHES(m, 1);
     FUEL_CUDA(m, cudaGetLastError());
     FUEL_CUDA(m, cudaMemcpyAsync(out_f64 + off, m->stage, cnt * 8, cudaMemcpyDeviceToHost, m->stream));
   }
@@ -338,9 +339,28 @@ int fuelgpu_frontier_search(FuelMap* m, const double upd_min[3], const double up
     return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   if (params->down_sample < 1) return fuel_fail(m, FUELGPU_EINVAL, "down_sample must be >= 1");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
-  tbegin(m, T_FRONTIER);
+  cudaStream_t fs = frontier_stream(m);
+  tbegin(m, T_FRONTIER, fs);
   int rc = frontier_search_impl(m, upd_min, upd_max, params, n_clusters, n_cells, n_filtered);
-  tend(m, T_FRONTIER);
+  tend(m, T_FRONTIER, fs);
+  return rc;
+}
+
+int fuelgpu_frontier_search_begin(FuelMap* m, const double upd_min[3], const double upd_max[3],
+                                  const FuelFrontierParams* params) {
+  if (!m || !upd_min || !upd_max || !params) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (params->down_sample < 1) return fuel_fail(m, FUELGPU_EINVAL, "down_sample must be >= 1");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  cudaStream_t fs = frontier_stream(m);
+  tbegin(m, T_FRONTIER, fs);
+  return frontier_search_begin_impl(m, upd_min, upd_max, params);
+}
+
+int fuelgpu_frontier_search_end(FuelMap* m, int32_t* n_clusters, int32_t* n_cells, int32_t* n_filtered) {
+  if (!m || !n_clusters || !n_cells || !n_filtered) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  int rc = frontier_search_end_impl(m, n_clusters, n_cells, n_filtered);
+  tend(m, T_FRONTIER, frontier_stream_raw(m));
   return rc;
 }
 
@@ -356,13 +376,16 @@ int fuelgpu_frontier_clear_flags(FuelMap* m, int32_t n, const int32_t* addr) {
   FUEL_CUDA(m, cudaSetDevice(m->dev));
   for (int i = 0; i < n; ++i)
     if (addr[i] < 0 || addr[i] >= m->nvox) return fuel_fail(m, FUELGPU_EINVAL, "address out of range");
-  int rc = ensure_stage(m, sizeof(int) * (size_t)n);
-  if (rc) return rc;
-  FUEL_CUDA(m, cudaMemcpyAsync(m->stage, addr, sizeof(int) * n, cudaMemcpyHostToDevice, m->stream));
-  clear_flags_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(m->flag, (const int*)m->stage, n);
-  m->launches += 1;
+  // own small allocation: m->stage belongs to the main-stream ingest path
+  int* d_addr = nullptr;
+  FUEL_CUDA(m, cudaMalloc(&d_addr, sizeof(int) * (size_t)n));
+  cudaStream_t fs = frontier_stream(m);
+  FUEL_CUDA(m, cudaMemcpyAsync(d_addr, addr, sizeof(int) * n, cudaMemcpyHostToDevice, fs));
+  clear_flags_kernel<<<(n + 255) / 256, 256, 0, fs>>>(m->flag, d_addr, n);
+  FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
-  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(fs));
+  cudaFree(d_addr);
   return 0;
 }
 
@@ -371,13 +394,14 @@ int fuelgpu_frontier_is_changed(FuelMap* m, int32_t mcl, const int32_t* cell_off
   if (!m || (mcl > 0 && (!cell_offsets || !cell_addr || !changed)))
     return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
+  frontier_stream(m);
   return frontier_is_changed_impl(m, mcl, cell_offsets, cell_addr, changed);
 }
 
 int fuelgpu_frontier_reset_flags(FuelMap* m) {
   if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
-  FUEL_CUDA(m, cudaMemsetAsync(m->flag, 0, m->nvox, m->stream));
+  FUEL_CUDA(m, cudaMemsetAsync(m->flag, 0, m->nvox, frontier_stream(m)));
   return 0;
 }
 
@@ -390,16 +414,18 @@ int fuelgpu_map_launch_count(FuelMap* m, int64_t* count) {
 int fuelgpu_frontier_download_flags(FuelMap* m, int8_t* out) {
   if (!m || !out) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
-  FUEL_CUDA(m, cudaMemcpyAsync(out, m->flag, m->nvox, cudaMemcpyDeviceToHost, m->stream));
-  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  cudaStream_t fs = frontier_stream(m);
+  FUEL_CUDA(m, cudaMemcpyAsync(out, m->flag, m->nvox, cudaMemcpyDeviceToHost, fs));
+  FUEL_CUDA(m, cudaStreamSynchronize(fs));
   return 0;
 }
 
 int fuelgpu_frontier_upload_flags(FuelMap* m, const int8_t* in) {
   if (!m || !in) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
-  FUEL_CUDA(m, cudaMemcpyAsync(m->flag, in, m->nvox, cudaMemcpyHostToDevice, m->stream));
-  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  cudaStream_t fs = frontier_stream(m);
+  FUEL_CUDA(m, cudaMemcpyAsync(m->flag, in, m->nvox, cudaMemcpyHostToDevice, fs));
+  FUEL_CUDA(m, cudaStreamSynchronize(fs));
   return 0;
 }
 

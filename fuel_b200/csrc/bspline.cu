@@ -895,7 +895,7 @@ int bspline_cost_batch_dev_impl(FuelMap* m, int B, int n_pts, int mask, const Fu
     cost_batch_thread_kernel<<<(B + 63) / 64, 64, 0, m->stream>>>(m->g, m->dist, *p, tc_dev, n_pts, mask, B,
                                                                   x_dev, f_dev, grad_dev);
   }
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
   return 0;
 }
@@ -913,7 +913,7 @@ int bspline_optimize_batch_dev_impl(FuelMap* m, int B, int n_pts, int mask, cons
   optimize_warp_kernel<<<(B + WPB - 1) / WPB, WPB * 32, smem, m->stream>>>(m->g, m->dist, *p, tc_dev, n_pts,
                                                                       mask, B, *sp, x_dev, fbest_dev,
                                                                       neval_dev);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
   return 0;
 }

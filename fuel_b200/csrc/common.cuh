@@ -73,11 +73,12 @@ static inline int fuel_fail(FuelMap* m, int code, const char* fmt, const char* a
     }                                                                                          \
   } while (0)
 
-static inline void tbegin(FuelMap* m, int t) { cudaEventRecord(m->ev0[t], m->stream); }
-static inline void tend(FuelMap* m, int t) {
-  cudaEventRecord(m->ev1[t], m->stream);
+static inline void tbegin(FuelMap* m, int t, cudaStream_t s = nullptr) { cudaEventRecord(m->ev0[t], s ? s : m->stream); }
+static inline void tend(FuelMap* m, int t, cudaStream_t s = nullptr) {
+  cudaEventRecord(m->ev1[t], s ? s : m->stream);
   m->ev_valid[t] = true;
 }
+#define FUEL_LAUNCHES(m, n) __atomic_fetch_add(&(m)->launches, (long long)(n), __ATOMIC_RELAXED)
 
 __host__ __device__ static inline int64_t addr_of(const Geom& g, int x, int y, int z) {
   return ((int64_t)x * g.ny + y) * g.nz + z;
@@ -92,10 +93,18 @@ int edt_z_chunks_dev_impl(cudaStream_t s, const int32_t* g2c, int G, int nxl, in
                           double res, float* out, int32_t* scratch);
 
 int frontier_state_create(FuelMap* m);
+// The frontier subsystem runs on its own stream (it only reads `occ` and owns `flag`), so a host
+// thread can search frontiers while another updates the ESDF / runs the B-spline batch on the
+// map's main stream.  frontier_stream() orders it after everything already queued on the main stream.
+cudaStream_t frontier_stream(FuelMap* m);
+cudaStream_t frontier_stream_raw(FuelMap* m);
 void frontier_state_destroy(FuelMap* m);
 int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
                          const FuelFrontierParams* p, int32_t* n_clusters, int32_t* n_cells,
                          int32_t* n_filtered);
+int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double umax[3],
+                               const FuelFrontierParams* p);
+int frontier_search_end_impl(FuelMap* m, int32_t* n_clusters, int32_t* n_cells, int32_t* n_filtered);
 int frontier_fetch_impl(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr, int32_t* filt_offsets,
                         double* filtered, double* average, double* box_min, double* box_max);
 int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const int32_t* addr,

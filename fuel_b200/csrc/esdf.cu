@@ -429,7 +429,7 @@ int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags
   const float res = (float)m->g.res;
   run_three_pass(m->stream, m->occ, m->g1, m->g2, m->stk, m->dist, m->g.nx, m->g.ny, m->g.nz, b, mode,
                  res);
-  m->launches += 3;
+  FUEL_LAUNCHES(m, 3);
   if (flags & FUELGPU_ESDF_SIGNED) {
     if (!m->dist_neg) FUEL_CUDA(m, cudaMalloc(&m->dist_neg, sizeof(float) * m->nvox));
     run_three_pass(m->stream, m->occ, m->g1, m->g2, m->stk, m->dist_neg, m->g.nx, m->g.ny, m->g.nz, b,
@@ -437,7 +437,7 @@ int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags
     const int64_t nb = (int64_t)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
     signed_merge_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, m->stream>>>(m->dist, m->dist_neg,
                                                                           m->g.ny, m->g.nz, b, res);
-    m->launches += 4;
+    FUEL_LAUNCHES(m, 4);
   }
   FUEL_CUDA(m, cudaGetLastError());
   return 0;
@@ -446,7 +446,7 @@ int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags
 int esdf_sample_impl(FuelMap* m, int64_t n, const double* pos, double* d, double* grad) {
   if (n <= 0) return 0;
   sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, m->stream>>>(m->g, m->dist, n, pos, d, grad);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
   return 0;
 }

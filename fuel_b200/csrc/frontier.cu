@@ -1107,6 +1107,13 @@ struct DevBuf {
 
 }  // namespace
 
+struct HostView {  // result arrays in pinned host memory
+  const int *addr, *cl, *leaf;
+  const float* cent;
+  const ClusterMeta* meta;
+  const ClusterStat* stat;
+};
+
 struct FrontierState {
   int* cellidx = nullptr;  // voxel -> cell index, -1 elsewhere (persistent, sparse use)
   DevBuf<uint32_t> maskE, maskS;
@@ -1118,6 +1125,14 @@ struct FrontierState {
   DevBuf<ClusterStat> stat;
   DevBuf<ClusterMeta> meta;
   bool small_ready = false;
+  // a search that has been enqueued (begin) but not yet collected (end)
+  bool pend_active = false, pend_empty = true;
+  FParams pend_fp;
+  unsigned pend_nb = 0;
+  int64_t pend_ndom = 0;
+  HostView pend_hv;
+  cudaStream_t stream = nullptr;  // the frontier subsystem's own stream
+  cudaEvent_t ev_in = nullptr;
   char* h_pin = nullptr;  // pinned host staging for the result download
   size_t h_pin_bytes = 0;
   int* d_counters = nullptr;  // [0] n_cand [1] n_roots [2] n_kept [3] n_new [4] small-path status [5] C
@@ -1126,8 +1141,18 @@ struct FrontierState {
   std::vector<double> h_filtered, h_avg, h_bmin, h_bmax;
 };
 
+cudaStream_t frontier_stream_raw(FuelMap* m) { return m->fs->stream; }
+cudaStream_t frontier_stream(FuelMap* m) {
+  FrontierState* f = m->fs;
+  cudaEventRecord(f->ev_in, m->stream);
+  cudaStreamWaitEvent(f->stream, f->ev_in, 0);
+  return f->stream;
+}
+
 int frontier_state_create(FuelMap* m) {
   m->fs = new FrontierState();
+  FUEL_CUDA(m, cudaStreamCreateWithFlags(&m->fs->stream, cudaStreamNonBlocking));
+  FUEL_CUDA(m, cudaEventCreateWithFlags(&m->fs->ev_in, cudaEventDisableTiming));
   FUEL_CUDA(m, cudaMalloc(&m->fs->cellidx, sizeof(int) * m->nvox));
   FUEL_CUDA(m, cudaMemsetAsync(m->fs->cellidx, 0xff, sizeof(int) * m->nvox, m->stream));
   FUEL_CUDA(m, cudaMalloc(&m->fs->d_counters, sizeof(int) * 8 + sizeof(long long) * 256));
@@ -1141,6 +1166,11 @@ void frontier_state_destroy(FuelMap* m) {
   if (f->cellidx) cudaFree(f->cellidx);
   if (f->d_counters) cudaFree(f->d_counters);
   if (f->h_pin) cudaFreeHost(f->h_pin);
+  if (f->stream) {
+    cudaStreamSynchronize(f->stream);
+    cudaStreamDestroy(f->stream);
+  }
+  if (f->ev_in) cudaEventDestroy(f->ev_in);
   f->maskE.release(); f->maskS.release(); f->blockcnt.release(); f->blockoff.release();
   f->scan_tot.release(); f->scan_off.release();
   f->cell_addr.release(); f->parent.release(); f->claim.release(); f->csize.release();
@@ -1161,10 +1191,10 @@ static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / 
 // exclusive scan of n ints on the stream; `total` (device) receives the sum
 static int scan_ints(FuelMap* m, const int* in, int* out, int n, int* total) {
   FrontierState* f = m->fs;
-  cudaStream_t s = m->stream;
+  cudaStream_t s = m->fs->stream;
   if (n <= 4096) {
     scan_kernel<<<1, 1024, 0, s>>>(in, out, n, total);
-    m->launches += 1;
+    FUEL_LAUNCHES(m, 1);
     return 0;
   }
   const int nchunk = (n + 1023) / 1024;
@@ -1173,16 +1203,9 @@ static int scan_ints(FuelMap* m, const int* in, int* out, int n, int* total) {
   scan_chunks_kernel<<<nchunk, 1024, 0, s>>>(in, out, n, f->scan_tot.p);
   scan_kernel<<<1, 1024, 0, s>>>(f->scan_tot.p, f->scan_off.p, nchunk, total);
   scan_add_kernel<<<nchunk, 1024, 0, s>>>(out, n, f->scan_off.p);
-  m->launches += 3;
+  FUEL_LAUNCHES(m, 3);
   return 0;
 }
-
-struct HostView {  // result arrays in pinned host memory
-  const int *addr, *cl, *leaf;
-  const float* cent;
-  const ClusterMeta* meta;
-  const ClusterStat* stat;
-};
 
 static size_t view_bytes(int K, int C) {
   return (size_t)K * (3 * sizeof(int) + 3 * sizeof(float)) + (size_t)C * (sizeof(ClusterMeta) + sizeof(ClusterStat)) + 64;
@@ -1202,7 +1225,7 @@ static int ensure_pin(FuelMap* m, size_t bytes) {
 // enqueue the D2H of K cells / C clusters into the pinned buffer at `base` (no sync)
 static int enqueue_download(FuelMap* m, int K, int C, char* base, HostView* v) {
   FrontierState* f = m->fs;
-  cudaStream_t s = m->stream;
+  cudaStream_t s = m->fs->stream;
   char* p = base;
   auto put = [&](const void* src, size_t bytes) -> char* {
     char* dst = p;
@@ -1230,7 +1253,7 @@ static int frontier_marshal(FuelMap* m, int K, int C, int32_t* n_clusters, int32
   HostView hv;
   rc = enqueue_download(m, K, C, m->fs->h_pin, &hv);
   if (rc) return rc;
-  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(m->fs->stream));
   return frontier_build_csr(m, K, C, hv, n_clusters, n_cells, n_filtered);
 }
 
@@ -1303,12 +1326,11 @@ static int frontier_build_csr(FuelMap* m, int K, int C, const HostView& hv, int3
   return 0;
 }
 
-int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
-                         const FuelFrontierParams* p, int32_t* n_clusters, int32_t* n_cells,
-                         int32_t* n_filtered) {
+int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double umax[3],
+                               const FuelFrontierParams* p) {
   FrontierState* f = m->fs;
   const Geom& g = m->g;
-  cudaStream_t s = m->stream;
+  cudaStream_t s = m->fs->stream;
   const int nmax[3] = { g.nx, g.ny, g.nz };
 
   // search box: updated box inflated by (1,1,0.5) m, clamped to the exploration box, then
@@ -1354,10 +1376,12 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   f->h_avg.clear();
   f->h_bmin.clear();
   f->h_bmax.clear();
-  *n_clusters = *n_cells = *n_filtered = 0;
+  f->pend_active = false;
+  f->pend_empty = true;
 
   const int64_t ndom = (int64_t)fp.dom_n[0] * fp.dom_n[1] * fp.dom_n[2];
   if (ndom <= 0) return 0;
+  f->pend_empty = false;
   const unsigned nb = nblk(ndom, CLS_BLOCK);
   const size_t nwords = (size_t)nb * (CLS_BLOCK / 32);
   ENSURE(f->maskE, nwords);
@@ -1366,9 +1390,8 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   ENSURE(f->blockoff, nb);
 
   classify_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, m->occ, m->flag, f->maskE.p, f->maskS.p, f->blockcnt.p, ndom);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   if (scan_ints(m, f->blockcnt.p, f->blockoff.p, (int)nb, f->d_counters + 0)) return FUELGPU_ENOMEM;
-  int n_cand = 0;
   // ---- small path: one compaction + ONE single-CTA launch, one host sync ------------------------
   {
     ENSURE(f->cell_addr, SMALL_CAP); ENSURE(f->cell_cls, SMALL_CAP); ENSURE(f->parent, SMALL_CAP);
@@ -1386,7 +1409,7 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
     sb.k_leaf = f->k_leaf.p; sb.k_cent = f->k_cent.p; sb.meta = f->meta.p; sb.stat = f->stat.p;
     sb.counters = f->d_counters;
     cluster_small_kernel<<<SMALL_CTAS, 1024, 0, s>>>(g, fp, m->flag, f->cellidx, sb);
-    m->launches += 2;
+    FUEL_LAUNCHES(m, 2);
     // one host sync in the common case: the counters and a speculative prefix of the results
     // (K0 cells, C0 clusters) are downloaded together; a second stage only if they did not fit
     constexpr int K0 = 12288, C0 = 256;
@@ -1394,9 +1417,35 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
     if (rc0) return rc0;
     int* cnt = (int*)f->h_pin;
     FUEL_CUDA(m, cudaMemcpyAsync(cnt, f->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, s));
-    HostView hv;
+    HostView& hv = f->pend_hv;
     rc0 = enqueue_download(m, K0, C0, f->h_pin + 64, &hv);
     if (rc0) return rc0;
+    f->pend_fp = fp;
+    f->pend_nb = nb;
+    f->pend_ndom = ndom;
+    f->pend_active = true;
+  }
+  return 0;
+}
+
+int frontier_search_end_impl(FuelMap* m, int32_t* n_clusters, int32_t* n_cells, int32_t* n_filtered) {
+  FrontierState* f = m->fs;
+  const Geom& g = m->g;
+  cudaStream_t s = m->fs->stream;
+  *n_clusters = *n_cells = *n_filtered = 0;
+  if (f->pend_empty || !f->pend_active) {
+    f->pend_active = false;
+    return 0;
+  }
+  f->pend_active = false;
+  const FParams fp = f->pend_fp;
+  const unsigned nb = f->pend_nb;
+  const int64_t ndom = f->pend_ndom;
+  int n_cand = 0;
+  {
+    constexpr int K0 = 12288, C0 = 256;
+    int* cnt = (int*)f->h_pin;
+    HostView& hv = f->pend_hv;
     FUEL_CUDA(m, cudaStreamSynchronize(s));
     n_cand = cnt[0];
     if (n_cand == 0) return 0;
@@ -1411,7 +1460,7 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
     // (status 2) or never touched beyond the cap (status 1: reset what compaction wrote).
     if (cnt[4] == 1) {
       reset_cellidx_kernel<<<nblk(SMALL_CAP, 256), 256, 0, s>>>(f->cell_addr.p, f->cellidx, SMALL_CAP);
-      m->launches += 1;
+      FUEL_LAUNCHES(m, 1);
     }
   }
 
@@ -1422,21 +1471,21 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
 
   compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p,
                                           f->cell_cls.p, f->cellidx, ndom, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   const unsigned cb = nblk(n_cand, 256);
   init_parent_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->claim.p, f->csize.p, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   union_kernel<<<cb, 256, 0, s>>>(g, f->cell_addr.p, f->cell_cls.p, f->cellidx, f->parent.p, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   flatten_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->cell_cls.p, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   claim_kernel<<<cb, 256, 0, s>>>(g, fp, f->cell_addr.p, f->cell_cls.p, f->cellidx, f->parent.p, f->claim.p, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   assign_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cell_cls.p, f->parent.p, f->claim.p, f->seed.p,
                                    f->csize.p, m->flag, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   mark_kernel<<<cb, 256, 0, s>>>(f->seed.p, f->csize.p, fp.cluster_min, f->is_root.p, f->is_kept.p, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   if (scan_ints(m, f->is_root.p, f->root_rank.p, n_cand, f->d_counters + 1)) return FUELGPU_ENOMEM;
   if (scan_ints(m, f->is_kept.p, f->kept_off.p, n_cand, f->d_counters + 2)) return FUELGPU_ENOMEM;
   int cnt[3];
@@ -1445,14 +1494,14 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   const int R = cnt[1], K = cnt[2];
   if (R == 0 || K == 0) {
     reset_cellidx_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cellidx, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     FUEL_CUDA(m, cudaGetLastError());
     return 0;
   }
   ENSURE(f->k_addr, K); ENSURE(f->k_cl, K); ENSURE(f->k_leaf, K); ENSURE(f->k_cent, (size_t)3 * K);
   gather_kept_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->seed.p, f->is_kept.p, f->kept_off.p,
                                         f->root_rank.p, f->k_addr.p, f->k_cl.p, f->cellidx, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
 
   // ---- split levels -------------------------------------------------------------------
   // at most one new cluster per kept cell; K bounds the cluster count
@@ -1460,7 +1509,7 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
   ENSURE(f->stat, (size_t)2 * R + 1024);
   int C = R;
   init_meta_kernel<<<nblk(R, 256), 256, 0, s>>>(f->meta.p, R);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   const unsigned kb = nblk(K, 256);
   for (int level = 0; level < 40; ++level) {
     // every active cluster may spawn one new cluster this level
@@ -1468,37 +1517,45 @@ int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
       return fuel_fail(m, FUELGPU_ENOMEM, "frontier: device allocation failed");
     const unsigned ccb = nblk(C, 256);
     stat_reset_kernel<<<ccb, 256, 0, s>>>(f->stat.p, f->meta.p, C);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     stat_accum_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, K);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     mean_kernel<<<ccb, 256, 0, s>>>(g, f->meta.p, f->stat.p, C);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     downsample_kernel<<<kb, 256, 0, s>>>(g, fp, f->k_addr.p, f->k_cl.p, f->cellidx, f->meta.p, f->stat.p,
                                          f->k_cent.p, f->k_leaf.p, K);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     cov_kernel<<<kb, 256, 0, s>>>(f->k_cl.p, f->k_leaf.p, f->k_cent.p, f->meta.p, f->stat.p, K);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     pca_kernel<<<ccb, 256, 0, s>>>(f->meta.p, f->stat.p, C);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     side_count_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, K);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     split_alloc_kernel<<<1, 1024, 0, s>>>(f->meta.p, f->stat.p, C, f->d_counters + 3);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     relabel_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, K, C);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     int n_new = 0;
     FUEL_CUDA(m, cudaMemcpyAsync(&n_new, f->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
     FUEL_CUDA(m, cudaStreamSynchronize(s));
     if (n_new == 0) break;
     clear_do_split_kernel<<<ccb, 256, 0, s>>>(f->meta.p, C);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
     C += n_new;
   }
 
   reset_cellidx_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cellidx, n_cand);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
   return frontier_marshal(m, K, C, n_clusters, n_cells, n_filtered);
+}
+
+int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],
+                         const FuelFrontierParams* p, int32_t* n_clusters, int32_t* n_cells,
+                         int32_t* n_filtered) {
+  int rc = frontier_search_begin_impl(m, umin, umax, p);
+  if (rc) return rc;
+  return frontier_search_end_impl(m, n_clusters, n_cells, n_filtered);
 }
 
 int frontier_fetch_impl(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr, int32_t* filt_offsets,
@@ -1523,11 +1580,11 @@ int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const
   FUEL_CUDA(m, cudaMalloc(&d_off, sizeof(int) * (mcl + 1)));
   FUEL_CUDA(m, cudaMalloc(&d_addr, sizeof(int) * (ncell > 0 ? ncell : 1)));
   FUEL_CUDA(m, cudaMalloc(&d_ch, mcl));
-  cudaStream_t s = m->stream;
+  cudaStream_t s = m->fs->stream;
   FUEL_CUDA(m, cudaMemcpyAsync(d_off, offs, sizeof(int) * (mcl + 1), cudaMemcpyHostToDevice, s));
   if (ncell > 0) FUEL_CUDA(m, cudaMemcpyAsync(d_addr, addr, sizeof(int) * ncell, cudaMemcpyHostToDevice, s));
   is_changed_kernel<<<mcl, 128, 0, s>>>(m->g, m->occ, d_off, d_addr, d_ch, mcl);
-  m->launches += 1;
+  FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaMemcpyAsync(changed, d_ch, mcl, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
   cudaFree(d_off);

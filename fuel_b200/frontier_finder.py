@@ -117,14 +117,23 @@ class FrontierFinder:
 
     def search_box(self, update_min, update_max):
         """The sweep + expandFrontier + splitLargeFrontiers part (:94-118) for a given updated box."""
-        m = self._map
-        h = m.handle
+        self.search_box_begin(update_min, update_max)
+        return self.search_box_end()
+
+    def search_box_begin(self, update_min, update_max):
+        """Enqueue the search on the frontier stream and return at once (fuelgpu_frontier_search_begin)."""
+        h = self._map.handle
         umin = np.ascontiguousarray(update_min, dtype=np.float64)
         umax = np.ascontiguousarray(update_max, dtype=np.float64)
         p = self._params()
+        check(lib().fuelgpu_frontier_search_begin(h, ptr(umin), ptr(umax), C.byref(p)), h)
+
+    def search_box_end(self):
+        """Wait for the enqueued search and build the Frontier list."""
+        m = self._map
+        h = m.handle
         nc, ncell, nf = C.c_int32(), C.c_int32(), C.c_int32()
-        check(lib().fuelgpu_frontier_search(h, ptr(umin), ptr(umax), C.byref(p), C.byref(nc), C.byref(ncell),
-                                            C.byref(nf)), h)
+        check(lib().fuelgpu_frontier_search_end(h, C.byref(nc), C.byref(ncell), C.byref(nf)), h)
         nc, ncell, nf = nc.value, ncell.value, nf.value
         offs = np.zeros(nc + 1, dtype=np.int32)
         addr = np.zeros(ncell, dtype=np.int32)

@@ -127,6 +127,15 @@ typedef struct {
 FUELGPU_API int fuelgpu_frontier_search(FuelMap* map, const double upd_min[3], const double upd_max[3],
                             const FuelFrontierParams* params, int32_t* n_clusters,
                             int32_t* n_cells, int32_t* n_filtered);
+/* The same search split in two so that the caller can overlap it with other work: _begin enqueues
+ * the sweep and the clustering on the handle's frontier stream and returns at once; _end waits for
+ * it and returns the sizes.  fuelgpu_frontier_search == _begin followed by _end.  The frontier
+ * subsystem only reads the occupancy byte and owns frontier_flag_, so ESDF updates and B-spline
+ * batches may be issued between the two calls (they run on the handle's main stream). */
+FUELGPU_API int fuelgpu_frontier_search_begin(FuelMap* map, const double upd_min[3], const double upd_max[3],
+                                  const FuelFrontierParams* params);
+FUELGPU_API int fuelgpu_frontier_search_end(FuelMap* map, int32_t* n_clusters, int32_t* n_cells,
+                                int32_t* n_filtered);
 /* cell_offsets [n_clusters+1], cell_addr [n_cells] (toAddress), filt_offsets [n_clusters+1],
  * filtered [n_filtered][3] (Frontier::filtered_cells_), average/box_min/box_max [n_clusters][3]
  * (Frontier::average_/box_min_/box_max_, frontier_finder.h:34-51).  Any pointer may be NULL. */
