@@ -7,8 +7,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfuelgpu.so")
-SOURCES = ["api.cu", "esdf.cu", "frontier.cu", "bspline.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "fuelgpu.h")]
+SOURCES = ["api.cu", "esdf.cu", "frontier.cu", "bspline.cu", "bspline_solve.cu"]
+FMAD_OK = {"bspline_solve.cu", "esdf.cu"}  # files whose arithmetic need not follow the host rounding sequence
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "bspline_eval.cuh"),
+           os.path.join(ROOT, "include", "fuelgpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -42,7 +44,8 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        flags = [f for f in NVCC_FLAGS if not (s in FMAD_OK and f == "-fmad=false")]
+        cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(o)

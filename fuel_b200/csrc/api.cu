@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stddef.h>
 #include <new>
 
 thread_local char g_fuelgpu_err[512] = "";
@@ -235,6 +236,28 @@ int fuelgpu_map_last_timing(FuelMap* m, float ms[8]) {
   return 0;
 }
 
+int fuelgpu_host_register(void* ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return fuel_fail(nullptr, FUELGPU_EINVAL, "null argument");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return 0;
+  }
+  FUEL_CUDA(nullptr, e);
+  return 0;
+}
+
+int fuelgpu_host_unregister(void* ptr) {
+  if (!ptr) return fuel_fail(nullptr, FUELGPU_EINVAL, "null argument");
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e == cudaErrorHostMemoryNotRegistered) {
+    cudaGetLastError();
+    return 0;
+  }
+  FUEL_CUDA(nullptr, e);
+  return 0;
+}
+
 int fuelgpu_map_upload_occupancy(FuelMap* m, const int8_t* inflate, const double* logodds,
                                  const uint8_t* tristate, double clamp_min_log,
                                  double min_occupancy_log, const int32_t bmin[3],
@@ -429,6 +452,22 @@ int fuelgpu_frontier_upload_flags(FuelMap* m, const int8_t* in) {
   return 0;
 }
 
+// H2D of the per-trajectory constants.  The guide / waypoint arrays are 3 KB of the 3.3 KB record;
+// when no trajectory uses them (the exploration objective) only the leading part is sent.
+static cudaError_t upload_traj(FuelMap* m, FuelTrajConst* d_tc, const FuelTrajConst* traj, int B) {
+  bool lean = true;
+  for (int b = 0; b < B && lean; ++b) lean = traj[b].n_guide == 0 && traj[b].n_waypt == 0;
+  if (!lean) return cudaMemcpyAsync(d_tc, traj, sizeof(FuelTrajConst) * (size_t)B, cudaMemcpyHostToDevice, m->stream);
+  const size_t head = offsetof(FuelTrajConst, guide);
+  cudaError_t e = cudaMemcpy2DAsync(d_tc, sizeof(FuelTrajConst), traj, sizeof(FuelTrajConst), head, B,
+                                    cudaMemcpyHostToDevice, m->stream);
+  if (e != cudaSuccess) return e;
+  // n_waypt lives after the guide array
+  return cudaMemcpy2DAsync((char*)d_tc + offsetof(FuelTrajConst, n_waypt), sizeof(FuelTrajConst),
+                           (const char*)traj + offsetof(FuelTrajConst, n_waypt), sizeof(FuelTrajConst),
+                           sizeof(int32_t), B, cudaMemcpyHostToDevice, m->stream);
+}
+
 static int check_bspline_args(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
                               const FuelOptParams* p) {
   if (!m || !p) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
@@ -475,7 +514,7 @@ int fuelgpu_bspline_cost_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mas
   double* d_x = (double*)(base + tcb);
   double* d_g = d_x + (size_t)B * nvar;
   double* d_f = d_g + (size_t)B * nvar;
-  FUEL_CUDA(m, cudaMemcpyAsync(d_tc, traj, tcb, cudaMemcpyHostToDevice, m->stream));
+  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B));
   FUEL_CUDA(m, cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, m->stream));
   tbegin(m, T_BSPLINE);
   rc = bspline_cost_batch_dev_impl(m, B, n_pts, mask, p, d_tc, d_x, d_f, d_g);
@@ -527,7 +566,7 @@ int fuelgpu_bspline_optimize_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t
   double* d_x = (double*)(base + tcb);
   double* d_f = d_x + (size_t)B * nvar;
   int32_t* d_n = (int32_t*)(d_f + B);
-  FUEL_CUDA(m, cudaMemcpyAsync(d_tc, traj, tcb, cudaMemcpyHostToDevice, m->stream));
+  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B));
   FUEL_CUDA(m, cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, m->stream));
   tbegin(m, T_BSPLINE);
   rc = bspline_optimize_batch_dev_impl(m, B, n_pts, mask, p, d_tc, solve, d_x, d_f, d_n);

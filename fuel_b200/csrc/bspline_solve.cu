@@ -1,0 +1,256 @@
+// bspline_solve.cu -- persistent per-trajectory solver (the NLopt loop of BsplineOptimizer::optimize()).
+// Compiled with FMA contraction enabled: the iterate sequence is our own (NLopt parity is unpinned),
+// only the faithful cost kernel in bspline.cu keeps the reference's rounding order.
+#include "bspline_eval.cuh"
+
+namespace {
+
+// =========================================================================================
+// Persistent per-trajectory solver: replaces the NLopt driver loop of
+// BsplineOptimizer::optimize() (:165-253) -- clamp to the box shrunk by 0.1 m (:175-204),
+// bounds q0 +- 10 m clipped to that box and dt in [0,5] (:206-217), maxeval stop (:170),
+// xtol_rel stop (:173), best-x tracking of costFunction (:693-706) -- around a projected
+// L-BFGS with Armijo backtracking.  One warp per trajectory for the whole solve; the
+// iterate, gradient and search direction live in registers (lane i = control point i,
+// lane n = dt), the (s,y) history in shared memory.
+// =========================================================================================
+constexpr int MAXM = 8;
+
+struct V3 {
+  double v[3];
+};
+__device__ __forceinline__ double dot3(const V3& a, const V3& b) {
+  return wsum(a.v[0] * b.v[0] + a.v[1] * b.v[1] + a.v[2] * b.v[2]);
+}
+
+__global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
+    Geom g, const float* __restrict__ dist, FuelOptParams p, const FuelTrajConst* __restrict__ tc, int n,
+    int mask, int B, FuelSolveParams sp, double* __restrict__ x, double* __restrict__ fbest,
+    int* __restrict__ neval_out) {
+  extern __shared__ double hist[];  // [WPB][2][m][32][3]
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int b = blockIdx.x * WPB + w;
+  if (b >= B) return;
+  const bool opt_time = (mask & FUELGPU_MINTIME) != 0;
+  const int nvar = opt_time ? 3 * n + 1 : 3 * n;
+  const int m = sp.lbfgs_m;
+  double* S = hist + (size_t)w * 2 * m * 96;
+  double* Y = S + (size_t)m * 96;
+  double* xb = x + (int64_t)b * nvar;
+  TrajRegs t;
+  load_traj(tc + b, t);
+
+  // variables of this lane: control point (lane < n), dt in component 0 of lane n
+  const bool is_pt = lane < n;
+  const bool is_dt = opt_time && lane == n;
+  V3 X, lb, ub;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    X.v[k] = 0.0;
+    lb.v[k] = 0.0;
+    ub.v[k] = 0.0;
+    if (is_pt) {
+      const double bmin = g.box_mind[k] + 0.1, bmax = g.box_maxd[k] - 0.1;
+      double c = xb[3 * lane + k];
+      c = fmax(fmin(c, bmax), bmin);  // :199-203
+      X.v[k] = c;
+      lb.v[k] = fmax(c - 10.0, bmin);  // :208-214
+      ub.v[k] = fmin(c + 10.0, bmax);
+    }
+  }
+  if (is_dt) {
+    X.v[0] = xb[nvar - 1];
+    lb.v[0] = 0.0;  // :215-218
+    ub.v[0] = 5.0;
+  }
+
+  auto evaluate = [&](const V3& xx, double& fo, V3& go) {
+    const double dtv = opt_time ? __shfl_sync(0xffffffffu, xx.v[0], n) : t.knot_span;
+    double gr[3], gdt;
+    eval_warp<true>(g, dist, p, t, tc + b, n, mask, xx.v, dtv, lane, fo, gr, gdt);
+    go.v[0] = is_pt ? gr[0] : (is_dt ? gdt : 0.0);
+    go.v[1] = is_pt ? gr[1] : 0.0;
+    go.v[2] = is_pt ? gr[2] : 0.0;
+  };
+  auto store_best = [&](const V3& xx, double fv) {
+    if (is_pt) {
+      xb[3 * lane] = xx.v[0];
+      xb[3 * lane + 1] = xx.v[1];
+      xb[3 * lane + 2] = xx.v[2];
+    }
+    if (is_dt) xb[nvar - 1] = xx.v[0];
+    if (lane == 0) fbest[b] = fv;
+  };
+
+  double F;
+  V3 G;
+  evaluate(X, F, G);
+  int neval = 1;
+  double best = F;
+  store_best(X, F);
+  // a NaN/inf start cannot be improved on by comparison; treat as +inf
+  if (!(best == best)) best = 1.7976931348623157e308;
+
+  int cnt = 0, head = 0;  // history ring: newest at (head-1) mod m
+  double rho[MAXM];
+#pragma unroll
+  for (int j = 0; j < MAXM; ++j) rho[j] = 0.0;
+
+  while (neval < sp.max_eval) {
+    // projected gradient
+    V3 PG, D;
+    bool actv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      actv[k] = (X.v[k] <= lb.v[k] && G.v[k] > 0.0) || (X.v[k] >= ub.v[k] && G.v[k] < 0.0);
+      PG.v[k] = actv[k] ? 0.0 : G.v[k];
+    }
+    const double pgn2 = dot3(PG, PG);
+    if (!(pgn2 > 1e-24)) break;
+    // two-loop recursion
+    V3 Q = PG;
+    double alpha[MAXM];
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) {
+      alpha[j] = 0.0;
+      if (j < cnt) {
+        const int slot = (head - 1 - j + 2 * MAXM * m) % m;
+        V3 s, y;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          s.v[k] = S[slot * 96 + lane * 3 + k];
+          y.v[k] = Y[slot * 96 + lane * 3 + k];
+        }
+        alpha[j] = rho[slot] * dot3(s, Q);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Q.v[k] -= alpha[j] * y.v[k];
+      }
+    }
+    if (cnt > 0) {
+      const int slot = (head - 1 + m) % m;
+      V3 s, y;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        s.v[k] = S[slot * 96 + lane * 3 + k];
+        y.v[k] = Y[slot * 96 + lane * 3 + k];
+      }
+      const double gamma = dot3(s, y) / dot3(y, y);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Q.v[k] *= gamma;
+    }
+#pragma unroll
+    for (int j = MAXM - 1; j >= 0; --j) {
+      if (j < cnt) {
+        const int slot = (head - 1 - j + 2 * MAXM * m) % m;
+        V3 s, y;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          s.v[k] = S[slot * 96 + lane * 3 + k];
+          y.v[k] = Y[slot * 96 + lane * 3 + k];
+        }
+        const double beta = rho[slot] * dot3(y, Q);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Q.v[k] += s.v[k] * (alpha[j] - beta);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) D.v[k] = actv[k] ? 0.0 : -Q.v[k];
+    double gd = dot3(G, D);
+    if (!(gd < 0.0)) {  // not a descent direction: restart from steepest descent
+#pragma unroll
+      for (int k = 0; k < 3; ++k) D.v[k] = -PG.v[k];
+      gd = -pgn2;
+      cnt = 0;
+    }
+    double step = cnt == 0 ? fmin(1.0, 1.0 / sqrt(pgn2)) : 1.0;
+
+    // Armijo backtracking on the projected path
+    bool accepted = false;
+    V3 XN, GN;
+    double FN = 0.0;
+    while (neval < sp.max_eval) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) XN.v[k] = fmax(fmin(X.v[k] + step * D.v[k], ub.v[k]), lb.v[k]);
+      evaluate(XN, FN, GN);
+      ++neval;
+      if (FN < best) {  // costFunction :698-704
+        best = FN;
+        store_best(XN, FN);
+      }
+      V3 dx;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dx.v[k] = XN.v[k] - X.v[k];
+      const double dec = dot3(G, dx);
+      if (FN <= F + 1e-4 * dec) {
+        accepted = true;
+        break;
+      }
+      step *= 0.5;
+      if (step < 1e-12) break;
+    }
+    if (!accepted) break;
+    V3 s, y;
+    bool small = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      s.v[k] = XN.v[k] - X.v[k];
+      y.v[k] = GN.v[k] - G.v[k];
+      small = small && (fabs(s.v[k]) <= sp.xtol_rel * fabs(XN.v[k]));
+    }
+    const double sy = dot3(s, y);
+    const double ss = dot3(s, s), yy = dot3(y, y);
+    if (sy > 1e-10 * sqrt(ss * yy)) {
+      const int slot = head;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        S[slot * 96 + lane * 3 + k] = s.v[k];
+        Y[slot * 96 + lane * 3 + k] = y.v[k];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j)
+        if (j == slot) rho[j] = 1.0 / sy;
+      head = (head + 1) % m;
+      if (cnt < m) ++cnt;
+    }
+    X = XN;
+    F = FN;
+    G = GN;
+    if (__all_sync(0xffffffffu, small)) break;  // xtol_rel, :173
+  }
+  // min_cost_ is reported from the full-precision evaluator (fp64 trilinear, per-term reductions) at
+  // the returned best_variable_, so it equals what combineCost gives for that x.
+  {
+    __syncwarp();
+    V3 XB;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) XB.v[k] = is_pt ? xb[3 * lane + k] : 0.0;
+    if (is_dt) XB.v[0] = xb[nvar - 1];
+    const double dtv = opt_time ? __shfl_sync(0xffffffffu, XB.v[0], n) : t.knot_span;
+    double fo, gr[3], gdt;
+    eval_warp<false>(g, dist, p, t, tc + b, n, mask, XB.v, dtv, lane, fo, gr, gdt);
+    if (lane == 0) fbest[b] = fo;
+  }
+  if (lane == 0) neval_out[b] = neval;
+}
+
+}  // namespace
+
+int bspline_optimize_batch_dev_impl(FuelMap* m, int B, int n_pts, int mask, const FuelOptParams* p,
+                                    const FuelTrajConst* tc_dev, const FuelSolveParams* sp,
+                                    double* x_dev, double* fbest_dev, int32_t* neval_dev) {
+  if (B <= 0) return 0;
+  const int need = n_pts + ((mask & FUELGPU_MINTIME) ? 1 : 0);
+  if (need > 32)
+    return fuel_fail(m, FUELGPU_EUNSUPPORTED, "optimize_batch supports at most 32 lanes (n_pts + dt)");
+  const size_t smem = (size_t)WPB * 2 * sp->lbfgs_m * 96 * sizeof(double);
+  FUEL_CUDA(m, cudaFuncSetAttribute(optimize_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  optimize_warp_kernel<<<(B + WPB - 1) / WPB, WPB * 32, smem, m->stream>>>(m->g, m->dist, *p, tc_dev, n_pts,
+                                                                      mask, B, *sp, x_dev, fbest_dev,
+                                                                      neval_dev);
+  FUEL_LAUNCHES(m, 1);
+  FUEL_CUDA(m, cudaGetLastError());
+  return 0;
+}

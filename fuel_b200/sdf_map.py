@@ -67,10 +67,22 @@ class SDFMap:
         check(lib().fuelgpu_map_create(C.byref(d), int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
+        # the occupancy mirrors are sized once here (initMap): page-lock them for the H2D leg
+        self._pinned = []
+        for a in (self.occupancy_buffer_inflate_, self.occupancy_tri_):
+            self.pin(a)
+
+    def pin(self, arr):
+        """cudaHostRegister a long-lived numpy buffer (full PCIe rate for upload/download)."""
+        if lib().fuelgpu_host_register(ptr(arr), arr.nbytes) == 0:
+            self._pinned.append(arr)
 
     # ---- lifetime -------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
+            for a in getattr(self, "_pinned", []):
+                lib().fuelgpu_host_unregister(ptr(a))
+            self._pinned = []
             lib().fuelgpu_map_destroy(self._h)
             self._h = None
 
@@ -220,6 +232,7 @@ class SDFMap:
         """Mirror distance_buffer_ to the host for getDistance()."""
         if self.distance_buffer_ is None or self.distance_buffer_.dtype != dtype:
             self.distance_buffer_ = np.full(self.shape, self.default_dist_, dtype=dtype)
+            self.pin(self.distance_buffer_)
         bmin_a = None if bmin is None else np.ascontiguousarray(bmin, dtype=np.int32)
         bmax_a = None if bmax is None else np.ascontiguousarray(bmax, dtype=np.int32)
         if dtype == np.float32:

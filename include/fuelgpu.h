@@ -77,6 +77,12 @@ FUELGPU_API int fuelgpu_map_last_timing(FuelMap* map, float ms[8]);
 /* Number of kernels this handle has launched since creation (every <<<>>> is counted). */
 FUELGPU_API int fuelgpu_map_launch_count(FuelMap* map, int64_t* count);
 
+/* Page-lock a long-lived caller buffer (e.g. the std::vector storage of occupancy_buffer_inflate_ /
+ * distance_buffer_ that SDFMap::initMap sizes once, sdf_map.cpp:62-76) so that the H2D / D2H legs run
+ * at full PCIe rate.  Optional; unregistered buffers work, slower.  cudaHostRegister underneath. */
+FUELGPU_API int fuelgpu_host_register(void* ptr, uint64_t bytes);
+FUELGPU_API int fuelgpu_host_unregister(void* ptr);
+
 /* ---- ingest: host occupancy -> resident occupancy byte ------------------------------
  * Replaces nothing in the reference (its buffers are already in RAM); this is the H2D leg.
  * inflate  : occupancy_buffer_inflate_ (char {0,1}), full volume                (sdf_map.h:110)
