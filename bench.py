@@ -288,10 +288,11 @@ class GpuPlanner:
         if not self.overlap:
             out = self.ff.search_box_end()
         m.updateESDF3d()
-        m.download()
+        m.download(wait=not self.overlap)  # overlap: the D2H mirror copy runs beside the solver
         x, f, ne = self.opt.optimizeBatch(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0)
         if self.overlap:
             out = self.ff.search_box_end()
+            m.synchronize()  # ESDF host mirror complete
         self.last_neval = ne
         return out, f
 

@@ -67,6 +67,7 @@ SIGNATURES = {
     "fuelgpu_map_upload_occupancy": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp]),
     "fuelgpu_esdf_update": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "fuelgpu_esdf_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "fuelgpu_esdf_download_async": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fuelgpu_esdf_sample": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "fuelgpu_frontier_search": (C.c_int, [_vp, _vp, _vp, C.POINTER(FuelFrontierParams),
                                           C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),

@@ -156,6 +156,8 @@ int fuelgpu_map_create(const FuelGridDesc* grid, int device_id, FuelMap** out) {
   CR(cudaSetDevice(device_id));
   CR(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   m->stream = m->own_stream;
+  CR(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  CR(cudaEventCreateWithFlags(&m->copy_ev, cudaEventDisableTiming));
   for (int t = 0; t < T_COUNT; ++t) {
     CR(cudaEventCreate(&m->ev0[t]));
     CR(cudaEventCreate(&m->ev1[t]));
@@ -199,6 +201,11 @@ int fuelgpu_map_destroy(FuelMap* m) {
     if (m->ev0[t]) cudaEventDestroy(m->ev0[t]);
     if (m->ev1[t]) cudaEventDestroy(m->ev1[t]);
   }
+  if (m->copy_stream) {
+    cudaStreamSynchronize(m->copy_stream);
+    cudaStreamDestroy(m->copy_stream);
+  }
+  if (m->copy_ev) cudaEventDestroy(m->copy_ev);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
   return 0;
@@ -213,6 +220,7 @@ int fuelgpu_map_set_stream(FuelMap* m, void* cuda_stream) {
 int fuelgpu_map_synchronize(FuelMap* m) {
   if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(m->copy_stream));
   FUEL_CUDA(m, cudaStreamSynchronize(frontier_stream_raw(m)));
   return 0;
 }
@@ -334,6 +342,21 @@ int fuelgpu_esdf_download(FuelMap* m, const int32_t bmin[3], const int32_t bmax[
   }
   tend(m, T_DOWNLOAD);
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int fuelgpu_esdf_download_async(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3], float* out_f32) {
+  if (!m || !out_f32) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  int lo[3], hi[3];
+  int rc = check_box(m, bmin, bmax, lo, hi);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  const int64_t plane = (int64_t)m->g.ny * m->g.nz;
+  const int64_t off = (int64_t)lo[0] * plane;
+  const int64_t cnt = (int64_t)(hi[0] - lo[0] + 1) * plane;
+  FUEL_CUDA(m, cudaEventRecord(m->copy_ev, m->stream));
+  FUEL_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->copy_ev, 0));
+  FUEL_CUDA(m, cudaMemcpyAsync(out_f32 + off, m->dist + off, cnt * 4, cudaMemcpyDeviceToHost, m->copy_stream));
   return 0;
 }
 

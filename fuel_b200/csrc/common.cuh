@@ -44,6 +44,8 @@ struct FuelMap {
   void* stage;
   size_t stage_bytes;
   cudaStream_t own_stream, stream;
+  cudaStream_t copy_stream;  // D2H mirror copies that may overlap the main stream
+  cudaEvent_t copy_ev;
   cudaEvent_t ev0[T_COUNT], ev1[T_COUNT];
   bool ev_valid[T_COUNT];
   FrontierState* fs;

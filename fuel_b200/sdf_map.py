@@ -228,14 +228,17 @@ class SDFMap:
         bmax = np.ascontiguousarray(self.local_bound_max_, dtype=np.int32)
         check(lib().fuelgpu_esdf_update(self._h, ptr(bmin), ptr(bmax), flags), self._h)
 
-    def download(self, bmin=None, bmax=None, dtype=np.float32):
-        """Mirror distance_buffer_ to the host for getDistance()."""
+    def download(self, bmin=None, bmax=None, dtype=np.float32, wait=True):
+        """Mirror distance_buffer_ to the host for getDistance().  wait=False (float32 only) queues
+        the copy behind the ESDF update and returns; the mirror is valid after synchronize()."""
         if self.distance_buffer_ is None or self.distance_buffer_.dtype != dtype:
             self.distance_buffer_ = np.full(self.shape, self.default_dist_, dtype=dtype)
             self.pin(self.distance_buffer_)
         bmin_a = None if bmin is None else np.ascontiguousarray(bmin, dtype=np.int32)
         bmax_a = None if bmax is None else np.ascontiguousarray(bmax, dtype=np.int32)
-        if dtype == np.float32:
+        if dtype == np.float32 and not wait:
+            check(lib().fuelgpu_esdf_download_async(self._h, ptr(bmin_a), ptr(bmax_a), ptr(self.distance_buffer_)), self._h)
+        elif dtype == np.float32:
             check(lib().fuelgpu_esdf_download(self._h, ptr(bmin_a), ptr(bmax_a), ptr(self.distance_buffer_), None), self._h)
         else:
             check(lib().fuelgpu_esdf_download(self._h, ptr(bmin_a), ptr(bmax_a), None, ptr(self.distance_buffer_)), self._h)

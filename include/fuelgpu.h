@@ -110,6 +110,11 @@ FUELGPU_API int fuelgpu_esdf_update(FuelMap* map, const int32_t bmin[3], const i
  * volume layout; the x-slab range of the box is copied. */
 FUELGPU_API int fuelgpu_esdf_download(FuelMap* map, const int32_t bmin[3], const int32_t bmax[3],
                           float* out_f32, double* out_f64);
+/* Same for float32, without blocking: the copy is queued on the handle's copy stream behind the
+ * ESDF update and overlaps whatever runs next on the main stream (the trajectory batch); the host
+ * buffer is valid after fuelgpu_map_synchronize().  Use with a page-locked buffer. */
+FUELGPU_API int fuelgpu_esdf_download_async(FuelMap* map, const int32_t bmin[3], const int32_t bmax[3],
+                                float* out_f32);
 /* Replaces SDFMap::getDistWithGrad (sdf_map.cpp:497-536) = EDTEnvironment::evaluateEDTWithGrad
  * (plan_env/src/edt_environment.cpp:78-87) for n positions.  pos [n][3], dist [n], grad [n][3]. */
 FUELGPU_API int fuelgpu_esdf_sample(FuelMap* map, int64_t n, const double* pos, double* dist, double* grad);
