@@ -458,94 +458,85 @@ int esdf_sample_impl(FuelMap* m, int64_t n, const double* pos, double* d, double
 // columns assembled from G chunks.
 namespace {
 
-// first sweep along y straight from the occupancy byte: 1-D distance to the nearest site on
-// the (x,z) line.  Thread per line, lanes along z.
-__global__ void ysweep_binary_kernel(const uint8_t* __restrict__ occ, int32_t* __restrict__ out,
-                                     int nx, int ny, int nz, int mode) {
+// first sweep along y straight from the occupancy byte: 1-D distance (uint16, voxels) to the
+// nearest site on the (x,z) line.  Thread per line, lanes along z; rows are read U at a time so
+// that every thread keeps U loads in flight (forward pass), then the backward pass folds in the
+// nearest site above.
+constexpr int YB_U = 8;
+__global__ void __launch_bounds__(128) ysweep_binary_kernel(const uint8_t* __restrict__ occ,
+                                                            uint16_t* __restrict__ out, int nx, int ny, int nz,
+                                                            int mode) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)nx * nz) return;
   const int z = (int)(t % nz);
   const int x = (int)(t / nz);
   const int64_t off0 = (int64_t)x * ny * nz + z;
-  int last = -1;
-  for (int y = 0; y < ny; ++y) {
-    if (is_site(occ[off0 + (int64_t)y * nz], mode)) last = y;
-    out[off0 + (int64_t)y * nz] = last < 0 ? INF_I : (y - last);
+  int d = BIG;
+  for (int y0 = 0; y0 < ny; y0 += YB_U) {
+    uint8_t o[YB_U];
+#pragma unroll
+    for (int u = 0; u < YB_U; ++u) o[u] = (y0 + u < ny) ? occ[off0 + (int64_t)(y0 + u) * nz] : 0;
+#pragma unroll
+    for (int u = 0; u < YB_U; ++u) {
+      if (y0 + u < ny) {
+        d = is_site(o[u], mode) ? 0 : min(d + 1, BIG);
+        out[off0 + (int64_t)(y0 + u) * nz] = d >= BIG ? INF16 : (uint16_t)d;
+      }
+    }
   }
-  int nxt = -1;
-  for (int y = ny - 1; y >= 0; --y) {
-    int d = out[off0 + (int64_t)y * nz];
-    if (d == 0) nxt = y;
-    int dr = nxt < 0 ? INF_I : (nxt - y);
-    d = min(d, dr);
-    out[off0 + (int64_t)y * nz] = (d == INF_I) ? INF_I : d * d;
+  int dr = BIG;
+  for (int y1 = ny - 1; y1 >= 0; y1 -= YB_U) {
+    uint16_t v[YB_U];
+#pragma unroll
+    for (int u = 0; u < YB_U; ++u) v[u] = (y1 - u >= 0) ? out[off0 + (int64_t)(y1 - u) * nz] : INF16;
+#pragma unroll
+    for (int u = 0; u < YB_U; ++u) {
+      if (y1 - u >= 0) {
+        const int dl = v[u] == INF16 ? BIG : (int)v[u];
+        dr = dl == 0 ? 0 : min(dr + 1, BIG);
+        const int m = min(dl, dr);
+        if (m != dl) out[off0 + (int64_t)(y1 - u) * nz] = m >= BIG ? INF16 : (uint16_t)m;
+      }
+    }
   }
 }
 
-// final z sweep over columns split in G chunks [G][nxl][ny][nzl]; thread per column.
-// z is contiguous inside a chunk; columns are strided by nzl so this kernel stages through
-// a per-thread walk (the volume of this pass is 1/G of the map per rank).
-__global__ void zsweep_chunks_kernel(const int32_t* __restrict__ in, float* __restrict__ out,
-                                     uint32_t* __restrict__ stk, int G, int nxl, int ny, int nzl,
-                                     float res) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t ncol = (int64_t)nxl * ny;
-  if (t >= ncol) return;
-  const int n = G * nzl;
-  const int64_t chunk = ncol * nzl;
-  const int64_t col = t * nzl;
-  const int64_t so = t * (int64_t)n;  // stack and output are [nxl][ny][G*nzl]
-  int k = -1;
-  int v1 = 0, h1 = 0, v0 = 0, h0 = 0;
-  for (int q = 0; q < n; ++q) {
-    const int f = in[(int64_t)(q / nzl) * chunk + col + (q % nzl)];
-    if (f >= INF_I) continue;
-    const int h = f + q * q;
-    while (k >= 1) {
-      const long long lhs = (long long)(h - h1) * (long long)(v1 - v0);
-      const long long rhs = (long long)(h1 - h0) * (long long)(q - v1);
-      if (lhs > rhs) break;
-      --k;
-      v1 = v0;
-      h1 = h0;
-      if (k >= 1) {
-        const uint32_t e = stk[so + (k - 1)];
-        v0 = unpack_v(e);
-        h0 = unpack_h(e);
-      }
-    }
-    ++k;
-    stk[so + k] = pack_vh(q, h);
-    v0 = v1;
-    h0 = h1;
-    v1 = q;
-    h1 = h;
+// [G][nxl][ny][nzl] chunks (z fastest inside a chunk) -> [nxl][nz][ny] (y fastest), 32x32 tiles
+// through shared memory so that both sides are coalesced.
+__global__ void __launch_bounds__(256) chunks_to_zy_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                           int G, int nxl, int ny, int nzl) {
+  __shared__ int32_t tile[32][33];
+  const int nz = G * nzl;
+  const int x = blockIdx.z;
+  const int y0 = blockIdx.y * 32, z0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t chunk = (int64_t)nxl * ny * nzl;
+  for (int r = ty; r < 32; r += 8) {
+    const int y = y0 + r, z = z0 + tx;
+    if (y < ny && z < nz) tile[r][tx] = in[(int64_t)(z / nzl) * chunk + ((int64_t)x * ny + y) * nzl + (z % nzl)];
   }
-  const int kmax = k;
-  if (kmax < 0) {
-    for (int q = 0; q < n; ++q) out[so + q] = __int_as_float(0x7f800000);
-    return;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int z = z0 + r, y = y0 + tx;
+    if (y < ny && z < nz) out[((int64_t)x * nz + z) * ny + y] = tile[tx][r];
   }
-  int kc = 0;
-  uint32_t e = stk[so];
-  int vc = unpack_v(e), hc = unpack_h(e), vn = 0, hn = 0;
-  if (kmax >= 1) {
-    e = stk[so + 1];
-    vn = unpack_v(e);
-    hn = unpack_h(e);
+}
+
+// [nxl][nz][ny] (y fastest) -> [nxl][ny][nz] (z fastest, the reference layout)
+__global__ void __launch_bounds__(256) zy_to_yz_kernel(const float* __restrict__ in, float* __restrict__ out, int nxl,
+                                                       int ny, int nz) {
+  __shared__ float tile[32][33];
+  const int x = blockIdx.z;
+  const int y0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int z = z0 + r, y = y0 + tx;
+    if (y < ny && z < nz) tile[r][tx] = in[((int64_t)x * nz + z) * ny + y];
   }
-  for (int q = 0; q < n; ++q) {
-    while (kc < kmax && (hn - hc) < 2 * q * (vn - vc)) {
-      ++kc;
-      vc = vn;
-      hc = hn;
-      if (kc < kmax) {
-        e = stk[so + kc + 1];
-        vn = unpack_v(e);
-        hn = unpack_h(e);
-      }
-    }
-    out[so + q] = res * sqrtf((float)(hc + q * q - 2 * q * vc));
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int y = y0 + r, z = z0 + tx;
+    if (y < ny && z < nz) out[((int64_t)x * ny + y) * nz + z] = tile[tx][r];
   }
 }
 
@@ -554,13 +545,11 @@ __global__ void zsweep_chunks_kernel(const int32_t* __restrict__ in, float* __re
 int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl, int flags,
                     int32_t* g2, int32_t* scratch) {
   const int mode = (flags & FUELGPU_ESDF_OPTIMISTIC) ? 0 : 1;
-  // y sweep from the bytes into scratch (used as g1), x sweep scratch -> g2 with the hull
-  // stack aliased on g2's own lines is not possible (in/out differ), so the stack uses the
-  // upper half of scratch: scratch must hold 2*nx*ny*nzl int32.
-  int32_t* g1 = scratch;
+  // scratch (2 * nx*ny*nzl int32): first half = uint16 y distances, second half = hull stacks
+  uint16_t* g1h = (uint16_t*)scratch;
   uint32_t* stk = (uint32_t*)(scratch + (int64_t)nx * ny * nzl);
   const int64_t nl = (int64_t)nx * nzl;
-  ysweep_binary_kernel<<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(occ, g1, nx, ny, nzl, mode);
+  ysweep_binary_kernel<<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(occ, g1h, nx, ny, nzl, mode);
   LineMap lm;
   lm.n = nx;
   lm.stride = (int64_t)ny * nzl;
@@ -569,14 +558,30 @@ int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl,
   lm.outer_stride = nzl;
   lm.base = 0;
   const int64_t nl2 = (int64_t)nzl * ny;
-  envelope_kernel<false, false, 8><<<(unsigned)((nl2 + 127) / 128), 128, 0, s>>>(g1, g2, stk, lm, 0.f);
+  envelope_kernel<true, false, 16><<<(unsigned)((nl2 + 127) / 128), 128, 0, s>>>(g1h, g2, stk, lm, 0.f);
   return cudaGetLastError() == cudaSuccess ? 0 : FUELGPU_ECUDA;
 }
 
 int edt_z_chunks_dev_impl(cudaStream_t s, const int32_t* g2c, int G, int nxl, int ny, int nzl,
                           double res, float* out, int32_t* scratch) {
-  const int64_t ncol = (int64_t)nxl * ny;
-  zsweep_chunks_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, s>>>(g2c, out, (uint32_t*)scratch, G,
-                                                                    nxl, ny, nzl, (float)res);
+  // scratch (2 * nxl*ny*nz int32): T = the chunks transposed to [nxl][nz][ny] (y fastest, so the
+  // z sweep has its lanes along a contiguous axis), T2 = the fp32 result in the same layout.
+  const int nz = G * nzl;
+  const int64_t voxl = (int64_t)nxl * ny * nz;
+  int32_t* T = scratch;
+  float* T2 = (float*)(scratch + voxl);
+  dim3 g1((nz + 31) / 32, (ny + 31) / 32, nxl);
+  chunks_to_zy_kernel<<<g1, 256, 0, s>>>(g2c, T, G, nxl, ny, nzl);
+  LineMap lm;
+  lm.n = nz;
+  lm.stride = ny;
+  lm.nz_run = ny;
+  lm.n_outer = nxl;
+  lm.outer_stride = (int64_t)nz * ny;
+  lm.base = 0;
+  const int64_t nl = (int64_t)ny * nxl;
+  envelope_kernel<false, true, 8><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(T, T2, (uint32_t*)T, lm, (float)res);
+  dim3 g2((ny + 31) / 32, (nz + 31) / 32, nxl);
+  zy_to_yz_kernel<<<g2, 256, 0, s>>>(T2, out, nxl, ny, nz);
   return cudaGetLastError() == cudaSuccess ? 0 : FUELGPU_ECUDA;
 }

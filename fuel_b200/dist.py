@@ -42,7 +42,7 @@ def _gpu_z(chunks, resolution):
     """[G,nxl,ny,nzl] int32 chunks -> [nxl,ny,G*nzl] float32 metres."""
     G, nxl, ny, nzl = chunks.shape
     out = torch.empty((nxl, ny, G * nzl), dtype=torch.float32, device=chunks.device)
-    scratch = torch.empty((nxl, ny, G * nzl), dtype=torch.int32, device=chunks.device)
+    scratch = torch.empty((2, nxl, ny, G * nzl), dtype=torch.int32, device=chunks.device)
     st = torch.cuda.current_stream(chunks.device).cuda_stream
     rc = _lib.lib().fuelgpu_edt_z_chunks_dev(C.c_void_p(st), C.c_void_p(chunks.data_ptr()), G, nxl, ny, nzl,
                                              float(resolution), C.c_void_p(out.data_ptr()),

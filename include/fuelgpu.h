@@ -238,7 +238,8 @@ FUELGPU_API int fuelgpu_bspline_optimize_batch_dev(FuelMap* map, int32_t B, int3
  * These operate on caller-owned DEVICE buffers so that torch.distributed/NCCL can move
  * them between ranks.  A slab is nx*ny*nzl voxels, z fastest.
  * xy passes: occupancy byte slab -> squared 2-D distance (int32, FUELGPU_EDT_INF = none)
- * z pass   : G received chunks [G][nxl][ny][nzl] -> float32 metres [nxl][ny][G*nzl]       */
+ * z pass   : G received chunks [G][nxl][ny][nzl] -> float32 metres [nxl][ny][G*nzl]
+ * scratch  : xy: 2*nx*ny*nzl int32;  z: 2*nxl*ny*(G*nzl) int32                               */
 #define FUELGPU_EDT_INF 0x3fffffff
 FUELGPU_API int fuelgpu_edt_xy_dev(void* cuda_stream, const void* occ_slab, int32_t nx, int32_t ny,
                        int32_t nzl, int flags, void* g2_out_i32, void* scratch_i32);

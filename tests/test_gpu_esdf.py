@@ -135,3 +135,35 @@ def test_sample_matches_getDistWithGrad(fuel, orc):
     assert np.allclose(dg, dr, rtol=1e-12, atol=1e-12)
     assert np.allclose(gg, gr, rtol=1e-12, atol=1e-10)
     m.close()
+
+
+@pytest.mark.parametrize("n", [(1024, 6, 5), (5, 1024, 6), (6, 5, 1024), (1024, 3, 1024)])
+def test_maximum_axis_extent(fuel, orc, n):
+    """1024 voxels per axis is the ABI limit (hull entries pack v in 10 bits, h in 22): distances up to
+    sqrt(2*1023^2 + ...) voxels must still be exact."""
+    g = W.Grid(n, (0, 0, 0), 0.1)
+    inflate = np.zeros(n, dtype=np.int8)
+    inflate[0, 0, 0] = 1
+    inflate[n[0] - 1, n[1] - 1, n[2] // 2] = 1
+    tri = np.full(n, W.FREE, dtype=np.uint8)
+    m = make_sdf_map(fuel, g, inflate, tri, optimistic=True)
+    m.updateESDF3d()
+    got = m.download().copy()
+    ref = orc.update_esdf3d(orc_grid(orc, g), inflate, tri, [0, 0, 0], np.array(n) - 1, True, False, threads=8)
+    compare(got, ref)
+    m.close()
+
+
+def test_rejects_bad_arguments(fuel):
+    with pytest.raises(fuel.FuelGpuError):
+        fuel.SDFMap((1025, 4, 4), 0.1, (0, 0, 0))  # beyond the 1024-per-axis limit
+    with pytest.raises(fuel.FuelGpuError):
+        fuel.SDFMap((8, 8, 8), -0.1, (0, 0, 0))
+    m = fuel.SDFMap((8, 8, 8), 0.1, (0, 0, 0))
+    m.local_bound_min_, m.local_bound_max_ = np.array([0, 0, 0]), np.array([8, 7, 7])  # outside the map
+    with pytest.raises(fuel.FuelGpuError):
+        m.updateESDF3d()
+    m.local_bound_min_, m.local_bound_max_ = np.array([3, 3, 3]), np.array([2, 7, 7])  # empty box
+    with pytest.raises(fuel.FuelGpuError):
+        m.updateESDF3d()
+    m.close()

@@ -46,6 +46,20 @@ for _ in range(5):
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms.append(float(t.item()))
+# stage breakdown on this rank
+from fuel_b200.dist import exchange_z_to_x  # noqa: E402
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+ev[0].record(st)
+g2 = sh.xy_fn(occ)
+ev[1].record(st)
+ch = exchange_z_to_x(g2)
+ev[2].record(st)
+part = sh.z_fn(ch)
+ev[3].record(st)
+torch.cuda.synchronize()
+if rank == 0:
+    print("rank0 stages ms: xy %.3f  exchange %.3f  z %.3f" % (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]),
+                                                           ev[2].elapsed_time(ev[3])))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(st)
 full = sh.gather_full(part)
