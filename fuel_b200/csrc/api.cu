@@ -304,6 +304,42 @@ int fuelgpu_map_upload_occupancy(FuelMap* m, const int8_t* inflate, const double
   return 0;
 }
 
+__global__ void split_occ_kernel(const uint8_t* __restrict__ occ, int8_t* __restrict__ inf, uint8_t* __restrict__ tri,
+                                 int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t o = occ[i];
+  if (inf) inf[i] = (o >> 2) & 1;
+  if (tri) tri[i] = o & 3;
+}
+
+int fuelgpu_map_inflate(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3], int32_t inf_step,
+                        int32_t virtual_ceil_idx) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  if (inf_step < 0 || inf_step > 16) return fuel_fail(m, FUELGPU_EINVAL, "inf_step out of range");
+  int lo[3], hi[3];
+  int rc = check_box(m, bmin, bmax, lo, hi);
+  if (rc) return rc;
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return map_inflate_impl(m, lo, hi, inf_step, virtual_ceil_idx);
+}
+
+int fuelgpu_map_download_occupancy(FuelMap* m, int8_t* inflate, uint8_t* tristate) {
+  if (!m || (!inflate && !tristate)) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  int rc = ensure_stage(m, (size_t)m->nvox * 2);
+  if (rc) return rc;
+  int8_t* d_inf = (int8_t*)m->stage;
+  uint8_t* d_tri = (uint8_t*)m->stage + m->nvox;
+  split_occ_kernel<<<(unsigned)((m->nvox + 255) / 256), 256, 0, m->stream>>>(m->occ, d_inf, d_tri, m->nvox);
+  FUEL_LAUNCHES(m, 1);
+  FUEL_CUDA(m, cudaGetLastError());
+  if (inflate) FUEL_CUDA(m, cudaMemcpyAsync(inflate, d_inf, m->nvox, cudaMemcpyDeviceToHost, m->stream));
+  if (tristate) FUEL_CUDA(m, cudaMemcpyAsync(tristate, d_tri, m->nvox, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
 int fuelgpu_esdf_update(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3], int flags) {
   if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
   int lo[3], hi[3];

@@ -88,6 +88,7 @@ __host__ __device__ static inline int64_t addr_of(const Geom& g, int x, int y, i
 
 // ---- stage entry points implemented per .cu file ----
 int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags);
+int map_inflate_impl(FuelMap* m, const int bmin[3], const int bmax[3], int step, int ceil_id);
 int esdf_sample_impl(FuelMap* m, int64_t n, const double* pos_dev, double* dist_dev, double* grad_dev);
 int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl, int flags,
                     int32_t* g2, int32_t* scratch);

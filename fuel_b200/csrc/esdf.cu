@@ -443,6 +443,68 @@ int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags
   return 0;
 }
 
+// ---- obstacle inflation: SDFMap::clearAndInflateLocalMap (sdf_map.cpp:364-472) -----------------
+namespace {
+__global__ void inflate_clear_kernel(uint8_t* __restrict__ occ, int ny, int nz, Box b) {
+  const int nzb = b.hi[2] - b.lo[2] + 1, nyb = b.hi[1] - b.lo[1] + 1, nxb = b.hi[0] - b.lo[0] + 1;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)nzb * nyb * nxb) return;
+  const int z = b.lo[2] + (int)(t % nzb);
+  const int y = b.lo[1] + (int)((t / nzb) % nyb);
+  const int x = b.lo[0] + (int)(t / ((int64_t)nzb * nyb));
+  const int64_t a = ((int64_t)x * ny + y) * nz + z;
+  occ[a] &= (uint8_t)~4u;  // :440-444
+}
+// one thread per voxel of the box; an occupied voxel stamps its (2s+1)^3 neighbourhood.  The
+// reference checks only the LINEAR address of a stamp cell (:452-458), so stamps wrap across rows
+// at the map faces; the same arithmetic is used here.  All writers set the same bit of a byte.
+__global__ void inflate_stamp_kernel(uint8_t* __restrict__ occ, int ny, int nz, int64_t nvox, Box b, int step) {
+  const int nzb = b.hi[2] - b.lo[2] + 1, nyb = b.hi[1] - b.lo[1] + 1, nxb = b.hi[0] - b.lo[0] + 1;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)nzb * nyb * nxb) return;
+  const int z = b.lo[2] + (int)(t % nzb);
+  const int y = b.lo[1] + (int)((t / nzb) % nyb);
+  const int x = b.lo[0] + (int)(t / ((int64_t)nzb * nyb));
+  if ((occ[((int64_t)x * ny + y) * nz + z] & 3) != FUELGPU_OCCUPIED) return;
+  for (int dx = -step; dx <= step; ++dx)
+    for (int dy = -step; dy <= step; ++dy)
+      for (int dz = -step; dz <= step; ++dz) {
+        const int64_t a = ((int64_t)(x + dx) * ny + (y + dy)) * nz + (z + dz);
+        if (a >= 0 && a < nvox) {
+          const uint8_t o = occ[a];
+          if (!(o & 4)) occ[a] = o | 4;
+        }
+      }
+}
+__global__ void ceiling_kernel(uint8_t* __restrict__ occ, int ny, int nz, Box b, int ceil_id) {
+  const int nyb = b.hi[1] - b.lo[1] + 1, nxb = b.hi[0] - b.lo[0] + 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nyb * nxb) return;
+  const int y = b.lo[1] + t % nyb, x = b.lo[0] + t / nyb;
+  const int64_t a = ((int64_t)x * ny + y) * nz + ceil_id;
+  occ[a] = (uint8_t)((occ[a] & ~3u) | FUELGPU_OCCUPIED);  // occupancy_buffer_ = clamp_max_log_ (:463-470)
+}
+}  // namespace
+
+int map_inflate_impl(FuelMap* m, const int bmin[3], const int bmax[3], int step, int ceil_id) {
+  Box b;
+  for (int i = 0; i < 3; ++i) {
+    b.lo[i] = bmin[i];
+    b.hi[i] = bmax[i];
+  }
+  const int64_t nb = (int64_t)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
+  inflate_clear_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, m->stream>>>(m->occ, m->g.ny, m->g.nz, b);
+  inflate_stamp_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, m->stream>>>(m->occ, m->g.ny, m->g.nz, m->nvox, b, step);
+  FUEL_LAUNCHES(m, 2);
+  if (ceil_id >= 0 && ceil_id < m->g.nz) {
+    const int n2 = (b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1);
+    ceiling_kernel<<<(n2 + 255) / 256, 256, 0, m->stream>>>(m->occ, m->g.ny, m->g.nz, b, ceil_id);
+    FUEL_LAUNCHES(m, 1);
+  }
+  FUEL_CUDA(m, cudaGetLastError());
+  return 0;
+}
+
 int esdf_sample_impl(FuelMap* m, int64_t n, const double* pos, double* d, double* grad) {
   if (n <= 0) return 0;
   sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, m->stream>>>(m->g, m->dist, n, pos, d, grad);

@@ -220,6 +220,19 @@ class SDFMap:
             check(lib().fuelgpu_map_upload_occupancy(self._h, ptr(inf), None, ptr(tri), self.clamp_min_log_,
                                                      self.min_occupancy_log_, ptr(bmin_a), ptr(bmax_a)), self._h)
 
+    def clearAndInflateLocalMap(self, obstacles_inflation=0.199, virtual_ceil_height=-10.0):
+        """sdf_map.cpp:364-472 on the resident occupancy byte over [local_bound_min_, local_bound_max_];
+        defaults = exploration_manager/launch/algorithm.xml:38,51.  The host mirrors are refreshed."""
+        inf_step = int(math.ceil(obstacles_inflation / self.resolution_))  # :436
+        ceil_id = -1
+        if virtual_ceil_height > -0.5:  # :462
+            ceil_id = int(math.floor((virtual_ceil_height - self.map_origin_[2]) * self.resolution_inv_))
+        bmin = np.ascontiguousarray(self.local_bound_min_, dtype=np.int32)
+        bmax = np.ascontiguousarray(self.local_bound_max_, dtype=np.int32)
+        check(lib().fuelgpu_map_inflate(self._h, ptr(bmin), ptr(bmax), inf_step, ceil_id), self._h)
+        check(lib().fuelgpu_map_download_occupancy(self._h, ptr(self.occupancy_buffer_inflate_),
+                                                   ptr(self.occupancy_tri_)), self._h)
+
     # ---- ESDF ------------------------------------------------------------------------------
     def updateESDF3d(self):
         """sdf_map.cpp:152-241 over [local_bound_min_, local_bound_max_]."""

@@ -97,6 +97,18 @@ FUELGPU_API int fuelgpu_map_upload_occupancy(FuelMap* map, const int8_t* inflate
                                  double min_occupancy_log, const int32_t bmin[3],
                                  const int32_t bmax[3]);
 
+/* Replaces SDFMap::clearAndInflateLocalMap (plan_env/src/sdf_map.cpp:364-472), the step between the
+ * occupancy fusion and updateESDF3d, on the resident occupancy byte: the inflate bit
+ * is cleared inside [bmin,bmax] and every OCCUPIED voxel of the box stamps its (2*inf_step+1)^3
+ * neighbourhood (inf_step = ceil(obstacles_inflation_/resolution_), :436), with the reference's
+ * linear-address-only bounds check (:452-458).  virtual_ceil_idx >= 0 marks z = idx OCCUPIED for the
+ * box's (x,y) (:462-470); pass -1 when virtual_ceil_height_ <= -0.5.  Read the bytes back with
+ * fuelgpu_map_download_occupancy. */
+FUELGPU_API int fuelgpu_map_inflate(FuelMap* map, const int32_t bmin[3], const int32_t bmax[3], int32_t inf_step,
+                        int32_t virtual_ceil_idx);
+/* Resident occupancy byte -> host: inflate (int8 {0,1}) and/or tristate (uint8), full volume. */
+FUELGPU_API int fuelgpu_map_download_occupancy(FuelMap* map, int8_t* inflate, uint8_t* tristate);
+
 /* ---- ESDF -------------------------------------------------------------------------- */
 #define FUELGPU_ESDF_OPTIMISTIC 1 /* mp_->optimistic_  (sdf_map.cpp:156) */
 #define FUELGPU_ESDF_SIGNED 2     /* mp_->signed_dist_ (sdf_map.cpp:201) */

@@ -216,6 +216,16 @@ public:
                                         distance_buffer_.data()),
                   gpu_);
   }
+  // clearAndInflateLocalMap (sdf_map.cpp:364-472) on the resident occupancy byte (the byte must have been
+  // uploaded, e.g. by the previous updateESDF3d); refreshes occupancy_buffer_inflate_
+  void clearAndInflateLocalMap(double obstacles_inflation, double virtual_ceil_height) {
+    const int inf_step = (int)std::ceil(obstacles_inflation / mp_.resolution_);
+    const int ceil_id = virtual_ceil_height > -0.5
+                            ? (int)std::floor((virtual_ceil_height - mp_.map_origin_(2)) * resolution_inv_)
+                            : -1;
+    fuelgpu_check(fuelgpu_map_inflate(gpu_, local_bound_min_.data(), local_bound_max_.data(), inf_step, ceil_id), gpu_);
+    fuelgpu_check(fuelgpu_map_download_occupancy(gpu_, occupancy_buffer_inflate_.data(), nullptr), gpu_);
+  }
   // getDistWithGrad (sdf_map.cpp:497-536) on the device ESDF
   double getDistWithGrad(const Vector3d& pos, Vector3d& grad) {
     double d = 0;

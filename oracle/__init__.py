@@ -139,6 +139,14 @@ def update_esdf3d(g, inflate, tri, bmin, bmax, optimistic, signed_dist, dist=Non
     return dist
 
 
+def clear_and_inflate(g, tri, inflate, bmin, bmax, inf_step, ceil_id=-1):
+    """clearAndInflateLocalMap (sdf_map.cpp:364-472); tri (uint8) and inflate (int8) are updated in place."""
+    assert tri.dtype == np.uint8 and inflate.dtype == np.int8 and tri.flags["C_CONTIGUOUS"] and inflate.flags["C_CONTIGUOUS"]
+    bmin = np.ascontiguousarray(bmin, dtype=np.int32)
+    bmax = np.ascontiguousarray(bmax, dtype=np.int32)
+    lib().orc_clear_and_inflate(C.byref(g), _p(tri), _p(inflate), _p(bmin), _p(bmax), C.c_int(inf_step), C.c_int(ceil_id))
+
+
 def dist_with_grad(g, dist_buf, pos):
     pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
     dist_buf = np.ascontiguousarray(dist_buf, dtype=np.float64)

@@ -204,6 +204,35 @@ void orc_update_esdf3d(const OrcGrid* g, const int8_t* inflate, const uint8_t* t
   }
 }
 
+/* clearAndInflateLocalMap, sdf_map.cpp:364-472 */
+void orc_clear_and_inflate(const OrcGrid* g, uint8_t* tri, int8_t* inflate, const int32_t bmin[3],
+                           const int32_t bmax[3], int inf_step, int ceil_id) {
+  const int64_t nvox = (int64_t)g->n[0] * g->n[1] * g->n[2];
+  /* clean outdated occupancy, :440-444 */
+  for (int x = bmin[0]; x <= bmax[0]; ++x)
+    for (int y = bmin[1]; y <= bmax[1]; ++y)
+      for (int z = bmin[2]; z <= bmax[2]; ++z) inflate[to_address(g, x, y, z)] = 0;
+  /* inflate newest occupied cells, :447-460; inflatePoint "all inflate", sdf_map.h:257-264 */
+  for (int x = bmin[0]; x <= bmax[0]; ++x)
+    for (int y = bmin[1]; y <= bmax[1]; ++y)
+      for (int z = bmin[2]; z <= bmax[2]; ++z) {
+        if (tri[to_address(g, x, y, z)] == ORC_OCCUPIED) { /* occupancy_buffer_ > min_occupancy_log_ */
+          for (int dx = -inf_step; dx <= inf_step; ++dx)
+            for (int dy = -inf_step; dy <= inf_step; ++dy)
+              for (int dz = -inf_step; dz <= inf_step; ++dz) {
+                /* toAddress on the raw (possibly out-of-range) index, checked only as a linear
+                 * address: :452-458 */
+                const int64_t idx_inf = to_address(g, x + dx, y + dy, z + dz);
+                if (idx_inf >= 0 && idx_inf < nvox) inflate[idx_inf] = 1;
+              }
+        }
+      }
+  /* virtual ceiling, :462-470: occupancy_buffer_ = clamp_max_log_ (-> OCCUPIED) */
+  if (ceil_id >= 0 && ceil_id < g->n[2])
+    for (int x = bmin[0]; x <= bmax[0]; ++x)
+      for (int y = bmin[1]; y <= bmax[1]; ++y) tri[to_address(g, x, y, ceil_id)] = ORC_OCCUPIED;
+}
+
 /* getDistance(idx), sdf_map.h:228-231 */
 static inline double get_distance(const OrcGrid* g, const double* dist_buf, const int32_t id[3]) {
   if (!is_in_map_idx(g, id)) return -1;

@@ -63,6 +63,17 @@ void orc_update_esdf3d(const OrcGrid* g, const int8_t* inflate, const uint8_t* t
                        int signed_dist, double* dist, double* dist_neg, double* tmp1,
                        double* tmp2, int threads);
 
+/* clearAndInflateLocalMap, sdf_map.cpp:364-472 (the step right before updateESDF3d).
+ * tri     : getOccupancy() of occupancy_buffer_ (in/out: the virtual ceiling writes clamp_max_log_,
+ *           i.e. OCCUPIED, at z = ceil_id, :463-470)
+ * inflate : occupancy_buffer_inflate_ (in/out)
+ * inf_step: ceil(obstacles_inflation_ / resolution_) (:436); the stamp is (2*inf_step+1)^3 ("all inflate",
+ *           sdf_map.h:257-264).  The linear-address-only bounds check of :452-458 (stamps wrap across
+ *           rows at the map faces) is reproduced as written.
+ * ceil_id : floor((virtual_ceil_height_ - origin_z) * resolution_inv_), or < 0 to disable (:462) */
+void orc_clear_and_inflate(const OrcGrid* g, uint8_t* tri, int8_t* inflate, const int32_t bmin[3],
+                           const int32_t bmax[3], int inf_step, int ceil_id);
+
 /* sdf_map.cpp:497-536 getDistWithGrad (via EDTEnvironment::evaluateEDTWithGrad,
  * edt_environment.cpp:78-87).  dist_buf = distance_buffer_. */
 double orc_dist_with_grad(const OrcGrid* g, const double* dist_buf, const double pos[3],
