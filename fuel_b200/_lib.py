@@ -32,6 +32,11 @@ class FuelFrontierParams(C.Structure):
                 ("down_sample", C.c_int32), ("min_z", C.c_double)]
 
 
+class FuelFusionParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in
+                ("p_hit", "p_miss", "p_min", "p_max", "p_occ", "max_ray_length", "local_bound_inflate")]
+
+
 class FuelOptParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in
                 ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide", "ld_waypt",
@@ -67,6 +72,10 @@ SIGNATURES = {
     "fuelgpu_map_upload_occupancy": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp]),
     "fuelgpu_map_inflate": (C.c_int, [_vp, _vp, _vp, _i32, _i32]),
     "fuelgpu_map_download_occupancy": (C.c_int, [_vp, _vp, _vp]),
+    "fuelgpu_map_input_point_cloud": (C.c_int, [_vp, _vp, _i32, _vp, C.POINTER(FuelFusionParams), _vp, _vp]),
+    "fuelgpu_map_get_updated_box": (C.c_int, [_vp, _vp, _vp, _i32]),
+    "fuelgpu_map_set_logodds": (C.c_int, [_vp, _vp, _dbl, _dbl]),
+    "fuelgpu_map_get_logodds": (C.c_int, [_vp, _vp]),
     "fuelgpu_esdf_update": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "fuelgpu_esdf_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "fuelgpu_esdf_download_async": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -194,6 +194,7 @@ int fuelgpu_map_destroy(FuelMap* m) {
   cudaSetDevice(m->dev);
   if (m->own_stream) cudaStreamSynchronize(m->own_stream);
   frontier_state_destroy(m);
+  fusion_state_destroy(m);
   void* ptrs[] = { m->occ, m->dist, m->dist_neg, m->flag, m->g1, m->g2, m->stk, m->stage, m->bs_buf };
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -322,6 +323,38 @@ int fuelgpu_map_inflate(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3]
   if (rc) return rc;
   FUEL_CUDA(m, cudaSetDevice(m->dev));
   return map_inflate_impl(m, lo, hi, inf_step, virtual_ceil_idx);
+}
+
+int fuelgpu_map_input_point_cloud(FuelMap* m, const float* points, int32_t point_num, const double camera_pos[3],
+                                  const FuelFusionParams* p, int32_t local_bound_min[3], int32_t local_bound_max[3]) {
+  if (!m || !camera_pos || !p || !local_bound_min || !local_bound_max || (point_num > 0 && !points))
+    return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (point_num < 0) return fuel_fail(m, FUELGPU_EINVAL, "negative point count");
+  const double pr[5] = { p->p_hit, p->p_miss, p->p_min, p->p_max, p->p_occ };
+  for (double v : pr)
+    if (!(v > 0.0 && v < 1.0)) return fuel_fail(m, FUELGPU_EINVAL, "fusion probabilities must lie in (0,1)");
+  if (!(p->max_ray_length > 0.0)) return fuel_fail(m, FUELGPU_EINVAL, "max_ray_length must be positive");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return fusion_input_impl(m, points, point_num, camera_pos, p, local_bound_min, local_bound_max);
+}
+
+int fuelgpu_map_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int32_t reset) {
+  if (!m || !bmin || !bmax) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  fusion_get_updated_box(m, bmin, bmax, reset);
+  return FUELGPU_OK;
+}
+
+int fuelgpu_map_set_logodds(FuelMap* m, const double* logodds, double p_min, double p_occ) {
+  if (!m || !logodds) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (!(p_min > 0.0 && p_min < 1.0 && p_occ > 0.0 && p_occ < 1.0)) return fuel_fail(m, FUELGPU_EINVAL, "probability out of (0,1)");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return fusion_set_logodds(m, logodds, p_min, p_occ);
+}
+
+int fuelgpu_map_get_logodds(FuelMap* m, double* logodds) {
+  if (!m || !logodds) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return fusion_get_logodds(m, logodds);
 }
 
 int fuelgpu_map_download_occupancy(FuelMap* m, int8_t* inflate, uint8_t* tristate) {

@@ -24,6 +24,7 @@ struct Geom {
 enum { T_ESDF = 0, T_FRONTIER = 1, T_BSPLINE = 2, T_UPLOAD = 3, T_DOWNLOAD = 4, T_COUNT = 8 };
 
 struct FrontierState;  // frontier.cu
+struct FusionState;    // fusion.cu
 
 struct FuelMap {
   FuelGridDesc desc;
@@ -49,6 +50,7 @@ struct FuelMap {
   cudaEvent_t ev0[T_COUNT], ev1[T_COUNT];
   bool ev_valid[T_COUNT];
   FrontierState* fs;
+  FusionState* fus;  // lazily created by the first fusion call
   // bspline scratch (device)
   void* bs_buf;
   size_t bs_bytes;
@@ -94,6 +96,13 @@ int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl,
                     int32_t* g2, int32_t* scratch);
 int edt_z_chunks_dev_impl(cudaStream_t s, const int32_t* g2c, int G, int nxl, int ny, int nzl,
                           double res, float* out, int32_t* scratch);
+
+int fusion_input_impl(FuelMap* m, const float* pts_host, int n, const double cam[3], const FuelFusionParams* p,
+                      int32_t lbmin[3], int32_t lbmax[3]);
+int fusion_set_logodds(FuelMap* m, const double* logodds_host, double p_min, double p_occ);
+int fusion_get_logodds(FuelMap* m, double* out);
+void fusion_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int reset);
+void fusion_state_destroy(FuelMap* m);
 
 int frontier_state_create(FuelMap* m);
 // The frontier subsystem runs on its own stream (it only reads `occ` and owns `flag`), so a host

@@ -54,6 +54,8 @@ class SDFMap:
         self.update_min_ = np.zeros(3)
         self.update_max_ = np.zeros(3)
         self.reset_updated_box_ = True
+        self._fusion = None
+        self._fused = False
 
         d = FuelGridDesc()
         for i in range(3):
@@ -160,10 +162,52 @@ class SDFMap:
         return self.box_mind_.copy(), self.box_maxd_.copy()
 
     def getUpdatedBox(self, reset=False):
+        """sdf_map.cpp:491-495; once inputPointCloud has run the box lives in the device handle."""
+        if self._fused:
+            bmin, bmax = np.zeros(3), np.zeros(3)
+            check(lib().fuelgpu_map_get_updated_box(self._h, ptr(bmin), ptr(bmax), 1 if reset else 0), self._h)
+            return bmin, bmax
         bmin, bmax = self.update_min_.copy(), self.update_max_.copy()
         if reset:
             self.reset_updated_box_ = True
         return bmin, bmax
+
+    # ---- occupancy fusion (sdf_map.cpp:259-345) ---------------------------------------------
+    def setFusionParams(self, p_hit=0.65, p_miss=0.35, p_min=0.12, p_max=0.90, p_occ=0.80, max_ray_length=4.5,
+                        local_bound_inflate=0.5):
+        """sdf_map/* parameters read in initMap (sdf_map.cpp:19-47); defaults algorithm.xml:39-50."""
+        fp = _lib.FuelFusionParams()
+        fp.p_hit, fp.p_miss, fp.p_min, fp.p_max, fp.p_occ = p_hit, p_miss, p_min, p_max, p_occ
+        fp.max_ray_length, fp.local_bound_inflate = max_ray_length, local_bound_inflate
+        self._fusion = fp
+        self.clamp_min_log_, self.min_occupancy_log_ = logit(p_min), logit(p_occ)
+
+    def inputPointCloud(self, points, point_num, camera_pos):
+        """inputPointCloud(points, point_num, camera_pos), sdf_map.cpp:259-345: fuses one depth frame into the
+        device-resident log-odds volume and sets local_bound_min_/max_ for clearAndInflateLocalMap/updateESDF3d."""
+        if self._fusion is None:
+            self.setFusionParams()
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)[:point_num]
+        cam = np.ascontiguousarray(camera_pos, dtype=np.float64)
+        lo, hi = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        check(lib().fuelgpu_map_input_point_cloud(self._h, ptr(pts), int(point_num), ptr(cam), C.byref(self._fusion),
+                                                  ptr(lo), ptr(hi)), self._h)
+        if point_num > 0:
+            self.local_bound_min_, self.local_bound_max_ = lo, hi
+            self._fused = True
+
+    def getLogOdds(self):
+        """occupancy_buffer_ (fp64 log-odds) from the device."""
+        out = np.empty(self.shape, dtype=np.float64)
+        check(lib().fuelgpu_map_get_logodds(self._h, ptr(out)), self._h)
+        return out
+
+    def setLogOdds(self, logodds):
+        if self._fusion is None:
+            self.setFusionParams()
+        lo = np.ascontiguousarray(logodds, dtype=np.float64).reshape(self.shape)
+        check(lib().fuelgpu_map_set_logodds(self._h, ptr(lo), self._fusion.p_min, self._fusion.p_occ), self._h)
+        self._fused = True
 
     # ---- occupancy (host mirrors; offline recipe of plan_manage/test/compare_topo.cpp:122-133) --
     def resetBuffer(self):

@@ -207,3 +207,43 @@ def pack_x(ctrl, dt, mintime=True):
     if mintime:
         x = np.concatenate([x, dt[:, None]], axis=1)
     return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def depth_frame(g, inflate, cam_pos, yaw, pitch=0.0, width=640, height=480, fx=387.229248046875, fy=387.229248046875,
+                cx=321.04638671875, cy=243.44969177246094, margin=2, skip=2, maxdist=5.0, mindist=0.2):
+    """One synthetic depth frame as MapROS::proessDepthImage (plan_env/src/map_ros.cpp:176-215) would hand it to
+    inputPointCloud: a pinhole camera (intrinsics of exploration.launch:38-41) at cam_pos looking along `yaw`
+    (camera z = forward, x = right, y = down) ray-marched against the ground-truth occupancy `inflate`, depth
+    quantised to uint16 millimetres, no-return pixels set to depth_filter_maxdist.  -> float32 [n,3] world points."""
+    cam_pos = np.asarray(cam_pos, dtype=np.float64)
+    us = np.arange(margin, width - margin, skip)
+    vs = np.arange(margin, height - margin, skip)
+    U, V = np.meshgrid(us, vs)  # row-major over v then u, like the reference's loops
+    dirs_c = np.stack([(U - cx) / fx, (V - cy) / fy, np.ones_like(U, dtype=np.float64)], axis=-1).reshape(-1, 3)
+    cyw, syw, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+    fwd = np.array([cyw * cp, syw * cp, sp])
+    right = np.array([syw, -cyw, 0.0])
+    down = np.cross(fwd, right)
+    R = np.stack([right, down, fwd], axis=1)  # camera -> world
+    dirs_w = dirs_c @ R.T
+    n = np.asarray(g.n)
+    depth = np.zeros(dirs_c.shape[0])  # 0 = no return
+    alive = np.ones(dirs_c.shape[0], dtype=bool)
+    flat = np.ascontiguousarray(inflate).reshape(-1)
+    for t in np.arange(mindist, maxdist + 0.3, 0.04):
+        idx_alive = np.nonzero(alive)[0]
+        if idx_alive.size == 0:
+            break
+        p = cam_pos + dirs_w[idx_alive] * t
+        vi = np.floor((p - np.asarray(g.origin)) / g.res).astype(np.int64)
+        inside = np.all((vi >= 0) & (vi < n), axis=1)
+        adr = (np.clip(vi[:, 0], 0, n[0] - 1) * n[1] + np.clip(vi[:, 1], 0, n[1] - 1)) * n[2] + np.clip(vi[:, 2], 0, n[2] - 1)
+        hit = inside & (flat[adr] != 0)
+        depth[idx_alive[hit]] = t
+        alive[idx_alive[hit]] = False
+    d16 = np.round(depth * 1000.0).astype(np.uint16)
+    d = d16 * (1.0 / 1000.0)
+    d = np.where((d16 == 0) | (d > maxdist), maxdist, d)
+    keep = d >= mindist
+    pts = (dirs_c * d[:, None]) @ R.T + cam_pos
+    return np.ascontiguousarray(pts[keep], dtype=np.float32)

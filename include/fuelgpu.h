@@ -109,6 +109,33 @@ FUELGPU_API int fuelgpu_map_inflate(FuelMap* map, const int32_t bmin[3], const i
 /* Resident occupancy byte -> host: inflate (int8 {0,1}) and/or tristate (uint8), full volume. */
 FUELGPU_API int fuelgpu_map_download_occupancy(FuelMap* map, int8_t* inflate, uint8_t* tristate);
 
+/* ---- occupancy fusion ------------------------------------------------ */
+/* MapParam's fusion constants as probabilities (sdf_map.cpp:36-47 logit()s them) */
+typedef struct {
+  double p_hit, p_miss, p_min, p_max, p_occ; /* sdf_map/p_hit, p_miss, p_min, p_max, p_occ */
+  double max_ray_length;                     /* sdf_map/max_ray_length */
+  double local_bound_inflate;                /* sdf_map/local_bound_inflate */
+} FuelFusionParams;
+
+/* Replaces SDFMap::inputPointCloud (plan_env/src/sdf_map.cpp:259-345; setCacheOccupancy :243-257,
+ * closetPointInMap :347-362, RayCaster plan_env/src/raycast.cpp:323-407) on a device-resident fp64
+ * log-odds volume (occupancy_buffer_, created on first use at clamp_min_log_ - unknown_flag_,
+ * sdf_map.cpp:56,64).  points = point_num float32 xyz (pcl::PointXYZ payload), host memory.  The resident
+ * tri-state byte is refreshed for every touched voxel, so fuelgpu_map_inflate / fuelgpu_esdf_update /
+ * fuelgpu_frontier_search can follow without any upload.  local_bound_min/max receive
+ * md_->local_bound_min_/max_ (:313-318). */
+FUELGPU_API int fuelgpu_map_input_point_cloud(FuelMap* map, const float* points, int32_t point_num,
+                                              const double camera_pos[3], const FuelFusionParams* params,
+                                              int32_t local_bound_min[3], int32_t local_bound_max[3]);
+/* SDFMap::getUpdatedBox (sdf_map.cpp:491-495): md_->update_min_/max_ accumulated by the fusion calls
+ * since the last reset. */
+FUELGPU_API int fuelgpu_map_get_updated_box(FuelMap* map, double bmin[3], double bmax[3], int32_t reset);
+/* Whole-volume access to the resident log-odds (tests, map save/restore).  set also re-derives the
+ * tri-state byte (getOccupancy, sdf_map.h:194-200) with clamp_min_log_ = logit(p_min),
+ * min_occupancy_log_ = logit(p_occ). */
+FUELGPU_API int fuelgpu_map_set_logodds(FuelMap* map, const double* logodds, double p_min, double p_occ);
+FUELGPU_API int fuelgpu_map_get_logodds(FuelMap* map, double* logodds);
+
 /* ---- ESDF -------------------------------------------------------------------------- */
 #define FUELGPU_ESDF_OPTIMISTIC 1 /* mp_->optimistic_  (sdf_map.cpp:156) */
 #define FUELGPU_ESDF_SIGNED 2     /* mp_->signed_dist_ (sdf_map.cpp:201) */

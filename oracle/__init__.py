@@ -43,6 +43,17 @@ class OrcFrontierParams(C.Structure):
                 ("down_sample", C.c_int32), ("min_z", C.c_double), ("cell_order", C.c_int32)]
 
 
+class OrcFusionParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in
+                ("p_hit", "p_miss", "p_min", "p_max", "p_occ", "max_ray_length", "local_bound_inflate")]
+
+
+class OrcFusionState(C.Structure):
+    _fields_ = [("count_hit", C.c_void_p), ("count_miss", C.c_void_p), ("flag_rayend", C.c_void_p),
+                ("raycast_num", C.c_int8), ("reset_updated_box", C.c_int32),
+                ("update_min", C.c_double * 3), ("update_max", C.c_double * 3)]
+
+
 class OrcOptParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in
                 ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide",
@@ -145,6 +156,52 @@ def clear_and_inflate(g, tri, inflate, bmin, bmax, inf_step, ceil_id=-1):
     bmin = np.ascontiguousarray(bmin, dtype=np.int32)
     bmax = np.ascontiguousarray(bmax, dtype=np.int32)
     lib().orc_clear_and_inflate(C.byref(g), _p(tri), _p(inflate), _p(bmin), _p(bmax), C.c_int(inf_step), C.c_int(ceil_id))
+
+
+def fusion_params(p_hit=0.65, p_miss=0.35, p_min=0.12, p_max=0.90, p_occ=0.80, max_ray_length=4.5,
+                  local_bound_inflate=0.5):
+    """defaults = exploration_manager/launch/algorithm.xml:39-50"""
+    p = OrcFusionParams()
+    p.p_hit, p.p_miss, p.p_min, p.p_max, p.p_occ = p_hit, p_miss, p_min, p_max, p_occ
+    p.max_ray_length, p.local_bound_inflate = max_ray_length, local_bound_inflate
+    return p
+
+
+class Fusion:
+    """occupancy_buffer_ + the cache arrays of MapData driven by inputPointCloud (sdf_map.cpp:259-345)."""
+
+    def __init__(self, g, params):
+        self.g, self.p = g, params
+        self.nvox = int(g.n[0]) * int(g.n[1]) * int(g.n[2])
+        clamp_min = np.log(params.p_min / (1 - params.p_min))
+        self.logodds = np.full(self.nvox, clamp_min - 0.01, dtype=np.float64)  # sdf_map.cpp:56,64
+        self.st = OrcFusionState()
+        lib().orc_fusion_state_init(C.byref(self.st), C.c_int64(self.nvox))
+
+    def __del__(self):
+        try:
+            lib().orc_fusion_state_free(C.byref(self.st))
+        except Exception:
+            pass
+
+    def input_point_cloud(self, points, camera_pos):
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        cam = np.ascontiguousarray(camera_pos, dtype=np.float64)
+        lo = np.zeros(3, np.int32)
+        hi = np.zeros(3, np.int32)
+        lib().orc_input_point_cloud(C.byref(self.g), C.byref(self.p), C.byref(self.st), _p(self.logodds), _p(pts),
+                                    C.c_int32(pts.shape[0]), _p(cam), _p(lo), _p(hi))
+        return lo, hi
+
+    def updated_box(self, reset=False):
+        lo, hi = np.array(self.st.update_min), np.array(self.st.update_max)
+        if reset:
+            self.st.reset_updated_box = 1
+        return lo, hi
+
+    def tristate(self):
+        p = self.p
+        return tristate_from_logodds(self.logodds, np.log(p.p_min / (1 - p.p_min)), np.log(p.p_occ / (1 - p.p_occ)))
 
 
 def dist_with_grad(g, dist_buf, pos):

@@ -74,6 +74,25 @@ void orc_update_esdf3d(const OrcGrid* g, const int8_t* inflate, const uint8_t* t
 void orc_clear_and_inflate(const OrcGrid* g, uint8_t* tri, int8_t* inflate, const int32_t bmin[3],
                            const int32_t bmax[3], int inf_step, int ceil_id);
 
+/* ---- occupancy fusion: sdf_map.cpp:243-345 inputPointCloud; fuel_oracle_fusion.c ---- */
+typedef struct {
+  double p_hit, p_miss, p_min, p_max, p_occ; /* probabilities; logit()ed like sdf_map.cpp:36-47 */
+  double max_ray_length, local_bound_inflate;
+} OrcFusionParams;
+typedef struct {
+  int16_t *count_hit, *count_miss; /* md_->count_hit_/count_miss_ (short) */
+  int8_t* flag_rayend;             /* md_->flag_rayend_ (char, initialised -1, sdf_map.cpp:71) */
+  int8_t raycast_num;              /* md_->raycast_num_ (char counter) */
+  int32_t reset_updated_box;       /* md_->reset_updated_box_ */
+  double update_min[3], update_max[3];
+} OrcFusionState;
+void orc_fusion_state_init(OrcFusionState* st, int64_t nvox);
+void orc_fusion_state_free(OrcFusionState* st);
+/* logodds = occupancy_buffer_ (in/out); points = float32 xyz; local_bound_min/max = md_->local_bound_min_/max_ out */
+void orc_input_point_cloud(const OrcGrid* g, const OrcFusionParams* fp, OrcFusionState* st, double* logodds,
+                           const float* points, int32_t point_num, const double camera_pos[3],
+                           int32_t local_bound_min[3], int32_t local_bound_max[3]);
+
 /* sdf_map.cpp:497-536 getDistWithGrad (via EDTEnvironment::evaluateEDTWithGrad,
  * edt_environment.cpp:78-87).  dist_buf = distance_buffer_. */
 double orc_dist_with_grad(const OrcGrid* g, const double* dist_buf, const double pos[3],

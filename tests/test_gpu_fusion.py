@@ -1,0 +1,94 @@
+"""Occupancy-fusion parity: fuelgpu_map_input_point_cloud (C ABI) vs the CPU oracle of
+SDFMap::inputPointCloud (plan_env/src/sdf_map.cpp:259-345).  Log-odds are fp64 sums of the same constants
+in both, so the bar is bit-exact: log-odds, tri-state, local bounds and the updated box."""
+import numpy as np
+import pytest
+
+from fuel_b200 import workloads as W
+from tests.helpers import orc_grid
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(fuel, orc, g, **kw):
+    m = fuel.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max)
+    m.setFusionParams(**kw)
+    f = orc.Fusion(orc_grid(orc, g), orc.fusion_params(**kw))
+    return m, f
+
+
+def check_frame(m, f, pts, cam):
+    lo, hi = f.input_point_cloud(pts, cam)
+    m.inputPointCloud(pts, pts.shape[0], cam)
+    got = m.getLogOdds().reshape(-1)
+    assert np.array_equal(got, f.logodds), "log-odds differ in %d voxels" % int((got != f.logodds).sum())
+    if pts.shape[0]:
+        assert np.array_equal(m.local_bound_min_, lo) and np.array_equal(m.local_bound_max_, hi)
+    tri = np.empty(m.shape, np.uint8)
+    inf = np.empty(m.shape, np.int8)
+    from fuel_b200._lib import check, lib, ptr
+    check(lib().fuelgpu_map_download_occupancy(m._h, ptr(inf), ptr(tri)), m._h)
+    assert np.array_equal(tri.reshape(-1), f.tristate())
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_clouds(fuel, orc, seed):
+    """Random clouds around a random camera: in-map hits, over-range points, points outside the map,
+    points under z = 0.2, duplicates in one voxel, exact-integer coordinates."""
+    rng = np.random.default_rng(seed)
+    g = W.Grid((70, 60, 30), (-3.5, -3.0, -0.5), 0.1)
+    m, f = pair(fuel, orc, g, max_ray_length=2.5)
+    for frame in range(4):
+        cam = np.array([rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(0.5, 2.0)])
+        pts = cam + rng.normal(size=(3000, 3)) * np.array([2.0, 2.0, 0.8])
+        pts[:50] = np.round(pts[:50])                      # coordinates on voxel faces
+        pts[50:100] = pts[50]                              # many points in one voxel
+        pts[100:130] *= 8.0                                # far outside the map
+        check_frame(m, f, pts.astype(np.float32), cam)
+    lo, hi = f.updated_box(reset=True)
+    glo, ghi = m.getUpdatedBox(reset=True)
+    assert np.array_equal(lo, glo) and np.array_equal(hi, ghi)
+    cam = np.array([0.3, 0.1, 1.0])
+    pts = (cam + rng.normal(size=(200, 3))).astype(np.float32)
+    check_frame(m, f, pts, cam)
+    assert np.array_equal(np.concatenate(f.updated_box()), np.concatenate(m.getUpdatedBox()))
+    m.close()
+
+
+def test_empty_cloud(fuel, orc):
+    g = W.Grid((20, 20, 20), (-1.0, -1.0, -0.5), 0.1)
+    m, f = pair(fuel, orc, g)
+    m.inputPointCloud(np.zeros((0, 3), np.float32), 0, np.array([0.0, 0.0, 0.5]))
+    check_frame(m, f, np.array([[0.5, 0.2, 0.7]], np.float32), np.array([0.0, 0.0, 0.5]))
+    m.close()
+
+
+def test_office_depth_frames_then_inflate_and_esdf(fuel, orc):
+    """The MapROS::depthPoseCallback chain (map_ros.cpp:121-154 + updateESDFCallback :105-119) on the office map:
+    inputPointCloud -> clearAndInflateLocalMap -> updateESDF3d, every stage on the device, against the oracle chain."""
+    g, inflate_truth = W.office_map()
+    og = orc_grid(orc, g)
+    m, f = pair(fuel, orc, g)
+    tri_o = None
+    inf_o = np.zeros(g.n, np.int8)
+    poses = [((0.0, 0.0, 1.0), 0.0), ((0.3, 0.1, 1.0), 0.8), ((0.8, 0.4, 1.1), 1.7), ((1.0, 1.0, 1.2), 3.0)]
+    for cam, yaw in poses:
+        cam = np.array(cam)
+        pts = W.depth_frame(g, inflate_truth, cam, yaw)
+        check_frame(m, f, pts, cam)
+        lo, hi = m.local_bound_min_.copy(), m.local_bound_max_.copy()
+        # oracle chain
+        tri_o = f.tristate().reshape(g.n).copy()
+        orc.clear_and_inflate(og, tri_o, inf_o, lo, hi, 2, -1)
+        ref = orc.update_esdf3d(og, inf_o, tri_o, lo, hi, False, False)
+        # device chain
+        m.clearAndInflateLocalMap(obstacles_inflation=0.199)
+        assert np.array_equal(m.occupancy_buffer_inflate_, inf_o)
+        m.updateESDF3d()
+        got = m.download(lo, hi).copy()
+        sl = tuple(slice(lo[i], hi[i] + 1) for i in range(3))
+        r, q = ref[sl], got[sl]
+        fin = r < 1e150
+        assert np.array_equal(np.isinf(q), ~fin)
+        assert np.all(np.abs(q[fin] - r[fin]) <= 1e-4 * np.abs(r[fin]))
+    m.close()
