@@ -72,7 +72,7 @@ SIGNATURES = {
     "fuelgpu_map_upload_occupancy": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp]),
     "fuelgpu_map_inflate": (C.c_int, [_vp, _vp, _vp, _i32, _i32]),
     "fuelgpu_map_download_occupancy": (C.c_int, [_vp, _vp, _vp]),
-    "fuelgpu_map_input_point_cloud": (C.c_int, [_vp, _vp, _i32, _vp, C.POINTER(FuelFusionParams), _vp, _vp]),
+    "fuelgpu_map_input_point_cloud": (C.c_int, [_vp, _vp, _i32, _i32, _vp, C.POINTER(FuelFusionParams), _vp, _vp]),
     "fuelgpu_map_get_updated_box": (C.c_int, [_vp, _vp, _vp, _i32]),
     "fuelgpu_map_set_logodds": (C.c_int, [_vp, _vp, _dbl, _dbl]),
     "fuelgpu_map_get_logodds": (C.c_int, [_vp, _vp]),

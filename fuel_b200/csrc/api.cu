@@ -325,17 +325,19 @@ int fuelgpu_map_inflate(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3]
   return map_inflate_impl(m, lo, hi, inf_step, virtual_ceil_idx);
 }
 
-int fuelgpu_map_input_point_cloud(FuelMap* m, const float* points, int32_t point_num, const double camera_pos[3],
+int fuelgpu_map_input_point_cloud(FuelMap* m, const float* points, int32_t point_num, int32_t point_stride,
+                                  const double camera_pos[3],
                                   const FuelFusionParams* p, int32_t local_bound_min[3], int32_t local_bound_max[3]) {
   if (!m || !camera_pos || !p || !local_bound_min || !local_bound_max || (point_num > 0 && !points))
     return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   if (point_num < 0) return fuel_fail(m, FUELGPU_EINVAL, "negative point count");
+  if (point_stride != 3 && point_stride != 4) return fuel_fail(m, FUELGPU_EINVAL, "point_stride must be 3 (packed xyz) or 4 (pcl::PointXYZ)");
   const double pr[5] = { p->p_hit, p->p_miss, p->p_min, p->p_max, p->p_occ };
   for (double v : pr)
     if (!(v > 0.0 && v < 1.0)) return fuel_fail(m, FUELGPU_EINVAL, "fusion probabilities must lie in (0,1)");
   if (!(p->max_ray_length > 0.0)) return fuel_fail(m, FUELGPU_EINVAL, "max_ray_length must be positive");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
-  return fusion_input_impl(m, points, point_num, camera_pos, p, local_bound_min, local_bound_max);
+  return fusion_input_impl(m, points, point_stride, point_num, camera_pos, p, local_bound_min, local_bound_max);
 }
 
 int fuelgpu_map_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int32_t reset) {

@@ -97,7 +97,7 @@ int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl,
 int edt_z_chunks_dev_impl(cudaStream_t s, const int32_t* g2c, int G, int nxl, int ny, int nzl,
                           double res, float* out, int32_t* scratch);
 
-int fusion_input_impl(FuelMap* m, const float* pts_host, int n, const double cam[3], const FuelFusionParams* p,
+int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, const double cam[3], const FuelFusionParams* p,
                       int32_t lbmin[3], int32_t lbmax[3]);
 int fusion_set_logodds(FuelMap* m, const double* logodds_host, double p_min, double p_occ);
 int fusion_get_logodds(FuelMap* m, double* out);

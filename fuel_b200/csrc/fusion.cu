@@ -51,14 +51,15 @@ __device__ __forceinline__ void mark_or(uint8_t* mark, int64_t adr, unsigned bit
   if ((*(volatile unsigned*)w & v) != v) atomicOr(w, v);
 }
 
-__global__ void classify_points_kernel(Geom g, FusionConsts fc, const float* __restrict__ pts, int n,
+__global__ void classify_points_kernel(Geom g, FusionConsts fc, const float* __restrict__ pts, int stride, int n,
                                        double cx, double cy, double cz, double* __restrict__ ptw,
                                        int* __restrict__ end_adr, uint8_t* __restrict__ mark,
                                        int* __restrict__ rayend, unsigned long long* __restrict__ bounds) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double cam[3] = { cx, cy, cz };
-  double p[3] = { (double)pts[3 * i], (double)pts[3 * i + 1], (double)pts[3 * i + 2] };
+  const float* q = pts + (int64_t)stride * i;
+  double p[3] = { (double)q[0], (double)q[1], (double)q[2] };
   int flag;
   end_adr[i] = -1;
   if (!in_map_pos(g, p)) {
@@ -286,7 +287,7 @@ void fusion_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int rese
   if (f && reset) f->reset_updated_box = true;  // getUpdatedBox(reset), sdf_map.cpp:491-495
 }
 
-int fusion_input_impl(FuelMap* m, const float* pts_host, int n, const double cam[3], const FuelFusionParams* p,
+int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, const double cam[3], const FuelFusionParams* p,
                       int32_t lbmin[3], int32_t lbmax[3]) {
   int rc = fusion_state_ensure(m, p->p_min);
   if (rc) return rc;
@@ -303,7 +304,7 @@ int fusion_input_impl(FuelMap* m, const float* pts_host, int n, const double cam
     f->d_end = nullptr;
     f->cap = 0;
     const int cap = n + n / 4 + 1024;
-    FUEL_CUDA(m, cudaMalloc(&f->d_pts, sizeof(float) * 3 * cap));
+    FUEL_CUDA(m, cudaMalloc(&f->d_pts, sizeof(float) * 4 * cap));
     FUEL_CUDA(m, cudaMalloc(&f->d_ptw, sizeof(double) * 3 * cap));
     FUEL_CUDA(m, cudaMalloc(&f->d_end, sizeof(int) * cap));
     f->cap = cap;
@@ -319,12 +320,29 @@ int fusion_input_impl(FuelMap* m, const float* pts_host, int n, const double cam
   unsigned long long hb[6];
   for (int k = 0; k < 3; ++k) hb[k] = hb[3 + k] = d2o(cam[k]);
   FUEL_CUDA(m, cudaMemcpyAsync(f->d_bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(f->d_pts, pts_host, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(f->d_pts, pts_host, sizeof(float) * ((size_t)stride * (n - 1) + 3), cudaMemcpyHostToDevice, s));
   const unsigned nb = (unsigned)((n + 127) / 128);
-  classify_points_kernel<<<nb, 128, 0, s>>>(g, fc, f->d_pts, n, cam[0], cam[1], cam[2], f->d_ptw, f->d_end, f->mark,
+  classify_points_kernel<<<nb, 128, 0, s>>>(g, fc, f->d_pts, stride, n, cam[0], cam[1], cam[2], f->d_ptw, f->d_end, f->mark,
                                             f->rayend, f->d_bounds);
   raycast_kernel<<<nb, 128, 0, s>>>(g, f->d_ptw, f->d_end, f->rayend, n, cam[0], cam[1], cam[2], f->mark);
   FUEL_LAUNCHES(m, 2);
+  // Every voxel touched this frame lies within max_ray_length of the camera (clipped points, :277-297) and
+  // inside the map, so the dense sweep needs no device round trip for its extent.
+  const int nmax[3] = { g.nx, g.ny, g.nz };
+  int blo[3], bhi[3];
+  for (int k = 0; k < 3; ++k) {
+    const int tlo = (int)floor((cam[k] - p->max_ray_length - g.origin[k]) * g.res_inv) - 1;
+    const int thi = (int)floor((cam[k] + p->max_ray_length - g.origin[k]) * g.res_inv) + 1;
+    blo[k] = tlo > 0 ? tlo : 0;
+    bhi[k] = thi < nmax[k] - 1 ? thi : nmax[k] - 1;
+  }
+  const int n0 = bhi[0] - blo[0] + 1, n1 = bhi[1] - blo[1] + 1, n2 = bhi[2] - blo[2] + 1;
+  if (n0 > 0 && n1 > 0 && n2 > 0) {
+    const int64_t nv = (int64_t)n0 * n1 * n2;
+    apply_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(g, fc, blo[0], blo[1], blo[2], n0, n1, n2, f->mark, f->rayend,
+                                                             f->logodds, m->occ);
+    FUEL_LAUNCHES(m, 1);
+  }
   FUEL_CUDA(m, cudaMemcpyAsync(hb, f->d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
   double umin[3], umax[3];
@@ -337,8 +355,6 @@ int fusion_input_impl(FuelMap* m, const float* pts_host, int n, const double cam
     f->reset_updated_box = false;
   }
   // local bound (:313-318) and accumulated updated box (:321-324)
-  const int nmax[3] = { g.nx, g.ny, g.nz };
-  int blo[3], bhi[3];
   for (int k = 0; k < 3; ++k) {
     const double infl = k < 2 ? p->local_bound_inflate : 0.0;
     int hi = (int)floor((umax[k] + infl - g.origin[k]) * g.res_inv);
@@ -351,17 +367,6 @@ int fusion_input_impl(FuelMap* m, const float* pts_host, int n, const double cam
     lbmax[k] = hi;
     f->update_min[k] = umin[k] < f->update_min[k] ? umin[k] : f->update_min[k];
     f->update_max[k] = umax[k] > f->update_max[k] ? umax[k] : f->update_max[k];
-    // every voxel touched this frame lies between the camera and the clipped points
-    int tlo = (int)floor((umin[k] - g.origin[k]) * g.res_inv) - 1, thi = (int)floor((umax[k] - g.origin[k]) * g.res_inv) + 1;
-    blo[k] = tlo > 0 ? tlo : 0;
-    bhi[k] = thi < nmax[k] - 1 ? thi : nmax[k] - 1;
-  }
-  const int n0 = bhi[0] - blo[0] + 1, n1 = bhi[1] - blo[1] + 1, n2 = bhi[2] - blo[2] + 1;
-  if (n0 > 0 && n1 > 0 && n2 > 0) {
-    const int64_t nv = (int64_t)n0 * n1 * n2;
-    apply_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(g, fc, blo[0], blo[1], blo[2], n0, n1, n2, f->mark, f->rayend,
-                                                             f->logodds, m->occ);
-    FUEL_LAUNCHES(m, 1);
   }
   FUEL_CUDA(m, cudaGetLastError());
   return 0;

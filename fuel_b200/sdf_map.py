@@ -187,10 +187,12 @@ class SDFMap:
         device-resident log-odds volume and sets local_bound_min_/max_ for clearAndInflateLocalMap/updateESDF3d."""
         if self._fusion is None:
             self.setFusionParams()
-        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)[:point_num]
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        assert pts.ndim == 2 and pts.shape[1] in (3, 4) and pts.shape[0] >= point_num  # [n,4] = pcl::PointXYZ layout
         cam = np.ascontiguousarray(camera_pos, dtype=np.float64)
         lo, hi = np.zeros(3, np.int32), np.zeros(3, np.int32)
-        check(lib().fuelgpu_map_input_point_cloud(self._h, ptr(pts), int(point_num), ptr(cam), C.byref(self._fusion),
+        check(lib().fuelgpu_map_input_point_cloud(self._h, ptr(pts), int(point_num), int(pts.shape[1]), ptr(cam),
+                                                  C.byref(self._fusion),
                                                   ptr(lo), ptr(hi)), self._h)
         if point_num > 0:
             self.local_bound_min_, self.local_bound_max_ = lo, hi

@@ -120,12 +120,13 @@ typedef struct {
 /* Replaces SDFMap::inputPointCloud (plan_env/src/sdf_map.cpp:259-345; setCacheOccupancy :243-257,
  * closetPointInMap :347-362, RayCaster plan_env/src/raycast.cpp:323-407) on a device-resident fp64
  * log-odds volume (occupancy_buffer_, created on first use at clamp_min_log_ - unknown_flag_,
- * sdf_map.cpp:56,64).  points = point_num float32 xyz (pcl::PointXYZ payload), host memory.  The resident
+ * sdf_map.cpp:56,64).  points = point_num float32 xyz in host memory, point_stride floats apart: 4 for
+ * pcl::PointCloud<pcl::PointXYZ>::points.data() (16-byte points), 3 for packed xyz.  The resident
  * tri-state byte is refreshed for every touched voxel, so fuelgpu_map_inflate / fuelgpu_esdf_update /
  * fuelgpu_frontier_search can follow without any upload.  local_bound_min/max receive
  * md_->local_bound_min_/max_ (:313-318). */
 FUELGPU_API int fuelgpu_map_input_point_cloud(FuelMap* map, const float* points, int32_t point_num,
-                                              const double camera_pos[3], const FuelFusionParams* params,
+                                              int32_t point_stride, const double camera_pos[3], const FuelFusionParams* params,
                                               int32_t local_bound_min[3], int32_t local_bound_max[3]);
 /* SDFMap::getUpdatedBox (sdf_map.cpp:491-495): md_->update_min_/max_ accumulated by the fusion calls
  * since the last reset. */

@@ -198,15 +198,33 @@ public:
     bmax = mp_.box_maxd_;
   }
   void getUpdatedBox(Vector3d& bmin, Vector3d& bmax, bool reset = false) {
+    if (fused_) {  // the box is accumulated by the device fusion calls (sdf_map.cpp:321-324)
+      fuelgpu_check(fuelgpu_map_get_updated_box(gpu_, bmin.data(), bmax.data(), reset ? 1 : 0), gpu_);
+      return;
+    }
     bmin = update_min_;
     bmax = update_max_;
     if (reset) reset_updated_box_ = true;
   }
 
+  // inputPointCloud (sdf_map.cpp:259-345): fuses one frame into the device-resident log-odds volume and
+  // sets local_bound_min_/max_.  `points` = cloud.points.data() of a pcl::PointCloud<pcl::PointXYZ>
+  // (point_stride 4) or packed xyz (point_stride 3).  From here on the occupancy lives on the device:
+  // updateESDF3d() no longer uploads occupancy_buffer_.
+  FuelFusionParams fusion_ = { 0.65, 0.35, 0.12, 0.90, 0.80, 4.5, 0.5 };  // algorithm.xml:39-50
+  void inputPointCloud(const float* points, int point_num, const Vector3d& camera_pos, int point_stride = 4) {
+    if (point_num == 0) return;
+    fuelgpu_check(fuelgpu_map_input_point_cloud(gpu_, points, point_num, point_stride, camera_pos.data(), &fusion_,
+                                                local_bound_min_.data(), local_bound_max_.data()),
+                  gpu_);
+    fused_ = true;
+  }
+
   // updateESDF3d (sdf_map.cpp:152-241): occupancy H2D for the x-slabs of the local box, the three
   // sweeps on the device, and the fp64 host mirror the scattered getDistance() readers use.
   void updateESDF3d() {
-    fuelgpu_check(fuelgpu_map_upload_occupancy(gpu_, occupancy_buffer_inflate_.data(), occupancy_buffer_.data(), nullptr,
+    if (!fused_)
+      fuelgpu_check(fuelgpu_map_upload_occupancy(gpu_, occupancy_buffer_inflate_.data(), occupancy_buffer_.data(), nullptr,
                                                clamp_min_log_, min_occupancy_log_, local_bound_min_.data(),
                                                local_bound_max_.data()),
                   gpu_);
@@ -241,6 +259,7 @@ public:
   Vector3i local_bound_min_, local_bound_max_;
   Vector3d update_min_, update_max_;
   bool reset_updated_box_ = true;
+  bool fused_ = false;
   MapParam mp_;
 
 private:

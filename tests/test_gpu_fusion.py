@@ -55,6 +55,21 @@ def test_random_clouds(fuel, orc, seed):
     m.close()
 
 
+def test_pcl_point_stride(fuel, orc):
+    """pcl::PointXYZ is 16 bytes (xyz + padding): stride 4 must give the same map as packed xyz."""
+    rng = np.random.default_rng(9)
+    g = W.Grid((40, 40, 20), (-2.0, -2.0, -0.5), 0.1)
+    m, f = pair(fuel, orc, g)
+    cam = np.array([0.1, -0.2, 0.8])
+    pts = (cam + rng.normal(size=(500, 3))).astype(np.float32)
+    f.input_point_cloud(pts, cam)
+    p4 = np.full((500, 4), np.nan, np.float32)
+    p4[:, :3] = pts
+    m.inputPointCloud(p4, 500, cam)
+    assert np.array_equal(m.getLogOdds().reshape(-1), f.logodds)
+    m.close()
+
+
 def test_empty_cloud(fuel, orc):
     g = W.Grid((20, 20, 20), (-1.0, -1.0, -0.5), 0.1)
     m, f = pair(fuel, orc, g)
