@@ -37,6 +37,12 @@ class FuelFusionParams(C.Structure):
                 ("p_hit", "p_miss", "p_min", "p_max", "p_occ", "max_ray_length", "local_bound_inflate")]
 
 
+class FuelCameraParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("fx", "fy", "cx", "cy", "k_depth_scaling_factor", "depth_filter_maxdist",
+                                          "depth_filter_mindist")] + [("depth_filter_margin", C.c_int32),
+                                                                      ("skip_pixel", C.c_int32)]
+
+
 class FuelOptParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in
                 ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide", "ld_waypt",
@@ -73,6 +79,8 @@ SIGNATURES = {
     "fuelgpu_map_inflate": (C.c_int, [_vp, _vp, _vp, _i32, _i32]),
     "fuelgpu_map_download_occupancy": (C.c_int, [_vp, _vp, _vp]),
     "fuelgpu_map_input_point_cloud": (C.c_int, [_vp, _vp, _i32, _i32, _vp, C.POINTER(FuelFusionParams), _vp, _vp]),
+    "fuelgpu_map_input_depth_image": (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(FuelCameraParams), _vp, _vp,
+                                                C.POINTER(FuelFusionParams), _vp, _vp, C.POINTER(_i32)]),
     "fuelgpu_map_get_updated_box": (C.c_int, [_vp, _vp, _vp, _i32]),
     "fuelgpu_map_set_logodds": (C.c_int, [_vp, _vp, _dbl, _dbl]),
     "fuelgpu_map_get_logodds": (C.c_int, [_vp, _vp]),

@@ -340,6 +340,23 @@ int fuelgpu_map_input_point_cloud(FuelMap* m, const float* points, int32_t point
   return fusion_input_impl(m, points, point_stride, point_num, camera_pos, p, local_bound_min, local_bound_max);
 }
 
+int fuelgpu_map_input_depth_image(FuelMap* m, const uint16_t* depth, int32_t rows, int32_t cols, const FuelCameraParams* c,
+                                  const double camera_R[9], const double camera_pos[3], const FuelFusionParams* p,
+                                  int32_t local_bound_min[3], int32_t local_bound_max[3], int32_t* proj_points_cnt) {
+  if (!m || !depth || !c || !camera_R || !camera_pos || !p || !local_bound_min || !local_bound_max)
+    return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (rows <= 0 || cols <= 0 || rows > 8192 || cols > 8192) return fuel_fail(m, FUELGPU_EINVAL, "image size out of range");
+  if (c->skip_pixel < 1 || c->depth_filter_margin < 0 || !(c->fx != 0.0) || !(c->fy != 0.0) || !(c->k_depth_scaling_factor > 0.0))
+    return fuel_fail(m, FUELGPU_EINVAL, "bad camera parameters");
+  const double pr[5] = { p->p_hit, p->p_miss, p->p_min, p->p_max, p->p_occ };
+  for (double v : pr)
+    if (!(v > 0.0 && v < 1.0)) return fuel_fail(m, FUELGPU_EINVAL, "fusion probabilities must lie in (0,1)");
+  if (!(p->max_ray_length > 0.0)) return fuel_fail(m, FUELGPU_EINVAL, "max_ray_length must be positive");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return fusion_input_depth_impl(m, depth, rows, cols, c, camera_R, camera_pos, p, local_bound_min, local_bound_max,
+                                 proj_points_cnt);
+}
+
 int fuelgpu_map_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int32_t reset) {
   if (!m || !bmin || !bmax) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   fusion_get_updated_box(m, bmin, bmax, reset);

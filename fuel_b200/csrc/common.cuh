@@ -99,6 +99,9 @@ int edt_z_chunks_dev_impl(cudaStream_t s, const int32_t* g2c, int G, int nxl, in
 
 int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, const double cam[3], const FuelFusionParams* p,
                       int32_t lbmin[3], int32_t lbmax[3]);
+int fusion_input_depth_impl(FuelMap* m, const uint16_t* img_host, int rows, int cols, const FuelCameraParams* cp,
+                            const double R[9], const double cam[3], const FuelFusionParams* p, int32_t lbmin[3],
+                            int32_t lbmax[3], int32_t* proj_cnt);
 int fusion_set_logodds(FuelMap* m, const double* logodds_host, double p_min, double p_occ);
 int fusion_get_logodds(FuelMap* m, double* out);
 void fusion_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int reset);

@@ -51,15 +51,13 @@ __device__ __forceinline__ void mark_or(uint8_t* mark, int64_t adr, unsigned bit
   if ((*(volatile unsigned*)w & v) != v) atomicOr(w, v);
 }
 
-__global__ void classify_points_kernel(Geom g, FusionConsts fc, const float* __restrict__ pts, int stride, int n,
-                                       double cx, double cy, double cz, double* __restrict__ ptw,
-                                       int* __restrict__ end_adr, uint8_t* __restrict__ mark,
-                                       int* __restrict__ rayend, unsigned long long* __restrict__ bounds) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// One point of the cloud (index i in the reference's iteration order): sdf_map.cpp:273-306 up to the ray election.
+__device__ __forceinline__ void classify_point(const Geom& g, const FusionConsts& fc, int i, double p0, double p1, double p2,
+                                               double cx, double cy, double cz, double* __restrict__ ptw,
+                                               int* __restrict__ end_adr, uint8_t* __restrict__ mark,
+                                               int* __restrict__ rayend, unsigned long long* __restrict__ bounds) {
   const double cam[3] = { cx, cy, cz };
-  const float* q = pts + (int64_t)stride * i;
-  double p[3] = { (double)q[0], (double)q[1], (double)q[2] };
+  double p[3] = { p0, p1, p2 };
   int flag;
   end_adr[i] = -1;
   if (!in_map_pos(g, p)) {
@@ -110,6 +108,53 @@ __global__ void classify_points_kernel(Geom g, FusionConsts fc, const float* __r
   }
   end_adr[i] = (int)adr;
   atomicMin(&rayend[adr], i);  // the first point of this end voxel traces the ray (:303-306)
+}
+
+__global__ void classify_points_kernel(Geom g, FusionConsts fc, const float* __restrict__ pts, int stride, int n,
+                                       double cx, double cy, double cz, double* __restrict__ ptw,
+                                       int* __restrict__ end_adr, uint8_t* __restrict__ mark,
+                                       int* __restrict__ rayend, unsigned long long* __restrict__ bounds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* q = pts + (int64_t)stride * i;
+  classify_point(g, fc, i, (double)q[0], (double)q[1], (double)q[2], cx, cy, cz, ptw, end_adr, mark, rayend, bounds);
+}
+
+struct CamConsts {
+  double fx, fy, cx, cy, inv_factor, maxdist, mindist;
+  double R[9];
+  int margin, skip, rows, cols, nu, nv;  // nu x nv sampled pixels
+};
+
+// MapROS::proessDepthImage (plan_env/src/map_ros.cpp:176-215) fused with the per-point part of inputPointCloud.
+// Thread i = sampled pixel (v-major, then u): that order is the reference's point order with the skipped pixels
+// (depth < mindist) left out, and leaving elements out does not change who is FIRST in a voxel.
+__global__ void classify_depth_kernel(Geom g, FusionConsts fc, CamConsts cc, const uint16_t* __restrict__ img, double cx,
+                                      double cy, double cz, double* __restrict__ ptw, int* __restrict__ end_adr,
+                                      uint8_t* __restrict__ mark, int* __restrict__ rayend,
+                                      unsigned long long* __restrict__ bounds, int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cc.nu * cc.nv) return;
+  end_adr[i] = -1;
+  const int v = cc.margin + (i / cc.nu) * cc.skip, u = cc.margin + (i % cc.nu) * cc.skip;
+  const int64_t at = (int64_t)v * cc.cols + u;
+  double depth = img[at] * cc.inv_factor;
+  // the reference tests the pixel `skip` to the right of the one it just read (row_ptr advanced first, :190-198)
+  const int64_t nx = at + cc.skip;
+  const unsigned nxt = nx < (int64_t)cc.rows * cc.cols ? img[nx] : 0u;
+  if (nxt == 0 || depth > cc.maxdist)
+    depth = cc.maxdist;
+  else if (depth < cc.mindist)
+    return;
+  atomicAdd(count, 1);
+  const double pc[3] = { __dmul_rn(u - cc.cx, depth) / cc.fx, __dmul_rn(v - cc.cy, depth) / cc.fy, depth };
+  float w[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    w[k] = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(cc.R[3 * k], pc[0]), __dmul_rn(cc.R[3 * k + 1], pc[1])),
+                                      __dmul_rn(cc.R[3 * k + 2], pc[2])),
+                            k == 0 ? cx : (k == 1 ? cy : cz));
+  classify_point(g, fc, i, (double)w[0], (double)w[1], (double)w[2], cx, cy, cz, ptw, end_adr, mark, rayend, bounds);
 }
 
 __device__ __forceinline__ double intbound(double s, double ds) {  // raycast.cpp:14-23
@@ -220,6 +265,7 @@ struct FusionState {
   int* rayend = nullptr;      // per voxel: first point index ending there this frame (flag_rayend_ analogue)
   uint8_t* mark = nullptr;    // per voxel: bit0 hit, bit1 missed this frame (count_hit_/count_miss_ analogue)
   unsigned long long* d_bounds = nullptr;
+  int* d_count = nullptr;
   float* d_pts = nullptr;
   double* d_ptw = nullptr;
   int* d_end = nullptr;
@@ -238,6 +284,7 @@ int fusion_state_ensure(FuelMap* m, double p_min) {
   FUEL_CUDA(m, cudaMalloc(&f->rayend, sizeof(int) * m->nvox));
   FUEL_CUDA(m, cudaMalloc(&f->mark, (m->nvox + 3) / 4 * 4));
   FUEL_CUDA(m, cudaMalloc(&f->d_bounds, sizeof(unsigned long long) * 6));
+  FUEL_CUDA(m, cudaMalloc(&f->d_count, sizeof(int)));
   const unsigned nb = (unsigned)((m->nvox + 255) / 256);
   // initMap: occupancy_buffer_ = clamp_min_log_ - unknown_flag_ (sdf_map.cpp:56,64)
   fill_f64_kernel<<<nb, 256, 0, m->stream>>>(f->logodds, m->nvox, logit(p_min) - 0.01);
@@ -251,7 +298,7 @@ int fusion_state_ensure(FuelMap* m, double p_min) {
 void fusion_state_destroy(FuelMap* m) {
   FusionState* f = m->fus;
   if (!f) return;
-  void* ptrs[] = { f->logodds, f->rayend, f->mark, f->d_bounds, f->d_pts, f->d_ptw, f->d_end };
+  void* ptrs[] = { f->logodds, f->rayend, f->mark, f->d_bounds, f->d_count, f->d_pts, f->d_ptw, f->d_end };
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete f;
@@ -287,15 +334,23 @@ void fusion_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int rese
   if (f && reset) f->reset_updated_box = true;  // getUpdatedBox(reset), sdf_map.cpp:491-495
 }
 
-int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, const double cam[3], const FuelFusionParams* p,
-                      int32_t lbmin[3], int32_t lbmax[3]) {
+// One frame.  Source = a point cloud (pts_host, stride, n) or, when cp != nullptr, a depth image (img_host, rows x cols)
+// projected on the device; n is then the number of sampled pixels and *proj_cnt receives proj_points_cnt.
+static int fusion_frame(FuelMap* m, const float* pts_host, int stride, int n, const uint16_t* img_host,
+                        const FuelCameraParams* cp, int rows, int cols, const double* Rm, int32_t* proj_cnt,
+                        const double cam[3], const FuelFusionParams* p, int32_t lbmin[3], int32_t lbmax[3]) {
   int rc = fusion_state_ensure(m, p->p_min);
   if (rc) return rc;
   FusionState* f = m->fus;
   const Geom& g = m->g;
   cudaStream_t s = m->stream;
   if (n == 0) return 0;  // :262
-  if (n > f->cap) {
+  int need = n;
+  if (cp) {  // the image is staged in d_pts: 16 bytes per slot hold 8 pixels
+    const int64_t px = ((int64_t)rows * cols + 7) / 8;
+    need = px > n ? (int)px : n;
+  }
+  if (need > f->cap) {
     if (f->d_pts) cudaFree(f->d_pts);
     if (f->d_ptw) cudaFree(f->d_ptw);
     if (f->d_end) cudaFree(f->d_end);
@@ -303,8 +358,8 @@ int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, cons
     f->d_ptw = nullptr;
     f->d_end = nullptr;
     f->cap = 0;
-    const int cap = n + n / 4 + 1024;
-    FUEL_CUDA(m, cudaMalloc(&f->d_pts, sizeof(float) * 4 * cap));
+    const int cap = need + need / 4 + 1024;
+    FUEL_CUDA(m, cudaMalloc(&f->d_pts, sizeof(float) * 4 * cap));  // also holds a uint16 image of <= 8*cap pixels
     FUEL_CUDA(m, cudaMalloc(&f->d_ptw, sizeof(double) * 3 * cap));
     FUEL_CUDA(m, cudaMalloc(&f->d_end, sizeof(int) * cap));
     f->cap = cap;
@@ -320,10 +375,25 @@ int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, cons
   unsigned long long hb[6];
   for (int k = 0; k < 3; ++k) hb[k] = hb[3 + k] = d2o(cam[k]);
   FUEL_CUDA(m, cudaMemcpyAsync(f->d_bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, s));
-  FUEL_CUDA(m, cudaMemcpyAsync(f->d_pts, pts_host, sizeof(float) * ((size_t)stride * (n - 1) + 3), cudaMemcpyHostToDevice, s));
   const unsigned nb = (unsigned)((n + 127) / 128);
-  classify_points_kernel<<<nb, 128, 0, s>>>(g, fc, f->d_pts, stride, n, cam[0], cam[1], cam[2], f->d_ptw, f->d_end, f->mark,
-                                            f->rayend, f->d_bounds);
+  if (!cp) {
+    FUEL_CUDA(m, cudaMemcpyAsync(f->d_pts, pts_host, sizeof(float) * ((size_t)stride * (n - 1) + 3), cudaMemcpyHostToDevice, s));
+    classify_points_kernel<<<nb, 128, 0, s>>>(g, fc, f->d_pts, stride, n, cam[0], cam[1], cam[2], f->d_ptw, f->d_end, f->mark,
+                                              f->rayend, f->d_bounds);
+  } else {
+    CamConsts cc;
+    cc.fx = cp->fx, cc.fy = cp->fy, cc.cx = cp->cx, cc.cy = cp->cy;
+    cc.inv_factor = 1.0 / cp->k_depth_scaling_factor;  // :185
+    cc.maxdist = cp->depth_filter_maxdist, cc.mindist = cp->depth_filter_mindist;
+    for (int k = 0; k < 9; ++k) cc.R[k] = Rm[k];
+    cc.margin = cp->depth_filter_margin, cc.skip = cp->skip_pixel, cc.rows = rows, cc.cols = cols;
+    cc.nu = (cols - 2 * cc.margin + cc.skip - 1) / cc.skip;
+    cc.nv = (rows - 2 * cc.margin + cc.skip - 1) / cc.skip;
+    FUEL_CUDA(m, cudaMemsetAsync(f->d_count, 0, sizeof(int), s));
+    FUEL_CUDA(m, cudaMemcpyAsync(f->d_pts, img_host, sizeof(uint16_t) * (size_t)rows * cols, cudaMemcpyHostToDevice, s));
+    classify_depth_kernel<<<nb, 128, 0, s>>>(g, fc, cc, (const uint16_t*)f->d_pts, cam[0], cam[1], cam[2], f->d_ptw, f->d_end,
+                                             f->mark, f->rayend, f->d_bounds, f->d_count);
+  }
   raycast_kernel<<<nb, 128, 0, s>>>(g, f->d_ptw, f->d_end, f->rayend, n, cam[0], cam[1], cam[2], f->mark);
   FUEL_LAUNCHES(m, 2);
   // Every voxel touched this frame lies within max_ray_length of the camera (clipped points, :277-297) and
@@ -344,7 +414,11 @@ int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, cons
     FUEL_LAUNCHES(m, 1);
   }
   FUEL_CUDA(m, cudaMemcpyAsync(hb, f->d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, s));
+  int cnt = n;
+  if (cp) FUEL_CUDA(m, cudaMemcpyAsync(&cnt, f->d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
+  if (proj_cnt) *proj_cnt = cnt;
+  if (cnt == 0) return 0;  // inputPointCloud returns before touching any box when point_num == 0 (:262)
   double umin[3], umax[3];
   for (int k = 0; k < 3; ++k) {
     umin[k] = o2d(hb[k]);
@@ -370,4 +444,19 @@ int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, cons
   }
   FUEL_CUDA(m, cudaGetLastError());
   return 0;
+}
+
+int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, const double cam[3], const FuelFusionParams* p,
+                      int32_t lbmin[3], int32_t lbmax[3]) {
+  return fusion_frame(m, pts_host, stride, n, nullptr, nullptr, 0, 0, nullptr, nullptr, cam, p, lbmin, lbmax);
+}
+
+int fusion_input_depth_impl(FuelMap* m, const uint16_t* img_host, int rows, int cols, const FuelCameraParams* cp,
+                            const double R[9], const double cam[3], const FuelFusionParams* p, int32_t lbmin[3],
+                            int32_t lbmax[3], int32_t* proj_cnt) {
+  const int nu = (cols - 2 * cp->depth_filter_margin + cp->skip_pixel - 1) / cp->skip_pixel;
+  const int nv = (rows - 2 * cp->depth_filter_margin + cp->skip_pixel - 1) / cp->skip_pixel;
+  if (proj_cnt) *proj_cnt = 0;
+  if (nu <= 0 || nv <= 0) return 0;
+  return fusion_frame(m, nullptr, 0, nu * nv, img_host, cp, rows, cols, R, proj_cnt, cam, p, lbmin, lbmax);
 }

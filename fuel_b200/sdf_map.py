@@ -55,6 +55,7 @@ class SDFMap:
         self.update_max_ = np.zeros(3)
         self.reset_updated_box_ = True
         self._fusion = None
+        self._camera = None
         self._fused = False
 
         d = FuelGridDesc()
@@ -197,6 +198,36 @@ class SDFMap:
         if point_num > 0:
             self.local_bound_min_, self.local_bound_max_ = lo, hi
             self._fused = True
+
+    def setCameraParams(self, fx=387.229248046875, fy=387.229248046875, cx=321.04638671875, cy=243.44969177246094,
+                        k_depth_scaling_factor=1000.0, depth_filter_maxdist=5.0, depth_filter_mindist=0.2,
+                        depth_filter_margin=2, skip_pixel=2):
+        """map_ros/* parameters (map_ros.cpp:24-37); defaults exploration.launch:38-41, algorithm.xml:61-69."""
+        c = _lib.FuelCameraParams()
+        c.fx, c.fy, c.cx, c.cy = fx, fy, cx, cy
+        c.k_depth_scaling_factor, c.depth_filter_maxdist, c.depth_filter_mindist = (
+            k_depth_scaling_factor, depth_filter_maxdist, depth_filter_mindist)
+        c.depth_filter_margin, c.skip_pixel = depth_filter_margin, skip_pixel
+        self._camera = c
+
+    def inputDepthImage(self, depth, camera_R, camera_pos):
+        """MapROS::depthPoseCallback's proessDepthImage + inputPointCloud (map_ros.cpp:139-140,176-215) in one device
+        call.  depth = uint16 [rows, cols]; camera_R = camera_q_.toRotationMatrix().  -> proj_points_cnt"""
+        if self._fusion is None:
+            self.setFusionParams()
+        if self._camera is None:
+            self.setCameraParams()
+        img = np.ascontiguousarray(depth, dtype=np.uint16)
+        R = np.ascontiguousarray(camera_R, dtype=np.float64).reshape(9)
+        cam = np.ascontiguousarray(camera_pos, dtype=np.float64)
+        lo, hi = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        cnt = C.c_int32(0)
+        check(lib().fuelgpu_map_input_depth_image(self._h, ptr(img), img.shape[0], img.shape[1], C.byref(self._camera), ptr(R),
+                                                  ptr(cam), C.byref(self._fusion), ptr(lo), ptr(hi), C.byref(cnt)), self._h)
+        if cnt.value > 0:
+            self.local_bound_min_, self.local_bound_max_ = lo, hi
+            self._fused = True
+        return cnt.value
 
     def getLogOdds(self):
         """occupancy_buffer_ (fp64 log-odds) from the device."""

@@ -209,22 +209,28 @@ def pack_x(ctrl, dt, mintime=True):
     return np.ascontiguousarray(x, dtype=np.float64)
 
 
-def depth_frame(g, inflate, cam_pos, yaw, pitch=0.0, width=640, height=480, fx=387.229248046875, fy=387.229248046875,
-                cx=321.04638671875, cy=243.44969177246094, margin=2, skip=2, maxdist=5.0, mindist=0.2):
-    """One synthetic depth frame as MapROS::proessDepthImage (plan_env/src/map_ros.cpp:176-215) would hand it to
-    inputPointCloud: a pinhole camera (intrinsics of exploration.launch:38-41) at cam_pos looking along `yaw`
-    (camera z = forward, x = right, y = down) ray-marched against the ground-truth occupancy `inflate`, depth
-    quantised to uint16 millimetres, no-return pixels set to depth_filter_maxdist.  -> float32 [n,3] world points."""
-    cam_pos = np.asarray(cam_pos, dtype=np.float64)
-    us = np.arange(margin, width - margin, skip)
-    vs = np.arange(margin, height - margin, skip)
-    U, V = np.meshgrid(us, vs)  # row-major over v then u, like the reference's loops
-    dirs_c = np.stack([(U - cx) / fx, (V - cy) / fy, np.ones_like(U, dtype=np.float64)], axis=-1).reshape(-1, 3)
+def _camera_rotation(yaw, pitch=0.0):
+    """camera -> world rotation: camera z = forward, x = right, y = down"""
     cyw, syw, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
     fwd = np.array([cyw * cp, syw * cp, sp])
     right = np.array([syw, -cyw, 0.0])
     down = np.cross(fwd, right)
-    R = np.stack([right, down, fwd], axis=1)  # camera -> world
+    return np.stack([right, down, fwd], axis=1)
+
+
+def depth_image(g, inflate, cam_pos, yaw, pitch=0.0, width=640, height=480, fx=387.229248046875, fy=387.229248046875,
+                cx=321.04638671875, cy=243.44969177246094, margin=2, skip=2, maxdist=5.0, mindist=0.2):
+    """Synthetic sensor frame: a pinhole depth camera (intrinsics of exploration.launch:38-41) at cam_pos looking
+    along `yaw`, ray-marched against the ground-truth occupancy `inflate`; uint16 millimetres, 0 = no return.  Rays
+    are marched for the pixels MapROS samples (margin + k*skip) and replicated to their neighbours.
+    -> (image uint16 [height,width], R [3,3] camera->world)"""
+    cam_pos = np.asarray(cam_pos, dtype=np.float64)
+    off = margin % skip
+    us = np.arange(off, width, skip)
+    vs = np.arange(off, height, skip)
+    U, V = np.meshgrid(us, vs)
+    dirs_c = np.stack([(U - cx) / fx, (V - cy) / fy, np.ones_like(U, dtype=np.float64)], axis=-1).reshape(-1, 3)
+    R = _camera_rotation(yaw, pitch)
     dirs_w = dirs_c @ R.T
     n = np.asarray(g.n)
     depth = np.zeros(dirs_c.shape[0])  # 0 = no return
@@ -241,9 +247,30 @@ def depth_frame(g, inflate, cam_pos, yaw, pitch=0.0, width=640, height=480, fx=3
         hit = inside & (flat[adr] != 0)
         depth[idx_alive[hit]] = t
         alive[idx_alive[hit]] = False
-    d16 = np.round(depth * 1000.0).astype(np.uint16)
+    low = np.round(depth * 1000.0).astype(np.uint16).reshape(len(vs), len(us))
+    vi = np.clip((np.arange(height) - off) // skip, 0, len(vs) - 1)
+    ui = np.clip((np.arange(width) - off) // skip, 0, len(us) - 1)
+    return np.ascontiguousarray(low[vi][:, ui]), R
+
+
+def depth_frame(g, inflate, cam_pos, yaw, pitch=0.0, width=640, height=480, fx=387.229248046875, fy=387.229248046875,
+                cx=321.04638671875, cy=243.44969177246094, margin=2, skip=2, maxdist=5.0, mindist=0.2):
+    """depth_image() projected to world points the way MapROS::proessDepthImage (plan_env/src/map_ros.cpp:176-215) hands
+    them to inputPointCloud (no-return pixels at depth_filter_maxdist).  Input generation only (numpy); the parity-checked
+    projection is fuelgpu_map_input_depth_image vs the oracle.  -> float32 [n,3] world points."""
+    img, R = depth_image(g, inflate, cam_pos, yaw, pitch, width, height, fx, fy, cx, cy, margin, skip, maxdist, mindist)
+    us = np.arange(margin, width - margin, skip)
+    vs = np.arange(margin, height - margin, skip)
+    U, V = np.meshgrid(us, vs)
+    d16 = img[V, U].reshape(-1)
     d = d16 * (1.0 / 1000.0)
-    d = np.where((d16 == 0) | (d > maxdist), maxdist, d)
-    keep = d >= mindist
-    pts = (dirs_c * d[:, None]) @ R.T + cam_pos
+    # the reference's "no return" test looks at the pixel `skip` further along the row buffer (map_ros.cpp:190-198)
+    flat = img.reshape(-1)
+    nxt_at = (V * width + U + skip).reshape(-1)
+    nxt = np.where(nxt_at < flat.size, flat[np.minimum(nxt_at, flat.size - 1)], 0)
+    far = (nxt == 0) | (d > maxdist)
+    keep = far | (d >= mindist)
+    d = np.where(far, maxdist, d)
+    dirs_c = np.stack([(U - cx) / fx, (V - cy) / fy, np.ones_like(U, dtype=np.float64)], axis=-1).reshape(-1, 3)
+    pts = (dirs_c * d[:, None]) @ R.T + np.asarray(cam_pos, dtype=np.float64)
     return np.ascontiguousarray(pts[keep], dtype=np.float32)

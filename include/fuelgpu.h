@@ -128,6 +128,22 @@ typedef struct {
 FUELGPU_API int fuelgpu_map_input_point_cloud(FuelMap* map, const float* points, int32_t point_num,
                                               int32_t point_stride, const double camera_pos[3], const FuelFusionParams* params,
                                               int32_t local_bound_min[3], int32_t local_bound_max[3]);
+/* MapROS's camera parameters (plan_env/src/map_ros.cpp:24-37; values exploration.launch:38-41, algorithm.xml:61-69) */
+typedef struct {
+  double fx, fy, cx, cy;
+  double k_depth_scaling_factor, depth_filter_maxdist, depth_filter_mindist;
+  int32_t depth_filter_margin, skip_pixel;
+} FuelCameraParams;
+
+/* Replaces MapROS::proessDepthImage + the inputPointCloud call of depthPoseCallback
+ * (plan_env/src/map_ros.cpp:139-140, 176-215): the uint16 depth image (rows x cols, row-major, host memory) is
+ * projected on the device (camera_R = row-major camera_q_.toRotationMatrix()) and fused as above; the world points
+ * never exist on the host.  proj_points_cnt (may be NULL) receives the number of projected points. */
+FUELGPU_API int fuelgpu_map_input_depth_image(FuelMap* map, const uint16_t* depth, int32_t rows, int32_t cols,
+                                              const FuelCameraParams* camera, const double camera_R[9],
+                                              const double camera_pos[3], const FuelFusionParams* params,
+                                              int32_t local_bound_min[3], int32_t local_bound_max[3],
+                                              int32_t* proj_points_cnt);
 /* SDFMap::getUpdatedBox (sdf_map.cpp:491-495): md_->update_min_/max_ accumulated by the fusion calls
  * since the last reset. */
 FUELGPU_API int fuelgpu_map_get_updated_box(FuelMap* map, double bmin[3], double bmax[3], int32_t reset);

@@ -219,6 +219,17 @@ public:
                   gpu_);
     fused_ = true;
   }
+  // MapROS::proessDepthImage + inputPointCloud (map_ros.cpp:139-140,176-215) as one device call; camera_R is
+  // camera_q_.toRotationMatrix() in row-major order.  Returns proj_points_cnt.
+  FuelCameraParams camera_ = { 387.229248046875, 387.229248046875, 321.04638671875, 243.44969177246094, 1000.0, 5.0, 0.2, 2, 2 };
+  int inputDepthImage(const uint16_t* depth, int rows, int cols, const double camera_R[9], const Vector3d& camera_pos) {
+    int32_t cnt = 0;
+    fuelgpu_check(fuelgpu_map_input_depth_image(gpu_, depth, rows, cols, &camera_, camera_R, camera_pos.data(), &fusion_,
+                                                local_bound_min_.data(), local_bound_max_.data(), &cnt),
+                  gpu_);
+    if (cnt > 0) fused_ = true;
+    return cnt;
+  }
 
   // updateESDF3d (sdf_map.cpp:152-241): occupancy H2D for the x-slabs of the local box, the three
   // sweeps on the device, and the fp64 host mirror the scattered getDistance() readers use.

@@ -54,6 +54,12 @@ class OrcFusionState(C.Structure):
                 ("update_min", C.c_double * 3), ("update_max", C.c_double * 3)]
 
 
+class OrcCameraParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("fx", "fy", "cx", "cy", "k_depth_scaling_factor", "depth_filter_maxdist",
+                                          "depth_filter_mindist")] + [("depth_filter_margin", C.c_int32),
+                                                                      ("skip_pixel", C.c_int32)]
+
+
 class OrcOptParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in
                 ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide",
@@ -165,6 +171,30 @@ def fusion_params(p_hit=0.65, p_miss=0.35, p_min=0.12, p_max=0.90, p_occ=0.80, m
     p.p_hit, p.p_miss, p.p_min, p.p_max, p.p_occ = p_hit, p_miss, p_min, p_max, p_occ
     p.max_ray_length, p.local_bound_inflate = max_ray_length, local_bound_inflate
     return p
+
+
+def camera_params(fx=387.229248046875, fy=387.229248046875, cx=321.04638671875, cy=243.44969177246094,
+                  k_depth_scaling_factor=1000.0, depth_filter_maxdist=5.0, depth_filter_mindist=0.2,
+                  depth_filter_margin=2, skip_pixel=2):
+    """defaults = exploration.launch:38-41, algorithm.xml:61-69"""
+    c = OrcCameraParams()
+    c.fx, c.fy, c.cx, c.cy = fx, fy, cx, cy
+    c.k_depth_scaling_factor, c.depth_filter_maxdist, c.depth_filter_mindist = (
+        k_depth_scaling_factor, depth_filter_maxdist, depth_filter_mindist)
+    c.depth_filter_margin, c.skip_pixel = depth_filter_margin, skip_pixel
+    return c
+
+
+def process_depth_image(cp, depth, R, camera_pos):
+    """proessDepthImage (map_ros.cpp:176-215) -> float32 [proj_points_cnt, 3]"""
+    depth = np.ascontiguousarray(depth, dtype=np.uint16)
+    rows, cols = depth.shape
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+    cam = np.ascontiguousarray(camera_pos, dtype=np.float64)
+    out = np.empty((rows * cols, 3), dtype=np.float32)
+    lib().orc_process_depth_image.restype = C.c_int32
+    n = lib().orc_process_depth_image(C.byref(cp), _p(depth), C.c_int32(rows), C.c_int32(cols), _p(R), _p(cam), _p(out))
+    return out[:n].copy()
 
 
 class Fusion:

@@ -93,6 +93,18 @@ void orc_input_point_cloud(const OrcGrid* g, const OrcFusionParams* fp, OrcFusio
                            const float* points, int32_t point_num, const double camera_pos[3],
                            int32_t local_bound_min[3], int32_t local_bound_max[3]);
 
+/* MapROS::proessDepthImage, plan_env/src/map_ros.cpp:176-215: depth image (uint16, rows x cols, row-major) ->
+ * world points (float32 xyz, as stored in pcl::PointXYZ), in the order the reference emits them.  R = row-major
+ * camera_q_.toRotationMatrix().  Returns proj_points_cnt.  The zero test reads the pixel skip_pixel to the right of
+ * the one whose depth is used (row_ptr is advanced first, :190-198) -- reproduced. */
+typedef struct {
+  double fx, fy, cx, cy;
+  double k_depth_scaling_factor, depth_filter_maxdist, depth_filter_mindist;
+  int32_t depth_filter_margin, skip_pixel;
+} OrcCameraParams;
+int32_t orc_process_depth_image(const OrcCameraParams* cp, const uint16_t* depth, int32_t rows, int32_t cols,
+                                const double R[9], const double camera_pos[3], float* points_out);
+
 /* sdf_map.cpp:497-536 getDistWithGrad (via EDTEnvironment::evaluateEDTWithGrad,
  * edt_environment.cpp:78-87).  dist_buf = distance_buffer_. */
 double orc_dist_with_grad(const OrcGrid* g, const double* dist_buf, const double pos[3],

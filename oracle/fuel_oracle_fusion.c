@@ -247,3 +247,34 @@ void orc_input_point_cloud(const OrcGrid* g, const OrcFusionParams* fp, OrcFusio
   }
   free(queue);
 }
+
+/* MapROS::proessDepthImage, map_ros.cpp:176-215 */
+int32_t orc_process_depth_image(const OrcCameraParams* cp, const uint16_t* depth_image, int32_t rows, int32_t cols,
+                                const double R[9], const double camera_pos[3], float* points_out) {
+  int32_t cnt = 0;
+  const double inv_factor = 1.0 / cp->k_depth_scaling_factor;
+  const int m = cp->depth_filter_margin, skip = cp->skip_pixel;
+  const uint16_t* const img_end = depth_image + (int64_t)rows * cols;
+  for (int v = m; v < rows - m; v += skip) {
+    const uint16_t* row_ptr = depth_image + (int64_t)v * cols + m;
+    for (int u = m; u < cols - m; u += skip) {
+      double depth = (*row_ptr) * inv_factor;
+      row_ptr = row_ptr + skip;
+      /* the reference dereferences the advanced pointer; with margin 0 the very last read would leave the
+       * image -- treat that one as "no return" instead of reading out of bounds */
+      const uint16_t nxt = row_ptr < img_end ? *row_ptr : 0;
+      if (nxt == 0 || depth > cp->depth_filter_maxdist)
+        depth = cp->depth_filter_maxdist;
+      else if (depth < cp->depth_filter_mindist)
+        continue;
+      const double pc[3] = { (u - cp->cx) * depth / cp->fx, (v - cp->cy) * depth / cp->fy, depth };
+      for (int k = 0; k < 3; ++k) {
+        /* Eigen 3x3 * vector, coefficient order, then + camera_pos_ (:206) */
+        const double w = R[3 * k] * pc[0] + R[3 * k + 1] * pc[1] + R[3 * k + 2] * pc[2] + camera_pos[k];
+        points_out[3 * cnt + k] = (float)w; /* pt.x = pt_world[0] (float member) */
+      }
+      ++cnt;
+    }
+  }
+  return cnt;
+}

@@ -107,3 +107,30 @@ def test_office_depth_frames_then_inflate_and_esdf(fuel, orc):
         assert np.array_equal(np.isinf(q), ~fin)
         assert np.all(np.abs(q[fin] - r[fin]) <= 1e-4 * np.abs(r[fin]))
     m.close()
+
+
+def test_depth_image_path(fuel, orc):
+    """fuelgpu_map_input_depth_image == oracle proessDepthImage -> inputPointCloud, bit for bit."""
+    g, inflate_truth = W.office_map()
+    m, f = pair(fuel, orc, g)
+    cp = orc.camera_params()
+    rng = np.random.default_rng(4)
+    for k, (cam, yaw, pitch) in enumerate([((0.0, 0.0, 1.0), 0.3, 0.0), ((0.4, 0.2, 1.2), 1.1, -0.2), ((0.4, 0.2, 1.2), 2.5, 0.15)]):
+        cam = np.array(cam)
+        img, R = W.depth_image(g, inflate_truth, cam, yaw, pitch)
+        if k == 1:   # sensor drop-outs and too-close returns
+            img[rng.integers(0, 480, 4000), rng.integers(0, 640, 4000)] = 0
+            img[rng.integers(0, 480, 3000), rng.integers(0, 640, 3000)] = 150
+        pts = orc.process_depth_image(cp, img, R, cam)
+        lo, hi = f.input_point_cloud(pts, cam)
+        cnt = m.inputDepthImage(img, R, cam)
+        assert cnt == pts.shape[0]
+        got = m.getLogOdds().reshape(-1)
+        assert np.array_equal(got, f.logodds), "log-odds differ in %d voxels" % int((got != f.logodds).sum())
+        assert np.array_equal(m.local_bound_min_, lo) and np.array_equal(m.local_bound_max_, hi)
+    assert np.array_equal(np.concatenate(f.updated_box()), np.concatenate(m.getUpdatedBox()))
+    # an all-too-close image projects nothing and changes nothing
+    before = m.getLogOdds()
+    assert m.inputDepthImage(np.full((480, 640), 50, np.uint16), np.eye(3), np.array([0.0, 0.0, 1.0])) == 0
+    assert np.array_equal(before, m.getLogOdds())
+    m.close()

@@ -129,3 +129,30 @@ def test_depth_frames_reconstruct_the_scene():
     assert (tri == W.FREE).sum() > 20 * occ.sum()
     ci = tuple(O.pos_to_index(og, cam + np.array([0.3, 0.0, 0.0])))
     assert tri[ci] == W.FREE
+
+
+def test_depth_projection_matches_numpy_and_keeps_the_next_pixel_quirk():
+    """orc_process_depth_image (map_ros.cpp:176-215) against an independent numpy pinhole projection."""
+    g, inflate = W.office_map()
+    cam = np.array([0.5, -0.3, 1.1])
+    img, R = W.depth_image(g, inflate, cam, 0.9, pitch=-0.1)
+    cp = O.camera_params()
+    pts = O.process_depth_image(cp, img, R, cam)
+    ref = W.depth_frame(g, inflate, cam, 0.9, pitch=-0.1)
+    assert pts.shape == ref.shape and 70000 < pts.shape[0] <= 238 * 318
+    assert np.max(np.abs(pts - ref)) < 2e-6
+    # quirk: the zero test looks at pixel u+skip, the depth comes from pixel u
+    img2 = np.full((480, 640), 1500, np.uint16)
+    img2[100, 204] = 0            # makes the point of pixel (100, 202) "no return" (depth 5.0), not its own
+    p2 = O.process_depth_image(cp, img2, np.eye(3), np.zeros(3))
+    k = 49 * 318 + 100            # v = 100 -> row 49, u = 202 -> column 100
+    assert np.isclose(p2[k, 2], 5.0) and np.isclose(p2[k - 1, 2], 1.5)
+    # ... and pixel (100, 204) itself (depth 0, right neighbour valid) is dropped as "too close"
+    assert p2.shape[0] == 238 * 318 - 1 and np.isclose(p2[k + 1, 2], 1.5)
+    assert np.isclose(p2[k + 1, 0], (206 - cp.cx) * 1.5 / cp.fx)
+    # depth below depth_filter_mindist is skipped (count drops by one), beyond maxdist is clamped
+    img3 = np.full((480, 640), 1500, np.uint16)
+    img3[10, 10] = 100
+    img3[10, 12] = 9000
+    p3 = O.process_depth_image(cp, img3, np.eye(3), np.zeros(3))
+    assert p3.shape[0] == 238 * 318 - 1 and np.isclose(p3[:, 2].max(), 5.0)
