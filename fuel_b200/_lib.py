@@ -43,6 +43,12 @@ class FuelCameraParams(C.Structure):
                                                                       ("skip_pixel", C.c_int32)]
 
 
+class FuelViewParams(C.Structure):
+    _fields_ = [("candidate_rmin", C.c_double), ("candidate_rmax", C.c_double), ("candidate_rnum", C.c_int32),
+                ("candidate_dphi", C.c_double), ("min_candidate_clearance", C.c_double), ("top_angle", C.c_double),
+                ("left_angle", C.c_double), ("right_angle", C.c_double), ("max_dist", C.c_double)]
+
+
 class FuelOptParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in
                 ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide", "ld_waypt",
@@ -96,6 +102,10 @@ SIGNATURES = {
     "fuelgpu_frontier_clear_flags": (C.c_int, [_vp, _i32, _vp]),
     "fuelgpu_frontier_is_changed": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "fuelgpu_frontier_reset_flags": (C.c_int, [_vp]),
+    "fuelgpu_frontier_changed_counts": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "fuelgpu_viewpoint_candidate_count": (_i32, [C.POINTER(FuelViewParams)]),
+    "fuelgpu_frontier_sample_viewpoints": (C.c_int, [_vp, _i32, _vp, _vp, _vp, C.POINTER(FuelViewParams), _i32, _vp, _vp,
+                                                     _vp]),
     "fuelgpu_map_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "fuelgpu_frontier_download_flags": (C.c_int, [_vp, _vp]),
     "fuelgpu_frontier_upload_flags": (C.c_int, [_vp, _vp]),

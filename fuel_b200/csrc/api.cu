@@ -1,6 +1,8 @@
 // api.cu -- the extern "C" boundary of libfuelgpu (see include/fuelgpu.h).
 #include "common.cuh"
 
+#include <vector>
+
 #include <math.h>
 #include <stddef.h>
 #include <new>
@@ -530,6 +532,35 @@ int fuelgpu_frontier_is_changed(FuelMap* m, int32_t mcl, const int32_t* cell_off
   FUEL_CUDA(m, cudaSetDevice(m->dev));
   frontier_stream(m);
   return frontier_is_changed_impl(m, mcl, cell_offsets, cell_addr, changed);
+}
+
+int fuelgpu_frontier_changed_counts(FuelMap* m, int32_t mcl, const int32_t* cell_offsets, const int32_t* cell_addr,
+                                    int32_t* counts) {
+  if (!m || (mcl > 0 && (!cell_offsets || !cell_addr || !counts))) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  frontier_stream(m);
+  return frontier_is_changed_impl(m, mcl, cell_offsets, cell_addr, nullptr, counts);
+}
+
+int viewpoint_candidates_host(const FuelViewParams* vp, std::vector<double>* off);
+
+int32_t fuelgpu_viewpoint_candidate_count(const FuelViewParams* p) {
+  if (!p || p->candidate_rnum <= 0 || !(p->candidate_dphi > 0.0) || !(p->candidate_rmax >= p->candidate_rmin)) return -1;
+  return viewpoint_candidates_host(p, nullptr);
+}
+
+int fuelgpu_frontier_sample_viewpoints(FuelMap* m, int32_t n_clusters, const int32_t* filt_offsets, const double* filtered,
+                                       const double* average, const FuelViewParams* p, int32_t n_cand, double* cand_pos,
+                                       double* cand_yaw, int32_t* cand_visib) {
+  if (!m || !p) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (n_clusters < 0) return fuel_fail(m, FUELGPU_EINVAL, "negative cluster count");
+  if (n_clusters > 0 && (!filt_offsets || !average || !cand_pos || !cand_yaw || !cand_visib || (filt_offsets[n_clusters] > 0 && !filtered)))
+    return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (fuelgpu_viewpoint_candidate_count(p) <= 0) return fuel_fail(m, FUELGPU_EINVAL, "degenerate candidate parameters");
+  for (int i = 0; i < n_clusters; ++i)
+    if (filt_offsets[i + 1] < filt_offsets[i]) return fuel_fail(m, FUELGPU_EINVAL, "filt_offsets not monotone");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return sample_viewpoints_impl(m, n_clusters, filt_offsets, filtered, average, p, n_cand, cand_pos, cand_yaw, cand_visib);
 }
 
 int fuelgpu_frontier_reset_flags(FuelMap* m) {

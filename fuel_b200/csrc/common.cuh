@@ -123,7 +123,9 @@ int frontier_search_end_impl(FuelMap* m, int32_t* n_clusters, int32_t* n_cells, 
 int frontier_fetch_impl(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr, int32_t* filt_offsets,
                         double* filtered, double* average, double* box_min, double* box_max);
 int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const int32_t* addr,
-                             uint8_t* changed);
+                             uint8_t* changed, int32_t* counts = nullptr);
+int sample_viewpoints_impl(FuelMap* m, int ncl, const int32_t* filt_off, const double* filt, const double* avg,
+                           const FuelViewParams* vp, int ncand, double* cand_pos, double* cand_yaw, int32_t* cand_visib);
 
 int bspline_cost_batch_dev_impl(FuelMap* m, int B, int n_pts, int mask, const FuelOptParams* p,
                                 const FuelTrajConst* tc_dev, const double* x_dev, double* f_dev,

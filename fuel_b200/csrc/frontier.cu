@@ -1053,20 +1053,26 @@ __global__ void __cluster_dims__(SMALL_CTAS, 1, 1) __launch_bounds__(1024) clust
 }
 
 __global__ void is_changed_kernel(Geom g, const uint8_t* __restrict__ occ, const int* __restrict__ offs,
-                                  const int* __restrict__ addr, uint8_t* __restrict__ changed, int m) {
-  // isFrontierChanged (:365-372): one block per stored cluster
+                                  const int* __restrict__ addr, uint8_t* __restrict__ changed, int* __restrict__ counts,
+                                  int m) {
+  // isFrontierChanged (:365-372) / the change count of isFrontierCovered (:703-712): one block per stored cluster
   const int c = blockIdx.x;
   if (c >= m) return;
-  __shared__ int any;
-  if (threadIdx.x == 0) any = 0;
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
+  int mine = 0;
   for (int i = offs[c] + threadIdx.x; i < offs[c + 1]; i += blockDim.x) {
     int x, y, z;
     addr_to_idx(g, addr[i], x, y, z);
-    if (!frontier_pred(g, occ, x, y, z)) any = 1;
+    if (!frontier_pred(g, occ, x, y, z)) ++mine;
   }
+  if (mine) atomicAdd(&cnt, mine);
   __syncthreads();
-  if (threadIdx.x == 0) changed[c] = (uint8_t)any;
+  if (threadIdx.x == 0) {
+    if (changed) changed[c] = (uint8_t)(cnt > 0);
+    if (counts) counts[c] = cnt;
+  }
 }
 
 template <typename T>
@@ -1572,24 +1578,27 @@ int frontier_fetch_impl(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr, i
 }
 
 int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const int32_t* addr,
-                             uint8_t* changed) {
+                             uint8_t* changed, int32_t* counts) {
   if (mcl <= 0) return 0;
   const int ncell = offs[mcl];
-  int *d_off = nullptr, *d_addr = nullptr;
+  int *d_off = nullptr, *d_addr = nullptr, *d_cnt = nullptr;
   uint8_t* d_ch = nullptr;
   FUEL_CUDA(m, cudaMalloc(&d_off, sizeof(int) * (mcl + 1)));
   FUEL_CUDA(m, cudaMalloc(&d_addr, sizeof(int) * (ncell > 0 ? ncell : 1)));
   FUEL_CUDA(m, cudaMalloc(&d_ch, mcl));
+  FUEL_CUDA(m, cudaMalloc(&d_cnt, sizeof(int) * mcl));
   cudaStream_t s = m->fs->stream;
   FUEL_CUDA(m, cudaMemcpyAsync(d_off, offs, sizeof(int) * (mcl + 1), cudaMemcpyHostToDevice, s));
   if (ncell > 0) FUEL_CUDA(m, cudaMemcpyAsync(d_addr, addr, sizeof(int) * ncell, cudaMemcpyHostToDevice, s));
-  is_changed_kernel<<<mcl, 128, 0, s>>>(m->g, m->occ, d_off, d_addr, d_ch, mcl);
+  is_changed_kernel<<<mcl, 128, 0, s>>>(m->g, m->occ, d_off, d_addr, d_ch, d_cnt, mcl);
   FUEL_LAUNCHES(m, 1);
-  FUEL_CUDA(m, cudaMemcpyAsync(changed, d_ch, mcl, cudaMemcpyDeviceToHost, s));
+  if (changed) FUEL_CUDA(m, cudaMemcpyAsync(changed, d_ch, mcl, cudaMemcpyDeviceToHost, s));
+  if (counts) FUEL_CUDA(m, cudaMemcpyAsync(counts, d_cnt, sizeof(int) * mcl, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
   cudaFree(d_off);
   cudaFree(d_addr);
   cudaFree(d_ch);
+  cudaFree(d_cnt);
   return 0;
 }
 

@@ -4,19 +4,20 @@ Mirrors active_perception/include/active_perception/frontier_finder.h:25-133 and
 active_perception/src/frontier_finder.cpp:23-121 (file:line under /root/reference/fuel_planner/):
 `searchFrontiers()` with the stored-frontier bookkeeping (haveOverlap :353-363,
 isFrontierChanged :365-372, removed_ids_) on the host and every voxel-scale step in
-libfuelgpu.  Viewpoint sampling / cost matrix (computeFrontiersToVisit etc.) are outside
-the hot path and not mirrored.
+libfuelgpu.  The step right after it is mirrored too: computeFrontiersToVisit
+(:392-423) with sampleViewpoints / countVisibleCells (:662-695,734-755) on the device, and
+isFrontierCovered (:697-719).  The cost matrix / TSP (updateFrontierCostMatrix etc.) stay out of scope.
 """
 import ctypes as C
 
 import numpy as np
 
-from ._lib import FuelFrontierParams, check, lib, ptr
+from ._lib import FuelFrontierParams, FuelViewParams, check, lib, ptr
 
 
 class Frontier:
     """frontier_finder.h:34-51"""
-    __slots__ = ("cells_addr_", "filtered_cells_", "average_", "id_", "box_min_", "box_max_", "_map")
+    __slots__ = ("cells_addr_", "filtered_cells_", "average_", "id_", "box_min_", "box_max_", "_map", "viewpoints_")
 
     def __init__(self, m, addr, filtered, average, box_min, box_max):
         self._map = m
@@ -26,6 +27,7 @@ class Frontier:
         self.box_min_ = box_min
         self.box_max_ = box_max
         self.id_ = -1
+        self.viewpoints_ = []  # [(pos_ [3], yaw_, visib_num_)], frontier_finder.h:25-31
 
     @property
     def cells_(self):
@@ -49,6 +51,24 @@ class FrontierFinder:
         self.dormant_frontiers_ = []
         self.tmp_frontiers_ = []
         self.removed_ids_ = []
+        self.first_new_ftr_ = None
+        self.min_visib_num_ = 15
+        self.min_view_finish_fraction_ = 0.2
+        self.setViewParams()
+
+    def setViewParams(self, candidate_rmin=1.5, candidate_rmax=2.5, candidate_rnum=3, candidate_dphi=15 * 3.1415926 / 180.0,
+                      min_candidate_clearance=0.21, min_visib_num=15, min_view_finish_fraction=0.2, top_angle=0.56125,
+                      left_angle=0.69222, right_angle=0.68901, max_dist=4.5):
+        """frontier/* (frontier_finder.cpp:32-40) and perception_utils/* (perception_utils.cpp:7-10) parameters;
+        defaults = exploration_manager/launch/algorithm.xml:106-121."""
+        v = FuelViewParams()
+        v.candidate_rmin, v.candidate_rmax, v.candidate_rnum, v.candidate_dphi = (
+            candidate_rmin, candidate_rmax, candidate_rnum, candidate_dphi)
+        v.min_candidate_clearance = min_candidate_clearance
+        v.top_angle, v.left_angle, v.right_angle, v.max_dist = top_angle, left_angle, right_angle, max_dist
+        self._view = v
+        self.min_visib_num_ = int(min_visib_num)
+        self.min_view_finish_fraction_ = float(min_view_finish_fraction)
 
     @property
     def _map(self):
@@ -146,6 +166,85 @@ class FrontierFinder:
                                            ptr(bmax)), h)
         return [Frontier(m, addr[offs[i]:offs[i + 1]].copy(), filt[foffs[i]:foffs[i + 1]].copy(), avg[i].copy(),
                          bmin[i].copy(), bmax[i].copy()) for i in range(nc)]
+
+    # ---- the step after the search -------------------------------------
+    def sampleViewpointsRaw(self, ftrs):
+        """All candidates of sampleViewpoints (:662-695) for a list of clusters in ONE device call.
+        -> (pos [n,c,3], yaw [n,c], visib [n,c]); visib = -1 where the candidate is rejected (:671-673)."""
+        h = self._map.handle
+        nc = lib().fuelgpu_viewpoint_candidate_count(C.byref(self._view))
+        n = len(ftrs)
+        pos = np.zeros((n, nc, 3))
+        yaw = np.zeros((n, nc))
+        vis = np.zeros((n, nc), dtype=np.int32)
+        if n == 0:
+            return pos, yaw, vis
+        foffs = np.zeros(n + 1, dtype=np.int32)
+        for i, f in enumerate(ftrs):
+            foffs[i + 1] = foffs[i] + len(f.filtered_cells_)
+        filt = np.ascontiguousarray(np.concatenate([np.asarray(f.filtered_cells_, dtype=np.float64).reshape(-1, 3)
+                                                    for f in ftrs]))
+        avg = np.ascontiguousarray(np.stack([f.average_ for f in ftrs]), dtype=np.float64)
+        check(lib().fuelgpu_frontier_sample_viewpoints(h, n, ptr(foffs), ptr(filt), ptr(avg), C.byref(self._view), nc,
+                                                       ptr(pos), ptr(yaw), ptr(vis)), h)
+        return pos, yaw, vis
+
+    def computeFrontiersToVisit(self):
+        """frontier_finder.cpp:392-423: viewpoints for every new cluster; clusters with none go dormant.  The
+        reference sorts with std::sort (order of equal visib_num_ unspecified); here the sort is stable."""
+        self.first_new_ftr_ = None
+        pos, yaw, vis = self.sampleViewpointsRaw(self.tmp_frontiers_)
+        for i, f in enumerate(self.tmp_frontiers_):
+            keep = np.nonzero(vis[i] > self.min_visib_num_)[0]  # :688
+            f.viewpoints_ = [(pos[i, k].copy(), float(yaw[i, k]), int(vis[i, k])) for k in keep]
+            if f.viewpoints_:
+                f.viewpoints_.sort(key=lambda v: -v[2])  # best view in front, :404-406
+                self.frontiers_.append(f)
+                if self.first_new_ftr_ is None:
+                    self.first_new_ftr_ = len(self.frontiers_) - 1
+            else:
+                self.dormant_frontiers_.append(f)
+        for idx, f in enumerate(self.frontiers_):
+            f.id_ = idx  # :414-418
+
+    def getTopViewpointsInfo(self, cur_pos, min_candidate_dist=0.75):
+        """frontier_finder.cpp:425-453: the best viewpoint of every cluster farther than min_candidate_dist_."""
+        pts, yaws, avgs = [], [], []
+        cur_pos = np.asarray(cur_pos, dtype=np.float64)
+        for f in self.frontiers_:
+            chosen = None
+            for v in f.viewpoints_:
+                if np.linalg.norm(v[0] - cur_pos) < min_candidate_dist:
+                    continue
+                chosen = v
+                break
+            if chosen is None:
+                chosen = f.viewpoints_[0]
+            pts.append(chosen[0])
+            yaws.append(chosen[1])
+            avgs.append(f.average_)
+        return pts, yaws, avgs
+
+    def isFrontierCovered(self):
+        """frontier_finder.cpp:697-719: has any stored cluster overlapping the updated box lost at least
+        min_view_finish_fraction_ of its cells?"""
+        update_min, update_max = self._map.getUpdatedBox(False)
+        ftrs = [f for f in self.frontiers_ + self.dormant_frontiers_
+                if self.haveOverlap(f.box_min_, f.box_max_, update_min, update_max)]
+        if not ftrs:
+            return False
+        offs = np.zeros(len(ftrs) + 1, dtype=np.int32)
+        for i, f in enumerate(ftrs):
+            offs[i + 1] = offs[i] + f.cells_addr_.size
+        addr = np.ascontiguousarray(np.concatenate([f.cells_addr_ for f in ftrs]).astype(np.int32))
+        counts = np.zeros(len(ftrs), dtype=np.int32)
+        h = self._map.handle
+        check(lib().fuelgpu_frontier_changed_counts(h, len(ftrs), ptr(offs), ptr(addr), ptr(counts)), h)
+        for f, c in zip(ftrs, counts):
+            thresh = int(self.min_view_finish_fraction_ * f.cells_addr_.size)  # :704
+            if c >= max(thresh, 1):  # `++change_num >= change_thresh` fires on a changed cell only
+                return True
+        return False
 
     def getFrontiers(self):
         return [f.cells_ for f in self.frontiers_]

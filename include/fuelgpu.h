@@ -220,6 +220,37 @@ FUELGPU_API int fuelgpu_frontier_reset_flags(FuelMap* map);
 FUELGPU_API int fuelgpu_frontier_download_flags(FuelMap* map, int8_t* out);
 FUELGPU_API int fuelgpu_frontier_upload_flags(FuelMap* map, const int8_t* in);
 
+/* ---- viewpoint sampling ---------------------------------------------- */
+typedef struct {
+  double candidate_rmin, candidate_rmax; /* frontier/candidate_rmin, candidate_rmax (frontier_finder.cpp:35-36) */
+  int32_t candidate_rnum;                /* frontier/candidate_rnum (:37) */
+  double candidate_dphi;                 /* frontier/candidate_dphi (:34) */
+  double min_candidate_clearance;        /* frontier/min_candidate_clearance (:33) */
+  double top_angle, left_angle, right_angle, max_dist; /* perception_utils params (perception_utils.cpp:7-10) */
+} FuelViewParams;
+
+/* Number of (radius, angle) candidates the loops of sampleViewpoints visit (frontier_finder.cpp:664-667);
+ * negative on a degenerate parameter set. */
+FUELGPU_API int32_t fuelgpu_viewpoint_candidate_count(const FuelViewParams* params);
+/* Replaces FrontierFinder::sampleViewpoints (active_perception/src/frontier_finder.cpp:662-695) with
+ * isNearUnknown (:721-732), countVisibleCells (:734-755) and PerceptionUtils::setPose/insideFOV
+ * (active_perception/src/perception_utils.cpp:49-93) for n_clusters clusters at once, against the resident
+ * occupancy byte.  Inputs in the layout fuelgpu_frontier_fetch returns: filt_offsets[n_clusters+1],
+ * filtered[3*filt_offsets[n]] (filtered_cells_), average[3*n_clusters].  Outputs, n_cand =
+ * fuelgpu_viewpoint_candidate_count() entries per cluster in the reference's loop order:
+ *   cand_pos[3*n*n_cand] sample_pos; cand_yaw[n*n_cand] avg_yaw; cand_visib[n*n_cand] = countVisibleCells,
+ *   or -1 where the candidate fails isInBox / getInflateOccupancy / isNearUnknown (:671-673).
+ * The caller keeps candidates with visib > min_visib_num_ (:688) and sorts them (:404-406). */
+FUELGPU_API int fuelgpu_frontier_sample_viewpoints(FuelMap* map, int32_t n_clusters, const int32_t* filt_offsets,
+                                                   const double* filtered, const double* average,
+                                                   const FuelViewParams* params, int32_t n_cand, double* cand_pos,
+                                                   double* cand_yaw, int32_t* cand_visib);
+/* isFrontierCovered's per-cluster count (frontier_finder.cpp:697-719): how many of each stored cluster's cells are
+ * no longer frontier cells; the caller compares with min_view_finish_fraction_ * size.  Same CSR input as
+ * fuelgpu_frontier_is_changed. */
+FUELGPU_API int fuelgpu_frontier_changed_counts(FuelMap* map, int32_t n_clusters, const int32_t* cell_offsets,
+                                                const int32_t* cell_addr, int32_t* counts);
+
 /* ---- B-spline cost ------------------------------------------------------------------ */
 /* cost-term bits = BsplineOptimizer::SMOOTHNESS..MINTIME (bspline_opt/src/bspline_optimizer.cpp:10-18) */
 #define FUELGPU_SMOOTHNESS (1 << 0)

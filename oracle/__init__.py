@@ -25,7 +25,8 @@ GUIDE_PHASE = SMOOTHNESS | GUIDE | START | END
 
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc -O3, the reference's flags)."""
-    src = [os.path.join(_HERE, f) for f in ("fuel_oracle.c", "fuel_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("fuel_oracle.c", "fuel_oracle_fusion.c", "fuel_oracle_viewpoints.c",
+                                            "fuel_oracle.h", "Makefile")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src)):
         return _SO
@@ -58,6 +59,12 @@ class OrcCameraParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("fx", "fy", "cx", "cy", "k_depth_scaling_factor", "depth_filter_maxdist",
                                           "depth_filter_mindist")] + [("depth_filter_margin", C.c_int32),
                                                                       ("skip_pixel", C.c_int32)]
+
+
+class OrcViewParams(C.Structure):
+    _fields_ = [("candidate_rmin", C.c_double), ("candidate_rmax", C.c_double), ("candidate_rnum", C.c_int32),
+                ("candidate_dphi", C.c_double), ("min_candidate_clearance", C.c_double), ("top_angle", C.c_double),
+                ("left_angle", C.c_double), ("right_angle", C.c_double), ("max_dist", C.c_double)]
 
 
 class OrcOptParams(C.Structure):
@@ -232,6 +239,44 @@ class Fusion:
     def tristate(self):
         p = self.p
         return tristate_from_logodds(self.logodds, np.log(p.p_min / (1 - p.p_min)), np.log(p.p_occ / (1 - p.p_occ)))
+
+
+def view_params(candidate_rmin=1.5, candidate_rmax=2.5, candidate_rnum=3, candidate_dphi=15 * 3.1415926 / 180.0,
+                min_candidate_clearance=0.21, top_angle=0.56125, left_angle=0.69222, right_angle=0.68901, max_dist=4.5):
+    """defaults = exploration_manager/launch/algorithm.xml:106-121"""
+    v = OrcViewParams()
+    v.candidate_rmin, v.candidate_rmax, v.candidate_rnum, v.candidate_dphi = (
+        candidate_rmin, candidate_rmax, candidate_rnum, candidate_dphi)
+    v.min_candidate_clearance = min_candidate_clearance
+    v.top_angle, v.left_angle, v.right_angle, v.max_dist = top_angle, left_angle, right_angle, max_dist
+    return v
+
+
+def sample_viewpoints(g, tri, inflate, vp, average, cells):
+    """sampleViewpoints (frontier_finder.cpp:662-695) for one cluster, all candidates reported.
+    -> dict(pos [c,3], yaw [c], visib [c] (-1 = rejected candidate), border [c])"""
+    L = lib()
+    L.orc_viewpoint_candidates.restype = C.c_int32
+    L.orc_sample_viewpoints.restype = C.c_int32
+    nc = L.orc_viewpoint_candidates(C.byref(vp), None, C.c_int32(0))
+    tri = np.ascontiguousarray(tri, dtype=np.uint8)
+    inflate = np.ascontiguousarray(inflate, dtype=np.int8)
+    cells = np.ascontiguousarray(cells, dtype=np.float64).reshape(-1, 3)
+    avg = np.ascontiguousarray(average, dtype=np.float64)
+    pos = np.zeros((nc, 3))
+    yaw = np.zeros(nc)
+    vis = np.zeros(nc, np.int32)
+    brd = np.zeros(nc, np.uint8)
+    L.orc_sample_viewpoints(C.byref(g), _p(tri), _p(inflate), C.byref(vp), _p(avg), _p(cells), C.c_int32(cells.shape[0]),
+                            _p(pos), _p(yaw), _p(vis), _p(brd))
+    return dict(pos=pos, yaw=yaw, visib=vis, border=brd)
+
+
+def frontier_changed_count(g, tri, addr):
+    addr = np.ascontiguousarray(addr, dtype=np.int32)
+    lib().orc_frontier_changed_count.restype = C.c_int32
+    return lib().orc_frontier_changed_count(C.byref(g), _p(np.ascontiguousarray(tri, dtype=np.uint8)), _p(addr),
+                                            C.c_int32(addr.shape[0]))
 
 
 def dist_with_grad(g, dist_buf, pos):

@@ -150,6 +150,20 @@ int orc_is_frontier_cell(const OrcGrid* g, const uint8_t* tri, const int32_t id[
  * EigenSolver convention (:202-213); exposed for its own tests */
 void orc_principal_axis_2x2(double a, double b, double d, double pc[2]);
 
+/* ---- viewpoint sampling; fuel_oracle_viewpoints.c ------------------------------- */
+typedef struct {
+  double candidate_rmin, candidate_rmax; /* frontier/candidate_rmin, rmax (frontier_finder.cpp:35-36) */
+  int32_t candidate_rnum;                /* frontier/candidate_rnum (:37) */
+  double candidate_dphi;                 /* frontier/candidate_dphi (:34) */
+  double min_candidate_clearance;        /* frontier/min_candidate_clearance (:33) */
+  double top_angle, left_angle, right_angle, max_dist; /* perception_utils params (perception_utils.cpp:7-10) */
+} OrcViewParams;
+int32_t orc_viewpoint_candidates(const OrcViewParams* vp, double* off_xy, int32_t max);
+int32_t orc_sample_viewpoints(const OrcGrid* g, const uint8_t* tri, const int8_t* inflate, const OrcViewParams* vp,
+                              const double average[3], const double* cells, int32_t n_cells, double* cand_pos,
+                              double* cand_yaw, int32_t* cand_visib, uint8_t* cand_border);
+int32_t orc_frontier_changed_count(const OrcGrid* g, const uint8_t* tri, const int32_t* addr, int32_t n);
+
 /* ---- B-spline cost: bspline_opt/src/bspline_optimizer.cpp ---------------------------- */
 enum {
   ORC_SMOOTHNESS = 1 << 0, ORC_DISTANCE = 1 << 1, ORC_FEASIBILITY = 1 << 2,
