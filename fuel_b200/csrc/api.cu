@@ -542,8 +542,6 @@ int fuelgpu_frontier_changed_counts(FuelMap* m, int32_t mcl, const int32_t* cell
   return frontier_is_changed_impl(m, mcl, cell_offsets, cell_addr, nullptr, counts);
 }
 
-int viewpoint_candidates_host(const FuelViewParams* vp, std::vector<double>* off);
-
 int32_t fuelgpu_viewpoint_candidate_count(const FuelViewParams* p) {
   if (!p || p->candidate_rnum <= 0 || !(p->candidate_dphi > 0.0) || !(p->candidate_rmax >= p->candidate_rmin)) return -1;
   return viewpoint_candidates_host(p, nullptr);

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "fuelgpu.h"
 
 #define FUELGPU_EDT_INF_I 0x3fffffff
@@ -124,6 +126,7 @@ int frontier_fetch_impl(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr, i
                         double* filtered, double* average, double* box_min, double* box_max);
 int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const int32_t* addr,
                              uint8_t* changed, int32_t* counts = nullptr);
+int viewpoint_candidates_host(const FuelViewParams* vp, std::vector<double>* off);
 int sample_viewpoints_impl(FuelMap* m, int ncl, const int32_t* filt_off, const double* filt, const double* avg,
                            const FuelViewParams* vp, int ncand, double* cand_pos, double* cand_yaw, int32_t* cand_visib);
 
