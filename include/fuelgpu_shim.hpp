@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <list>
 #include <memory>
 #include <stdexcept>
@@ -300,8 +301,15 @@ private:
 };
 
 // ---- FrontierFinder (frontier_finder.h:25-131) ---------------------------------------------------
-struct Frontier {  // frontier_finder.h:34-51 (viewpoints_/paths_/costs_ belong to out-of-scope stages)
+struct Viewpoint {  // frontier_finder.h:25-31
+  Vector3d pos_;
+  double yaw_;
+  int visib_num_;
+};
+
+struct Frontier {  // frontier_finder.h:34-51 (paths_/costs_ belong to out-of-scope stages)
   std::vector<Vector3d> cells_;
+  std::vector<Viewpoint> viewpoints_;
   std::vector<Vector3d> filtered_cells_;
   Vector3d average_;
   int id_ = -1;
@@ -358,6 +366,54 @@ public:
       tmp_frontiers_.push_back(f);
     }
   }
+  // computeFrontiersToVisit (frontier_finder.cpp:392-423): sampleViewpoints (:662-695) of every new cluster in one
+  // device call; clusters without a qualified viewpoint go dormant.
+  FuelViewParams view_ = { 1.5, 2.5, 3, 15 * 3.1415926 / 180.0, 0.21, 0.56125, 0.69222, 0.68901, 4.5 };  // algorithm.xml:106-121
+  int min_visib_num_ = 15;
+  void computeFrontiersToVisit() {
+    first_new_ftr_ = frontiers_.end();
+    const int n = (int)tmp_frontiers_.size(), nc = fuelgpu_viewpoint_candidate_count(&view_);
+    std::vector<int32_t> fo(n + 1, 0);
+    std::vector<double> filt, avg;
+    int i = 0;
+    for (auto& f : tmp_frontiers_) {
+      for (auto& c : f.filtered_cells_) filt.insert(filt.end(), { c(0), c(1), c(2) });
+      avg.insert(avg.end(), { f.average_(0), f.average_(1), f.average_(2) });
+      fo[i + 1] = fo[i] + (int)f.filtered_cells_.size();
+      ++i;
+    }
+    std::vector<double> pos(3 * (size_t)n * nc), yaw((size_t)n * nc);
+    std::vector<int32_t> vis((size_t)n * nc);
+    if (n > 0)
+      fuelgpu_check(fuelgpu_frontier_sample_viewpoints(gpu(), n, fo.data(), filt.data(), avg.data(), &view_, nc, pos.data(),
+                                                       yaw.data(), vis.data()),
+                    gpu());
+    i = 0;
+    for (auto& f : tmp_frontiers_) {
+      for (int k = 0; k < nc; ++k) {
+        const size_t o = (size_t)i * nc + k;
+        if (vis[o] > min_visib_num_) {  // :688
+          Viewpoint vp;
+          for (int d = 0; d < 3; ++d) vp.pos_(d) = pos[3 * o + d];
+          vp.yaw_ = yaw[o];
+          vp.visib_num_ = vis[o];
+          f.viewpoints_.push_back(vp);
+        }
+      }
+      if (!f.viewpoints_.empty()) {
+        auto inserted = frontiers_.insert(frontiers_.end(), f);
+        std::sort(inserted->viewpoints_.begin(), inserted->viewpoints_.end(),
+                  [](const Viewpoint& a, const Viewpoint& b) { return a.visib_num_ > b.visib_num_; });  // :404-406
+        if (first_new_ftr_ == frontiers_.end()) first_new_ftr_ = inserted;
+      } else
+        dormant_frontiers_.push_back(f);
+      ++i;
+    }
+    int idx = 0;
+    for (auto& ft : frontiers_) ft.id_ = idx++;
+  }
+  std::list<Frontier>::iterator first_new_ftr_;
+
   void getFrontiers(std::vector<std::vector<Vector3d>>& clusters) const {
     clusters.clear();
     for (auto& f : frontiers_) clusters.push_back(f.cells_);
