@@ -19,9 +19,21 @@ constexpr int MAXM = 8;
 struct V3 {
   double v[3];
 };
-__device__ __forceinline__ double dot3(const V3& a, const V3& b) {
-  return wsum(a.v[0] * b.v[0] + a.v[1] * b.v[1] + a.v[2] * b.v[2]);
+// Solver-internal inner products (L-BFGS coefficients, Armijo slope, curvature test): the per-lane partial is
+// formed in fp64 and the 32-lane sum runs as an fp32 xor butterfly (one SHFL per stage instead of two, the sum
+// lands in every lane).  A relative 1e-7 on these scalars only perturbs the quasi-Newton direction; the cost F
+// that decides acceptance and best-x stays fp64.
+__device__ __forceinline__ double wsum_x(double v) {
+  float f = (float)v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+  return (double)f;
 }
+__device__ __forceinline__ double dot3(const V3& a, const V3& b) {
+  return wsum_x(a.v[0] * b.v[0] + a.v[1] * b.v[1] + a.v[2] * b.v[2]);
+}
+// history element (slot, component k) of this lane: [slot][k][lane], conflict-free
+#define HIDX(slot, k) ((slot) * 96 + (k) * 32 + lane)
 
 __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
     Geom g, const float* __restrict__ dist, FuelOptParams p, const FuelTrajConst* __restrict__ tc, int n,
@@ -93,7 +105,7 @@ __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
   if (!(best == best)) best = 1.7976931348623157e308;
 
   int cnt = 0, head = 0;  // history ring: newest at (head-1) mod m
-  double rho[MAXM];
+  double rho[MAXM];  // rho[j] belongs to the j-th newest pair (static indices: stays in registers)
 #pragma unroll
   for (int j = 0; j < MAXM; ++j) rho[j] = 0.0;
 
@@ -115,25 +127,26 @@ __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
     for (int j = 0; j < MAXM; ++j) {
       alpha[j] = 0.0;
       if (j < cnt) {
-        const int slot = (head - 1 - j + 2 * MAXM * m) % m;
+        int slot = head - 1 - j;  // j < cnt <= m: one wrap at most
+        if (slot < 0) slot += m;
         V3 s, y;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          s.v[k] = S[slot * 96 + lane * 3 + k];
-          y.v[k] = Y[slot * 96 + lane * 3 + k];
+          s.v[k] = S[HIDX(slot, k)];
+          y.v[k] = Y[HIDX(slot, k)];
         }
-        alpha[j] = rho[slot] * dot3(s, Q);
+        alpha[j] = rho[j] * dot3(s, Q);
 #pragma unroll
         for (int k = 0; k < 3; ++k) Q.v[k] -= alpha[j] * y.v[k];
       }
     }
     if (cnt > 0) {
-      const int slot = (head - 1 + m) % m;
+      const int slot = head == 0 ? m - 1 : head - 1;
       V3 s, y;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        s.v[k] = S[slot * 96 + lane * 3 + k];
-        y.v[k] = Y[slot * 96 + lane * 3 + k];
+        s.v[k] = S[HIDX(slot, k)];
+        y.v[k] = Y[HIDX(slot, k)];
       }
       const double gamma = dot3(s, y) / dot3(y, y);
 #pragma unroll
@@ -142,14 +155,15 @@ __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
 #pragma unroll
     for (int j = MAXM - 1; j >= 0; --j) {
       if (j < cnt) {
-        const int slot = (head - 1 - j + 2 * MAXM * m) % m;
+        int slot = head - 1 - j;
+        if (slot < 0) slot += m;
         V3 s, y;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          s.v[k] = S[slot * 96 + lane * 3 + k];
-          y.v[k] = Y[slot * 96 + lane * 3 + k];
+          s.v[k] = S[HIDX(slot, k)];
+          y.v[k] = Y[HIDX(slot, k)];
         }
-        const double beta = rho[slot] * dot3(y, Q);
+        const double beta = rho[j] * dot3(y, Q);
 #pragma unroll
         for (int k = 0; k < 3; ++k) Q.v[k] += s.v[k] * (alpha[j] - beta);
       }
@@ -204,14 +218,14 @@ __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
       const int slot = head;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        S[slot * 96 + lane * 3 + k] = s.v[k];
-        Y[slot * 96 + lane * 3 + k] = y.v[k];
+        S[HIDX(slot, k)] = s.v[k];
+        Y[HIDX(slot, k)] = y.v[k];
       }
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < MAXM; ++j)
-        if (j == slot) rho[j] = 1.0 / sy;
-      head = (head + 1) % m;
+      for (int j = MAXM - 1; j > 0; --j) rho[j] = rho[j - 1];
+      rho[0] = 1.0 / sy;
+      head = head + 1 == m ? 0 : head + 1;
       if (cnt < m) ++cnt;
     }
     X = XN;
