@@ -245,6 +245,8 @@ class GpuPlanner:
         self._tcs_view = np.frombuffer(self.tcs, dtype=np.uint8)
         m.pin(self._tcs_view)
         self.n_clusters = 0
+        # result buffers of the optimiser, reused every replan (the reference keeps best_variable_ as a member)
+        self.opt_out = (np.empty_like(self.x_host), np.empty(batch, dtype=np.float64), np.empty(batch, dtype=np.int32))
         # the frontier subsystem has its own stream in the library: the search is enqueued first
         # (fuelgpu_frontier_search_begin), the ESDF update and the solver run beside it on the main
         # stream, and the result is collected last (fuelgpu_frontier_search_end)
@@ -289,7 +291,8 @@ class GpuPlanner:
             out = self.ff.search_box_end()
         m.updateESDF3d()
         m.download(wait=not self.overlap)  # overlap: the D2H mirror copy runs beside the solver
-        x, f, ne = self.opt.optimizeBatch(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0)
+        x, f, ne = self.opt.optimizeBatch(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0,
+                                          out=self.opt_out)
         if self.overlap:
             out = self.ff.search_box_end()
             m.synchronize()  # ESDF host mirror complete

@@ -163,19 +163,23 @@ class BsplineOptimizer:
                                                ptr(f), ptr(g)), h)
         return f, g
 
-    def optimizeBatch(self, x, traj_consts, n_pts, cost_function, max_eval, lbfgs_m=6, xtol_rel=1e-5):
+    def optimizeBatch(self, x, traj_consts, n_pts, cost_function, max_eval, lbfgs_m=6, xtol_rel=1e-5, out=None):
         """The solver loop of optimize() (:165-253) for B trajectories in one persistent kernel.
         x [B, nvar] initial variables (clamped to the box shrunk by 0.1 m on the device, :196-204).
-        Returns (x_best [B, nvar], f_best [B], n_eval [B])."""
+        Returns (x_best [B, nvar], f_best [B], n_eval [B]); `out` = a tuple of such arrays to reuse (like
+        the reference's best_variable_ member) instead of allocating new ones per call."""
         mask = int(cost_function)
-        x = np.array(x, dtype=np.float64, order="C", copy=True)
-        B = x.shape[0]
-        if x.shape[1] != self.nvar(n_pts, mask):
+        B = len(x)
+        if out is None:
+            out = (np.empty((B, self.nvar(n_pts, mask)), dtype=np.float64), np.empty(B, dtype=np.float64),
+                   np.empty(B, dtype=np.int32))
+        xw, fb, ne = out
+        if np.shape(x)[1] != self.nvar(n_pts, mask) or xw.shape != np.shape(x):
             raise ValueError("x must be [B, %d]" % self.nvar(n_pts, mask))
+        np.copyto(xw, x)
+        x = xw
         sp = FuelSolveParams()
         sp.max_eval, sp.lbfgs_m, sp.xtol_rel = int(max_eval), int(lbfgs_m), float(xtol_rel)
-        fb = np.empty(B, dtype=np.float64)
-        ne = np.empty(B, dtype=np.int32)
         h = self.edt_environment_.sdf_map_.handle
         check(lib().fuelgpu_bspline_optimize_batch(h, B, n_pts, mask, C.byref(self.params_), traj_consts,
                                                    C.byref(sp), ptr(x), ptr(fb), ptr(ne)), h)

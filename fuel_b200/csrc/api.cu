@@ -66,6 +66,16 @@ int ensure_bs(FuelMap* m, size_t bytes) {
   return 0;
 }
 
+static int ensure_bs_pin(FuelMap* m, size_t bytes) {
+  if (bytes <= m->bs_pin_bytes) return 0;
+  if (m->bs_pin) cudaFreeHost(m->bs_pin);
+  m->bs_pin = nullptr;
+  m->bs_pin_bytes = 0;
+  FUEL_CUDA(m, cudaMallocHost(&m->bs_pin, bytes + bytes / 4));
+  m->bs_pin_bytes = bytes + bytes / 4;
+  return 0;
+}
+
 int check_box(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3], int lo[3], int hi[3]) {
   const int n[3] = { m->g.nx, m->g.ny, m->g.nz };
   for (int i = 0; i < 3; ++i) {
@@ -197,6 +207,7 @@ int fuelgpu_map_destroy(FuelMap* m) {
   if (m->own_stream) cudaStreamSynchronize(m->own_stream);
   frontier_state_destroy(m);
   fusion_state_destroy(m);
+  if (m->bs_pin) cudaFreeHost(m->bs_pin);
   void* ptrs[] = { m->occ, m->dist, m->dist_neg, m->flag, m->g1, m->g2, m->stk, m->stage, m->bs_buf };
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -592,20 +603,26 @@ int fuelgpu_frontier_upload_flags(FuelMap* m, const int8_t* in) {
   return 0;
 }
 
-// H2D of the per-trajectory constants.  The guide / waypoint arrays are 3 KB of the 3.3 KB record;
-// when no trajectory uses them (the exploration objective) only the leading part is sent.
-static cudaError_t upload_traj(FuelMap* m, FuelTrajConst* d_tc, const FuelTrajConst* traj, int B) {
+// H2D of the per-trajectory constants.  The guide / waypoint arrays are 3 KB of the 3.3 KB record; when no
+// trajectory uses them (the exploration objective) only the leading part (+ n_waypt) is sent: packed into the
+// page-locked bounce buffer, one contiguous DMA, then two strided device-side copies into the records.
+// `pin` = host bounce area of >= B*(head+4) bytes, `d_pack` = device scratch of the same size.
+static cudaError_t upload_traj(FuelMap* m, FuelTrajConst* d_tc, const FuelTrajConst* traj, int B, uint8_t* pin,
+                               uint8_t* d_pack) {
   bool lean = true;
   for (int b = 0; b < B && lean; ++b) lean = traj[b].n_guide == 0 && traj[b].n_waypt == 0;
   if (!lean) return cudaMemcpyAsync(d_tc, traj, sizeof(FuelTrajConst) * (size_t)B, cudaMemcpyHostToDevice, m->stream);
-  const size_t head = offsetof(FuelTrajConst, guide);
-  cudaError_t e = cudaMemcpy2DAsync(d_tc, sizeof(FuelTrajConst), traj, sizeof(FuelTrajConst), head, B,
-                                    cudaMemcpyHostToDevice, m->stream);
+  const size_t head = offsetof(FuelTrajConst, guide), rec = head + sizeof(int32_t);
+  for (int b = 0; b < B; ++b) {
+    memcpy(pin + rec * b, &traj[b], head);
+    memcpy(pin + rec * b + head, &traj[b].n_waypt, sizeof(int32_t));
+  }
+  cudaError_t e = cudaMemcpyAsync(d_pack, pin, rec * B, cudaMemcpyHostToDevice, m->stream);
   if (e != cudaSuccess) return e;
-  // n_waypt lives after the guide array
-  return cudaMemcpy2DAsync((char*)d_tc + offsetof(FuelTrajConst, n_waypt), sizeof(FuelTrajConst),
-                           (const char*)traj + offsetof(FuelTrajConst, n_waypt), sizeof(FuelTrajConst),
-                           sizeof(int32_t), B, cudaMemcpyHostToDevice, m->stream);
+  e = cudaMemcpy2DAsync(d_tc, sizeof(FuelTrajConst), d_pack, rec, head, B, cudaMemcpyDeviceToDevice, m->stream);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy2DAsync((char*)d_tc + offsetof(FuelTrajConst, n_waypt), sizeof(FuelTrajConst), d_pack + head, rec,
+                           sizeof(int32_t), B, cudaMemcpyDeviceToDevice, m->stream);
 }
 
 static int check_bspline_args(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
@@ -647,22 +664,34 @@ int fuelgpu_bspline_cost_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mas
   const int nvar = (mask & FUELGPU_MINTIME) ? 3 * n_pts + 1 : 3 * n_pts;
   const size_t tcb = sizeof(FuelTrajConst) * (size_t)B;
   const size_t xb = sizeof(double) * (size_t)B * nvar;
-  rc = ensure_bs(m, tcb + 2 * xb + sizeof(double) * (size_t)B + 64);
+  const size_t packb = ((offsetof(FuelTrajConst, guide) + sizeof(int32_t)) * (size_t)B + 63) & ~(size_t)63;
+  const size_t fb = sizeof(double) * (size_t)B;
+  rc = ensure_bs(m, tcb + 2 * xb + fb + packb + 64);
+  if (rc) return rc;
+  rc = ensure_bs_pin(m, packb + 2 * xb + fb);
   if (rc) return rc;
   uint8_t* base = (uint8_t*)m->bs_buf;
   FuelTrajConst* d_tc = (FuelTrajConst*)base;
   double* d_x = (double*)(base + tcb);
   double* d_g = d_x + (size_t)B * nvar;
   double* d_f = d_g + (size_t)B * nvar;
-  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B));
-  FUEL_CUDA(m, cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, m->stream));
+  uint8_t* d_pack = (uint8_t*)(d_f + B);
+  // host buffers of unknown provenance (pageable or pinned) bounce through the page-locked area
+  uint8_t* pin = (uint8_t*)m->bs_pin;
+  double* h_x = (double*)(pin + packb);
+  double* h_g = h_x + (size_t)B * nvar;
+  double* h_f = h_g + (size_t)B * nvar;
+  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack));
+  memcpy(h_x, x, xb);
+  FUEL_CUDA(m, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, m->stream));
   tbegin(m, T_BSPLINE);
   rc = bspline_cost_batch_dev_impl(m, B, n_pts, mask, p, d_tc, d_x, d_f, d_g);
   tend(m, T_BSPLINE);
   if (rc) return rc;
-  FUEL_CUDA(m, cudaMemcpyAsync(f, d_f, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream));
-  FUEL_CUDA(m, cudaMemcpyAsync(grad, d_g, xb, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_g, d_g, xb + fb, cudaMemcpyDeviceToHost, m->stream));  // grad and f are adjacent
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  memcpy(grad, h_g, xb);
+  memcpy(f, h_f, fb);
   return 0;
 }
 
@@ -699,23 +728,32 @@ int fuelgpu_bspline_optimize_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t
   const int nvar = (mask & FUELGPU_MINTIME) ? 3 * n_pts + 1 : 3 * n_pts;
   const size_t tcb = sizeof(FuelTrajConst) * (size_t)B;
   const size_t xb = sizeof(double) * (size_t)B * nvar;
-  rc = ensure_bs(m, tcb + xb + sizeof(double) * (size_t)B + sizeof(int32_t) * (size_t)B + 64);
+  const size_t packb = ((offsetof(FuelTrajConst, guide) + sizeof(int32_t)) * (size_t)B + 63) & ~(size_t)63;
+  const size_t fb = sizeof(double) * (size_t)B, nb = sizeof(int32_t) * (size_t)B;
+  rc = ensure_bs(m, tcb + xb + fb + nb + packb + 64);
+  if (rc) return rc;
+  rc = ensure_bs_pin(m, packb + xb + fb + nb);
   if (rc) return rc;
   uint8_t* base = (uint8_t*)m->bs_buf;
   FuelTrajConst* d_tc = (FuelTrajConst*)base;
   double* d_x = (double*)(base + tcb);
   double* d_f = d_x + (size_t)B * nvar;
   int32_t* d_n = (int32_t*)(d_f + B);
-  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B));
-  FUEL_CUDA(m, cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, m->stream));
+  uint8_t* d_pack = (uint8_t*)(((uintptr_t)(d_n + B) + 63) & ~(uintptr_t)63);
+  uint8_t* pin = (uint8_t*)m->bs_pin;
+  double* h_x = (double*)(pin + packb);  // x, f_best, n_eval adjacent on both sides: one DMA back
+  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack));
+  memcpy(h_x, x, xb);
+  FUEL_CUDA(m, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, m->stream));
   tbegin(m, T_BSPLINE);
   rc = bspline_optimize_batch_dev_impl(m, B, n_pts, mask, p, d_tc, solve, d_x, d_f, d_n);
   tend(m, T_BSPLINE);
   if (rc) return rc;
-  FUEL_CUDA(m, cudaMemcpyAsync(x, d_x, xb, cudaMemcpyDeviceToHost, m->stream));
-  FUEL_CUDA(m, cudaMemcpyAsync(f_best, d_f, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream));
-  FUEL_CUDA(m, cudaMemcpyAsync(n_eval, d_n, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, m->stream));
+  FUEL_CUDA(m, cudaMemcpyAsync(h_x, d_x, xb + fb + nb, cudaMemcpyDeviceToHost, m->stream));
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  memcpy(x, h_x, xb);
+  memcpy(f_best, (uint8_t*)h_x + xb, fb);
+  memcpy(n_eval, (uint8_t*)h_x + xb + fb, nb);
   return 0;
 }
 

@@ -56,6 +56,8 @@ struct FuelMap {
   // bspline scratch (device)
   void* bs_buf;
   size_t bs_bytes;
+  void* bs_pin;  // page-locked bounce buffer for the host-facing B-spline calls
+  size_t bs_pin_bytes;
   long long launches;  // kernels launched so far
   char err[512];
 };

@@ -155,17 +155,17 @@ class FrontierFinder:
         nc, ncell, nf = C.c_int32(), C.c_int32(), C.c_int32()
         check(lib().fuelgpu_frontier_search_end(h, C.byref(nc), C.byref(ncell), C.byref(nf)), h)
         nc, ncell, nf = nc.value, ncell.value, nf.value
-        offs = np.zeros(nc + 1, dtype=np.int32)
-        addr = np.zeros(ncell, dtype=np.int32)
-        foffs = np.zeros(nc + 1, dtype=np.int32)
-        filt = np.zeros((nf, 3), dtype=np.float64)
-        avg = np.zeros((nc, 3), dtype=np.float64)
-        bmin = np.zeros((nc, 3), dtype=np.float64)
-        bmax = np.zeros((nc, 3), dtype=np.float64)
+        # arrays of this call; the Frontier objects hold views into them
+        offs = np.empty(nc + 1, dtype=np.int32)
+        addr = np.empty(ncell, dtype=np.int32)
+        foffs = np.empty(nc + 1, dtype=np.int32)
+        filt = np.empty((nf, 3), dtype=np.float64)
+        stats = np.empty((3, nc, 3), dtype=np.float64)
+        avg, bmin, bmax = stats[0], stats[1], stats[2]
         check(lib().fuelgpu_frontier_fetch(h, ptr(offs), ptr(addr), ptr(foffs), ptr(filt), ptr(avg), ptr(bmin),
                                            ptr(bmax)), h)
-        return [Frontier(m, addr[offs[i]:offs[i + 1]].copy(), filt[foffs[i]:foffs[i + 1]].copy(), avg[i].copy(),
-                         bmin[i].copy(), bmax[i].copy()) for i in range(nc)]
+        o, fo = offs.tolist(), foffs.tolist()
+        return [Frontier(m, addr[o[i]:o[i + 1]], filt[fo[i]:fo[i + 1]], avg[i], bmin[i], bmax[i]) for i in range(nc)]
 
     # ---- the step after the search -------------------------------------
     def sampleViewpointsRaw(self, ftrs):
