@@ -291,11 +291,15 @@ class GpuPlanner:
             out = self.ff.search_box_end()
         m.updateESDF3d()
         m.download(wait=not self.overlap)  # overlap: the D2H mirror copy runs beside the solver
-        x, f, ne = self.opt.optimizeBatch(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0,
-                                          out=self.opt_out)
         if self.overlap:
+            # solver enqueued; the frontier result is marshalled on the host while it runs
+            self.opt.optimizeBatchBegin(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0)
             out = self.ff.search_box_end()
+            x, f, ne = self.opt.optimizeBatchEnd(out=self.opt_out)
             m.synchronize()  # ESDF host mirror complete
+        else:
+            x, f, ne = self.opt.optimizeBatch(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0,
+                                              out=self.opt_out)
         self.last_neval = ne
         return out, f
 

@@ -115,6 +115,9 @@ SIGNATURES = {
                                                  _vp, _vp, _vp]),
     "fuelgpu_bspline_optimize_batch": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp,
                                                  C.POINTER(FuelSolveParams), _vp, _vp, _vp]),
+    "fuelgpu_bspline_optimize_batch_begin": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp,
+                                                       C.POINTER(FuelSolveParams), _vp]),
+    "fuelgpu_bspline_optimize_batch_end": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fuelgpu_bspline_optimize_batch_dev": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp,
                                                      C.POINTER(FuelSolveParams), _vp, _vp, _vp]),
     "fuelgpu_edt_xy_dev": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_int, _vp, _vp]),

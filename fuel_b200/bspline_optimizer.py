@@ -185,6 +185,29 @@ class BsplineOptimizer:
                                                    C.byref(sp), ptr(x), ptr(fb), ptr(ne)), h)
         return x, fb, ne
 
+    def optimizeBatchBegin(self, x, traj_consts, n_pts, cost_function, max_eval, lbfgs_m=6, xtol_rel=1e-5):
+        """First half of optimizeBatch: stage the inputs and enqueue the solver, return at once
+        (fuelgpu_bspline_optimize_batch_begin).  Collect with optimizeBatchEnd()."""
+        mask = int(cost_function)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.shape[1] != self.nvar(n_pts, mask):
+            raise ValueError("x must be [B, %d]" % self.nvar(n_pts, mask))
+        sp = FuelSolveParams()
+        sp.max_eval, sp.lbfgs_m, sp.xtol_rel = int(max_eval), int(lbfgs_m), float(xtol_rel)
+        h = self.edt_environment_.sdf_map_.handle
+        check(lib().fuelgpu_bspline_optimize_batch_begin(h, x.shape[0], n_pts, mask, C.byref(self.params_), traj_consts,
+                                                         C.byref(sp), ptr(x)), h)
+        self._pending_shape = x.shape
+
+    def optimizeBatchEnd(self, out=None):
+        """Second half: wait for the solver and return (x_best, f_best, n_eval)."""
+        B, nvar = self._pending_shape
+        if out is None:
+            out = (np.empty((B, nvar), dtype=np.float64), np.empty(B, dtype=np.float64), np.empty(B, dtype=np.int32))
+        h = self.edt_environment_.sdf_map_.handle
+        check(lib().fuelgpu_bspline_optimize_batch_end(h, ptr(out[0]), ptr(out[1]), ptr(out[2])), h)
+        return out
+
     def _own_traj_const(self, ctrl, dt):
         tc = (FuelTrajConst * 1)()
         start = np.zeros((3, 3))

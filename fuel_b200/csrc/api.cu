@@ -714,14 +714,13 @@ int fuelgpu_bspline_optimize_batch_dev(FuelMap* m, int32_t B, int32_t n_pts, int
   return rc;
 }
 
-int fuelgpu_bspline_optimize_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
-                                   const FuelOptParams* p, const FuelTrajConst* traj,
-                                   const FuelSolveParams* solve, double* x, double* f_best,
-                                   int32_t* n_eval) {
+int fuelgpu_bspline_optimize_batch_begin(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask, const FuelOptParams* p,
+                                         const FuelTrajConst* traj, const FuelSolveParams* solve, const double* x) {
   int rc = check_bspline_args(m, B, n_pts, mask, p);
   if (rc) return rc;
+  if (m->bs_pend_B) return fuel_fail(m, FUELGPU_EINVAL, "an optimize_batch_begin is already outstanding");
   if (B == 0) return 0;
-  if (!traj || !x || !f_best || !n_eval || !solve) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (!traj || !x || !solve) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   if (solve->lbfgs_m < 1 || solve->lbfgs_m > 8 || solve->max_eval < 1)
     return fuel_fail(m, FUELGPU_EINVAL, "bad solver parameters");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
@@ -740,6 +739,7 @@ int fuelgpu_bspline_optimize_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t
   double* d_f = d_x + (size_t)B * nvar;
   int32_t* d_n = (int32_t*)(d_f + B);
   uint8_t* d_pack = (uint8_t*)(((uintptr_t)(d_n + B) + 63) & ~(uintptr_t)63);
+  // host buffers of unknown provenance (pageable or pinned) bounce through the page-locked area
   uint8_t* pin = (uint8_t*)m->bs_pin;
   double* h_x = (double*)(pin + packb);  // x, f_best, n_eval adjacent on both sides: one DMA back
   FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack));
@@ -750,11 +750,36 @@ int fuelgpu_bspline_optimize_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t
   tend(m, T_BSPLINE);
   if (rc) return rc;
   FUEL_CUDA(m, cudaMemcpyAsync(h_x, d_x, xb + fb + nb, cudaMemcpyDeviceToHost, m->stream));
-  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
-  memcpy(x, h_x, xb);
-  memcpy(f_best, (uint8_t*)h_x + xb, fb);
-  memcpy(n_eval, (uint8_t*)h_x + xb + fb, nb);
+  m->bs_pend_B = B;
+  m->bs_pend_nvar = nvar;
+  m->bs_pend_off = packb;
   return 0;
+}
+
+int fuelgpu_bspline_optimize_batch_end(FuelMap* m, double* x, double* f_best, int32_t* n_eval) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  if (!m->bs_pend_B) return 0;
+  if (!x || !f_best || !n_eval) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  const int B = m->bs_pend_B;
+  const size_t xb = sizeof(double) * (size_t)B * m->bs_pend_nvar, fb = sizeof(double) * (size_t)B, nb = sizeof(int32_t) * (size_t)B;
+  m->bs_pend_B = 0;
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  const uint8_t* h = (const uint8_t*)m->bs_pin + m->bs_pend_off;
+  memcpy(x, h, xb);
+  memcpy(f_best, h + xb, fb);
+  memcpy(n_eval, h + xb + fb, nb);
+  return 0;
+}
+
+int fuelgpu_bspline_optimize_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
+                                   const FuelOptParams* p, const FuelTrajConst* traj,
+                                   const FuelSolveParams* solve, double* x, double* f_best,
+                                   int32_t* n_eval) {
+  if (B > 0 && (!x || !f_best || !n_eval)) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  int rc = fuelgpu_bspline_optimize_batch_begin(m, B, n_pts, mask, p, traj, solve, x);
+  if (rc) return rc;
+  return fuelgpu_bspline_optimize_batch_end(m, x, f_best, n_eval);
 }
 
 int fuelgpu_edt_xy_dev(void* cuda_stream, const void* occ_slab, int32_t nx, int32_t ny, int32_t nzl,

@@ -58,6 +58,8 @@ struct FuelMap {
   size_t bs_bytes;
   void* bs_pin;  // page-locked bounce buffer for the host-facing B-spline calls
   size_t bs_pin_bytes;
+  int bs_pend_B, bs_pend_nvar;  // optimize_batch_begin issued, _end outstanding (B == 0: none)
+  size_t bs_pend_off;           // offset of the result block inside bs_pin
   long long launches;  // kernels launched so far
   char err[512];
 };

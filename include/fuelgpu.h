@@ -316,6 +316,13 @@ FUELGPU_API int fuelgpu_bspline_optimize_batch(FuelMap* map, int32_t B, int32_t 
                                    int32_t* n_eval);
 
 /* Same, all pointers in device memory. */
+/* The same in two halves, so the caller can do other host work (e.g. fuelgpu_frontier_search_end + fetch) while
+ * the solver runs: _begin stages the inputs and enqueues everything, _end waits and copies x / f_best / n_eval
+ * out.  One outstanding call per map; other work on the map's main stream queues behind the solver. */
+FUELGPU_API int fuelgpu_bspline_optimize_batch_begin(FuelMap* map, int32_t B, int32_t n_pts, int32_t cost_mask,
+                                                     const FuelOptParams* p, const FuelTrajConst* traj,
+                                                     const FuelSolveParams* solve, const double* x);
+FUELGPU_API int fuelgpu_bspline_optimize_batch_end(FuelMap* map, double* x, double* f_best, int32_t* n_eval);
 FUELGPU_API int fuelgpu_bspline_optimize_batch_dev(FuelMap* map, int32_t B, int32_t n_pts, int32_t cost_mask,
                                        const FuelOptParams* params, const void* traj_dev,
                                        const FuelSolveParams* solve, void* x_dev, void* f_best_dev,

@@ -219,3 +219,23 @@ def test_optimize_single_and_small_budget(fuel, orc, scene):
     xg, fg, ng = opt.optimizeBatch(x0, gpu_consts(fuel, tr, 2), 20, O.NORMAL_PHASE | O.MINTIME, 1)
     assert np.all(ng == 1)
     assert np.allclose(xg, x0)  # the workload's control points are already inside the shrunk box
+
+
+def test_optimize_begin_end_equals_one_shot(fuel, orc, scene):
+    """fuelgpu_bspline_optimize_batch_begin/_end is the one-shot call cut in two: same bits out, the input x untouched,
+    a second begin before the end is refused."""
+    B, N, K = 64, 20, 32
+    O = fuel.BsplineOptimizer
+    tr = W.make_trajectories(scene["g"], scene["inflate"], B=B, n_pts=N, seed=5)
+    mask = O.NORMAL_PHASE | O.MINTIME
+    x0 = W.pack_x(tr["ctrl"], tr["dt"])
+    keep = x0.copy()
+    tc = gpu_consts(fuel, tr, B)
+    opt = scene["opt"]
+    x1, f1, n1 = opt.optimizeBatch(x0, tc, N, mask, K)
+    opt.optimizeBatchBegin(x0, tc, N, mask, K)
+    with pytest.raises(fuel.FuelGpuError):
+        opt.optimizeBatchBegin(x0, tc, N, mask, K)
+    x2, f2, n2 = opt.optimizeBatchEnd()
+    assert np.array_equal(x0, keep)
+    assert np.array_equal(x1, x2) and np.array_equal(f1, f2) and np.array_equal(n1, n2)
