@@ -349,6 +349,69 @@ def esdf512_roofline(dev, peak, peak_src, variant="V1", reps=5):
                                                                   else "V0 (file as is, mostly empty cube)")}
 
 
+def next_rows_timing(dev):
+    """SURVEY 8f rows built on top of the hot path, timed beside it (not part of the metric): one fused depth
+    frame (proessDepthImage + inputPointCloud), clearAndInflateLocalMap, and sampleViewpoints for the clusters of
+    the office replan -- wall time per call through the host API, and the oracle's single-thread time."""
+    import fuel_b200
+    import oracle
+    from fuel_b200 import workloads as W
+    g, inflate = W.office_map()
+    tri = W.office_known(g, inflate)
+    og = oracle.make_grid(g.n, g.res, g.origin, g.box_min, g.box_max)
+    out = {}
+    m = fuel_b200.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max, device=dev)
+    m.setFusionParams()
+    frames = []
+    for i in range(4):
+        cam = np.array([0.25 * i, 0.1 * i, 1.0])
+        img, R = W.depth_image(g, inflate, cam, 0.8 * i)
+        m.pin(img)
+        frames.append((img, R, cam))
+    for img, R, cam in frames:
+        m.inputDepthImage(img, R, cam)
+    m.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        for img, R, cam in frames:
+            m.inputDepthImage(img, R, cam)
+    m.synchronize()
+    out["fusion_depth_frame_ms"] = 1e3 * (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(10):
+        m.clearAndInflateLocalMap()
+    m.synchronize()
+    out["inflate_local_map_ms"] = 1e3 * (time.perf_counter() - t0) / 10
+    fus = oracle.Fusion(og, oracle.fusion_params())
+    cp = oracle.camera_params()
+    t0 = time.perf_counter()
+    for img, R, cam in frames:
+        fus.input_point_cloud(oracle.process_depth_image(cp, img, R, cam), cam)
+    out["cpu_fusion_depth_frame_ms"] = 1e3 * (time.perf_counter() - t0) / len(frames)
+    m.close()
+    m = fuel_b200.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max, optimistic=True, device=dev)
+    m.occupancy_buffer_inflate_[...] = inflate
+    m.setOccupancyBuffer(tristate=tri)
+    m.upload()
+    env = fuel_b200.EDTEnvironment()
+    env.setMap(m)
+    ff = fuel_b200.FrontierFinder(env)
+    ftrs = ff.search_box(g.origin, g.map_max)
+    ff.sampleViewpointsRaw(ftrs)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ff.sampleViewpointsRaw(ftrs)
+    out["sample_viewpoints_ms"] = 1e3 * (time.perf_counter() - t0) / 10
+    vp = oracle.view_params()
+    t0 = time.perf_counter()
+    for f in ftrs:
+        oracle.sample_viewpoints(og, tri, inflate, vp, f.average_, f.filtered_cells_)
+    out["cpu_sample_viewpoints_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["n_clusters"] = len(ftrs)
+    m.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -456,6 +519,11 @@ def run_ours(args):
             extra["roofline_esdf512_v0"] = esdf512_roofline(local, peak, peak_src, "V0")
         except Exception as e:  # noqa: BLE001
             extra["roofline_esdf512"] = {"error": repr(e)}
+
+        try:
+            extra["next_rows"] = next_rows_timing(local)
+        except Exception as e:  # noqa: BLE001
+            extra["next_rows"] = {"error": repr(e)}
 
     # ---- CPU baseline: the oracle, 1 thread (faithful to the single-threaded reference) ----
     S = cpu_replan_setup(args.batch)
