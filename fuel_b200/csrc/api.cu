@@ -208,7 +208,7 @@ int fuelgpu_map_destroy(FuelMap* m) {
   frontier_state_destroy(m);
   fusion_state_destroy(m);
   if (m->bs_pin) cudaFreeHost(m->bs_pin);
-  void* ptrs[] = { m->occ, m->dist, m->dist_neg, m->flag, m->g1, m->g2, m->stk, m->stage, m->bs_buf };
+  void* ptrs[] = { m->occ, m->dist, m->dist_neg, m->flag, m->g1, m->g2, m->stk, m->stage, m->bs_buf, m->fr_scr };
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int t = 0; t < T_COUNT; ++t) {

@@ -58,6 +58,8 @@ struct FuelMap {
   size_t bs_bytes;
   void* bs_pin;  // page-locked bounce buffer for the host-facing B-spline calls
   size_t bs_pin_bytes;
+  void* fr_scr;  // device scratch of the small frontier-side calls (is_changed, viewpoints), grown on demand
+  size_t fr_scr_bytes;
   int bs_pend_B, bs_pend_nvar;  // optimize_batch_begin issued, _end outstanding (B == 0: none)
   size_t bs_pend_off;           // offset of the result block inside bs_pin
   long long launches;  // kernels launched so far
@@ -113,6 +115,7 @@ int fusion_get_logodds(FuelMap* m, double* out);
 void fusion_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int reset);
 void fusion_state_destroy(FuelMap* m);
 
+int ensure_fr_scratch(FuelMap* m, size_t bytes);
 int frontier_state_create(FuelMap* m);
 // The frontier subsystem runs on its own stream (it only reads `occ` and owns `flag`), so a host
 // thread can search frontiers while another updates the ESDF / runs the B-spline batch on the

@@ -1577,16 +1577,31 @@ int frontier_fetch_impl(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr, i
   return 0;
 }
 
+int ensure_fr_scratch(FuelMap* m, size_t bytes) {
+  if (bytes <= m->fr_scr_bytes) return 0;
+  if (m->fr_scr) {
+    cudaDeviceSynchronize();  // both streams may still use the old block
+    cudaFree(m->fr_scr);
+  }
+  m->fr_scr = nullptr;
+  m->fr_scr_bytes = 0;
+  const size_t want = bytes + bytes / 2 + 4096;
+  FUEL_CUDA(m, cudaMalloc(&m->fr_scr, want));
+  m->fr_scr_bytes = want;
+  return 0;
+}
+
 int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const int32_t* addr,
                              uint8_t* changed, int32_t* counts) {
   if (mcl <= 0) return 0;
   const int ncell = offs[mcl];
-  int *d_off = nullptr, *d_addr = nullptr, *d_cnt = nullptr;
-  uint8_t* d_ch = nullptr;
-  FUEL_CUDA(m, cudaMalloc(&d_off, sizeof(int) * (mcl + 1)));
-  FUEL_CUDA(m, cudaMalloc(&d_addr, sizeof(int) * (ncell > 0 ? ncell : 1)));
-  FUEL_CUDA(m, cudaMalloc(&d_ch, mcl));
-  FUEL_CUDA(m, cudaMalloc(&d_cnt, sizeof(int) * mcl));
+  const size_t nci = (size_t)(ncell > 0 ? ncell : 1);
+  int rc = ensure_fr_scratch(m, sizeof(int) * ((size_t)2 * mcl + 1 + nci) + mcl + 16);
+  if (rc) return rc;
+  int* d_off = (int*)m->fr_scr;
+  int* d_addr = d_off + mcl + 1;
+  int* d_cnt = d_addr + nci;
+  uint8_t* d_ch = (uint8_t*)(d_cnt + mcl);
   cudaStream_t s = m->fs->stream;
   FUEL_CUDA(m, cudaMemcpyAsync(d_off, offs, sizeof(int) * (mcl + 1), cudaMemcpyHostToDevice, s));
   if (ncell > 0) FUEL_CUDA(m, cudaMemcpyAsync(d_addr, addr, sizeof(int) * ncell, cudaMemcpyHostToDevice, s));
@@ -1595,10 +1610,6 @@ int frontier_is_changed_impl(FuelMap* m, int32_t mcl, const int32_t* offs, const
   if (changed) FUEL_CUDA(m, cudaMemcpyAsync(changed, d_ch, mcl, cudaMemcpyDeviceToHost, s));
   if (counts) FUEL_CUDA(m, cudaMemcpyAsync(counts, d_cnt, sizeof(int) * mcl, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
-  cudaFree(d_off);
-  cudaFree(d_addr);
-  cudaFree(d_ch);
-  cudaFree(d_cnt);
   return 0;
 }
 

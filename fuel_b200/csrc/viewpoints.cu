@@ -247,10 +247,11 @@ int sample_viewpoints_impl(FuelMap* m, int ncl, const int32_t* filt_off, const d
   // one staging allocation: [off 2nc][avg 3ncl][filt 3nfilt][pos 3n_out][yaw n_out] doubles, then ints
   const size_t nd = 2 * (size_t)nc + 3 * (size_t)ncl + 3 * (size_t)(nfilt > 0 ? nfilt : 1) + 4 * n_out;
   const size_t ni = (size_t)ncl + 1 + n_out;
-  double* d_d = nullptr;
-  int* d_i = nullptr;
-  FUEL_CUDA(m, cudaMallocAsync(&d_d, sizeof(double) * nd, s));
-  FUEL_CUDA(m, cudaMallocAsync(&d_i, sizeof(int) * ni, s));
+  const size_t dbytes = (sizeof(double) * nd + 255) & ~(size_t)255;
+  int rc = ensure_fr_scratch(m, dbytes + sizeof(int) * ni);
+  if (rc) return rc;
+  double* d_d = (double*)m->fr_scr;
+  int* d_i = (int*)((uint8_t*)m->fr_scr + dbytes);
   double *d_off = d_d, *d_avg = d_off + 2 * nc, *d_filt = d_avg + 3 * ncl, *d_pos = d_filt + 3 * (size_t)(nfilt > 0 ? nfilt : 1),
          *d_yaw = d_pos + 3 * n_out;
   int *d_fo = d_i, *d_vis = d_i + ncl + 1;
@@ -265,8 +266,6 @@ int sample_viewpoints_impl(FuelMap* m, int ncl, const int32_t* filt_off, const d
   FUEL_CUDA(m, cudaMemcpyAsync(cand_pos, d_pos, sizeof(double) * 3 * n_out, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaMemcpyAsync(cand_yaw, d_yaw, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaMemcpyAsync(cand_visib, d_vis, sizeof(int) * n_out, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaFreeAsync(d_d, s));
-  FUEL_CUDA(m, cudaFreeAsync(d_i, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
   return 0;
 }
