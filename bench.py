@@ -285,7 +285,7 @@ class GpuPlanner:
         and BsplineOptimizer::optimize()'s solver loop on the device (x and the trajectory constants
         H2D once, best x / cost / eval count D2H once)."""
         m = self.m
-        m.upload()
+        m.upload(wait=not self.overlap)  # overlap: the mirrors are not touched before the final synchronize()
         self._frontier_begin()
         if not self.overlap:
             out = self.ff.search_box_end()

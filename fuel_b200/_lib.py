@@ -82,6 +82,7 @@ SIGNATURES = {
     "fuelgpu_host_register": (C.c_int, [_vp, C.c_uint64]),
     "fuelgpu_host_unregister": (C.c_int, [_vp]),
     "fuelgpu_map_upload_occupancy": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp]),
+    "fuelgpu_map_upload_occupancy_async": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp]),
     "fuelgpu_map_inflate": (C.c_int, [_vp, _vp, _vp, _i32, _i32]),
     "fuelgpu_map_download_occupancy": (C.c_int, [_vp, _vp, _vp]),
     "fuelgpu_map_input_point_cloud": (C.c_int, [_vp, _vp, _i32, _i32, _vp, C.POINTER(FuelFusionParams), _vp, _vp]),

@@ -280,10 +280,9 @@ int fuelgpu_host_unregister(void* ptr) {
   return 0;
 }
 
-int fuelgpu_map_upload_occupancy(FuelMap* m, const int8_t* inflate, const double* logodds,
-                                 const uint8_t* tristate, double clamp_min_log,
-                                 double min_occupancy_log, const int32_t bmin[3],
-                                 const int32_t bmax[3]) {
+static int upload_occupancy_impl(FuelMap* m, const int8_t* inflate, const double* logodds, const uint8_t* tristate,
+                                 double clamp_min_log, double min_occupancy_log, const int32_t bmin[3],
+                                 const int32_t bmax[3], bool wait) {
   if (!m || !inflate) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   if ((logodds == nullptr) == (tristate == nullptr))
     return fuel_fail(m, FUELGPU_EINVAL, "give exactly one of logodds / tristate");
@@ -314,8 +313,20 @@ int fuelgpu_map_upload_occupancy(FuelMap* m, const int8_t* inflate, const double
   FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
   tend(m, T_UPLOAD);
-  FUEL_CUDA(m, cudaStreamSynchronize(m->stream));  // host buffers may be reused by the caller
+  if (wait) FUEL_CUDA(m, cudaStreamSynchronize(m->stream));  // host buffers may be reused by the caller
   return 0;
+}
+
+int fuelgpu_map_upload_occupancy(FuelMap* m, const int8_t* inflate, const double* logodds, const uint8_t* tristate,
+                                 double clamp_min_log, double min_occupancy_log, const int32_t bmin[3],
+                                 const int32_t bmax[3]) {
+  return upload_occupancy_impl(m, inflate, logodds, tristate, clamp_min_log, min_occupancy_log, bmin, bmax, true);
+}
+
+int fuelgpu_map_upload_occupancy_async(FuelMap* m, const int8_t* inflate, const double* logodds, const uint8_t* tristate,
+                                       double clamp_min_log, double min_occupancy_log, const int32_t bmin[3],
+                                       const int32_t bmax[3]) {
+  return upload_occupancy_impl(m, inflate, logodds, tristate, clamp_min_log, min_occupancy_log, bmin, bmax, false);
 }
 
 __global__ void split_occ_kernel(const uint8_t* __restrict__ occ, int8_t* __restrict__ inf, uint8_t* __restrict__ tri,

@@ -282,19 +282,21 @@ class SDFMap:
             return -1
         return int(self.occupancy_buffer_inflate_[idx[0], idx[1], idx[2]])
 
-    def upload(self, bmin=None, bmax=None, logodds=None):
+    def upload(self, bmin=None, bmax=None, logodds=None, wait=True):
         """H2D of the occupancy state.  With `logodds` the device thresholds the fp64 buffer
-        itself (9 B/voxel ingest); otherwise the host tri-state byte is sent (2 B/voxel)."""
+        itself (9 B/voxel ingest); otherwise the host tri-state byte is sent (2 B/voxel).
+        wait=False queues the copies and returns: leave the mirrors alone until synchronize()."""
+        fn = lib().fuelgpu_map_upload_occupancy if wait else lib().fuelgpu_map_upload_occupancy_async
         bmin_a = None if bmin is None else np.ascontiguousarray(bmin, dtype=np.int32)
         bmax_a = None if bmax is None else np.ascontiguousarray(bmax, dtype=np.int32)
         inf = np.ascontiguousarray(self.occupancy_buffer_inflate_)
         if logodds is not None:
             lo = np.ascontiguousarray(logodds, dtype=np.float64)
-            check(lib().fuelgpu_map_upload_occupancy(self._h, ptr(inf), ptr(lo), None, self.clamp_min_log_,
+            check(fn(self._h, ptr(inf), ptr(lo), None, self.clamp_min_log_,
                                                      self.min_occupancy_log_, ptr(bmin_a), ptr(bmax_a)), self._h)
         else:
             tri = np.ascontiguousarray(self.occupancy_tri_)
-            check(lib().fuelgpu_map_upload_occupancy(self._h, ptr(inf), None, ptr(tri), self.clamp_min_log_,
+            check(fn(self._h, ptr(inf), None, ptr(tri), self.clamp_min_log_,
                                                      self.min_occupancy_log_, ptr(bmin_a), ptr(bmax_a)), self._h)
 
     def clearAndInflateLocalMap(self, obstacles_inflation=0.199, virtual_ceil_height=-10.0):

@@ -96,6 +96,12 @@ FUELGPU_API int fuelgpu_map_upload_occupancy(FuelMap* map, const int8_t* inflate
                                  const uint8_t* tristate, double clamp_min_log,
                                  double min_occupancy_log, const int32_t bmin[3],
                                  const int32_t bmax[3]);
+/* Same, but returns as soon as the copies are queued: the caller must leave the host buffers alone until the
+ * next fuelgpu_map_synchronize / blocking call on this map (page-locked buffers are read by DMA later). */
+FUELGPU_API int fuelgpu_map_upload_occupancy_async(FuelMap* map, const int8_t* inflate, const double* logodds,
+                                                   const uint8_t* tristate, double clamp_min_log,
+                                                   double min_occupancy_log, const int32_t bmin[3],
+                                                   const int32_t bmax[3]);
 
 /* Replaces SDFMap::clearAndInflateLocalMap (plan_env/src/sdf_map.cpp:364-472), the step between the
  * occupancy fusion and updateESDF3d, on the resident occupancy byte: the inflate bit
