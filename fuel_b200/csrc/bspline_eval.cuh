@@ -247,6 +247,33 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
     if (opt_time && !FAST) gdt += p.ld_feasi * gt;
   }
   if (mask & FUELGPU_START) {  // calcStartCost :355-391
+    if (FAST) {
+      // same terms with the three rows written as per-lane coefficients (0 beyond lane 2) instead of 27 predicated updates
+      double a[3], b[3], c3[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        a[k] = __shfl_sync(0xffffffffu, q[k], 0);
+        b[k] = __shfl_sync(0xffffffffu, q[k], 1);
+        c3[k] = __shfl_sync(0xffffffffu, q[k], 2);
+      }
+      const double w_pos = 10.0;
+      const double cp = lane == 1 ? 4 / 6.0 : (lane == 0 || lane == 2 ? 1 / 6.0 : 0.0);
+      const double cv = lane == 0 ? -inv2dt : (lane == 2 ? inv2dt : 0.0);
+      const double ca = lane == 1 ? -2.0 * invdt2 : (lane == 0 || lane == 2 ? invdt2 : 0.0);
+      double cost = 0.0, gt = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double dv = c3[k] - a[k], da = a[k] - 2 * b[k] + c3[k];
+        const double dqp = 1 / 6.0 * (a[k] + 4 * b[k] + c3[k]) - t.start[0][k];
+        const double dqv = inv2dt * dv - t.start[1][k];
+        const double dqa = invdt2 * da - t.start[2][k];
+        cost += w_pos * dqp * dqp + dqv * dqv + dqa * dqa;
+        gr[k] += p.ld_start * 2.0 * (w_pos * dqp * cp + dqv * cv + dqa * ca);
+        gt -= dqv * dv * invdt2 + dqa * da * invdt2 * dt_inv_f;
+      }
+      f += p.ld_start * cost;
+      if (opt_time) gdt += p.ld_start * gt;
+    } else {
     double a[3], b[3], c3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -301,8 +328,35 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
       for (int k = 0; k < 3; ++k) gr[k] += p.ld_start * row[k];
     }
     if (opt_time) gdt += p.ld_start * gt;
+      }
   }
   if (mask & FUELGPU_END) {  // calcEndCost :393-431
+    if (FAST) {
+      double q_3[3], q_2[3], q_1[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        q_3[k] = __shfl_sync(0xffffffffu, q[k], n - 3);
+        q_2[k] = __shfl_sync(0xffffffffu, q[k], n - 2);
+        q_1[k] = __shfl_sync(0xffffffffu, q[k], n - 1);
+      }
+      const bool e2 = t.n_end >= 2, e3 = t.n_end == 3;
+      const double cp = lane == n - 2 ? 4 / 6.0 : (lane == n - 1 || lane == n - 3 ? 1 / 6.0 : 0.0);
+      const double cv = !e2 ? 0.0 : (lane == n - 1 ? inv2dt : (lane == n - 3 ? -inv2dt : 0.0));
+      const double ca = !e3 ? 0.0 : (lane == n - 2 ? -2.0 * invdt2 : (lane == n - 1 || lane == n - 3 ? invdt2 : 0.0));
+      double cost = 0.0, gt = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double dv = q_1[k] - q_3[k], da = q_1[k] - 2 * q_2[k] + q_3[k];
+        const double dqp = 1 / 6.0 * (q_1[k] + 4 * q_2[k] + q_3[k]) - t.end[0][k];
+        const double dqv = e2 ? inv2dt * dv - t.end[1][k] : 0.0;
+        const double dqa = e3 ? invdt2 * da - t.end[2][k] : 0.0;
+        cost += dqp * dqp + dqv * dqv + dqa * dqa;
+        gr[k] += p.ld_end * 2.0 * (dqp * cp + dqv * cv + dqa * ca);
+        gt -= dqv * dv * invdt2 + dqa * da * invdt2 * dt_inv_f;
+      }
+      f += p.ld_end * cost;
+      if (opt_time) gdt += p.ld_end * gt;
+    } else {
     double q_3[3], q_2[3], q_1[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -360,6 +414,7 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
       for (int k = 0; k < 3; ++k) gr[k] += p.ld_end * row[k];
     }
     if (opt_time) gdt += p.ld_end * gt;
+      }
   }
   if (mask & FUELGPU_GUIDE) {  // calcGuideCost :462-475
     double c = 0.0, gq[3] = { 0.0, 0.0, 0.0 };

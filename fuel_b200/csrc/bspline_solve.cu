@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
   if (!(best == best)) best = 1.7976931348623157e308;
 
   int cnt = 0, head = 0;  // history ring: newest at (head-1) mod m
+  double gamma_new = 1.0;
   double rho[MAXM];  // rho[j] belongs to the j-th newest pair (static indices: stays in registers)
 #pragma unroll
   for (int j = 0; j < MAXM; ++j) rho[j] = 0.0;
@@ -140,17 +141,9 @@ __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
         for (int k = 0; k < 3; ++k) Q.v[k] -= alpha[j] * y.v[k];
       }
     }
-    if (cnt > 0) {
-      const int slot = head == 0 ? m - 1 : head - 1;
-      V3 s, y;
+    if (cnt > 0) {  // gamma = s.y / y.y of the newest pair, kept from the moment it was stored
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        s.v[k] = S[HIDX(slot, k)];
-        y.v[k] = Y[HIDX(slot, k)];
-      }
-      const double gamma = dot3(s, y) / dot3(y, y);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) Q.v[k] *= gamma;
+      for (int k = 0; k < 3; ++k) Q.v[k] *= gamma_new;
     }
 #pragma unroll
     for (int j = MAXM - 1; j >= 0; --j) {
@@ -184,18 +177,26 @@ __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
     V3 XN, GN;
     double FN = 0.0;
     while (neval < sp.max_eval) {
+      bool clipped = false;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) XN.v[k] = fmax(fmin(X.v[k] + step * D.v[k], ub.v[k]), lb.v[k]);
+      for (int k = 0; k < 3; ++k) {
+        const double xt = X.v[k] + step * D.v[k];
+        clipped = clipped || xt > ub.v[k] || xt < lb.v[k];
+        XN.v[k] = fmax(fmin(xt, ub.v[k]), lb.v[k]);
+      }
       evaluate(XN, FN, GN);
       ++neval;
       if (FN < best) {  // costFunction :698-704
         best = FN;
         store_best(XN, FN);
       }
-      V3 dx;
+      double dec = step * gd;  // = G.(XN - X) as long as no component hit a bound
+      if (__any_sync(0xffffffffu, clipped)) {
+        V3 dx;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) dx.v[k] = XN.v[k] - X.v[k];
-      const double dec = dot3(G, dx);
+        for (int k = 0; k < 3; ++k) dx.v[k] = XN.v[k] - X.v[k];
+        dec = dot3(G, dx);
+      }
       if (FN <= F + 1e-4 * dec) {
         accepted = true;
         break;
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(WPB * 32) optimize_warp_kernel(
 #pragma unroll
       for (int j = MAXM - 1; j > 0; --j) rho[j] = rho[j - 1];
       rho[0] = 1.0 / sy;
+      gamma_new = sy / yy;
       head = head + 1 == m ? 0 : head + 1;
       if (cnt < m) ++cnt;
     }
