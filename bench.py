@@ -342,7 +342,9 @@ def esdf512_roofline(dev, peak, peak_src, variant="V1", reps=5):
     alg = 5.0 * g.nvox
     ach = alg / t / 1e9
     return {"kernel": "esdf_update 512^3 (zsweep_vec_kernel + envelope_kernel y + envelope_kernel x)", "bound": "hbm",
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            # DRAM read+write of the three sweeps per update, ncu --set full (profiles/r01_esdf512_ncu_full.txt)
+            "traffic": 2.516e9 if variant == "V1" else None,
             "algorithmic_bytes": alg, "ms": 1e3 * t, "peak_source": peak_src,
             "workload": "pillar.pcd %s on 512^3 @0.1m, optimistic, full rebuild (box = whole map); "
                         "L2 flushed before every timed update" % ("V1 (tiled to fill the cube)" if variant == "V1"
@@ -510,8 +512,11 @@ def run_ours(args):
     roofline = {"kernel": {"esdf": "esdf_update (3 sweeps)", "frontier": "frontier_search (sweep + clustering)",
                            "bspline": "optimize_warp_kernel (K evaluations of the batch in one launch)"}[dom],
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "algorithmic_bytes": alg[dom], "peak_source": peak_src,
-                "note": "dominant stage of the office replan; the map (10 MB) is L2-resident by nature"}
+                # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_office_kernels_ncu_full.txt)
+                "traffic": {"bspline": 3.78e6, "frontier": 1.43e6}.get(dom), "algorithmic_bytes": alg[dom],
+                "peak_source": peak_src,
+                "note": "dominant stage of the office replan: latency-bound (1 warp per trajectory, 7 warps per SM), the "
+                        "3.8 MB map is L2-resident, so the HBM fraction is reported for completeness only"}
     extra = {}
     if not args.no_esdf512 and world == 1:
         try:
