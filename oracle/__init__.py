@@ -26,8 +26,10 @@ GUIDE_PHASE = SMOOTHNESS | GUIDE | START | END
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc -O3, the reference's flags)."""
     src = [os.path.join(_HERE, f) for f in ("fuel_oracle.c", "fuel_oracle_fusion.c", "fuel_oracle_viewpoints.c",
-                                            "fuel_oracle.h", "Makefile")]
-    if (not force and os.path.exists(_SO)
+                                            "fuel_oracle.h", "Makefile", "ref_raycast_wrap.cpp", "ref_sdfmap_wrap.cpp")]
+    ref_src = "/root/reference/fuel_planner/plan_env/src/raycast.cpp"
+    ref_ok = not os.path.exists(ref_src) or os.path.exists(os.path.join(_HERE, "_ref", "libfuel_ref.so"))
+    if (not force and os.path.exists(_SO) and ref_ok
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src)):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-s"])
@@ -277,6 +279,111 @@ def frontier_changed_count(g, tri, addr):
     lib().orc_frontier_changed_count.restype = C.c_int32
     return lib().orc_frontier_changed_count(C.byref(g), _p(np.ascontiguousarray(tri, dtype=np.uint8)), _p(addr),
                                             C.c_int32(addr.shape[0]))
+
+
+def raycast_ids(g, start, end, max_ids=8192):
+    """the oracle's RayCaster: voxel indices nextId() reports for input(start, end)"""
+    out = np.zeros((max_ids, 3), np.int32)
+    lib().orc_raycast_ids.restype = C.c_int32
+    n = lib().orc_raycast_ids(C.byref(g), _p(np.ascontiguousarray(start, dtype=np.float64)),
+                              _p(np.ascontiguousarray(end, dtype=np.float64)), _p(out), C.c_int32(max_ids))
+    return out[:n]
+
+
+_REF_RAYCAST = os.path.join(_HERE, "_ref", "libfuel_ref.so")
+_ref_rc = None
+
+
+def ref_raycast():
+    """The REFERENCE's own code (plan_env/src/raycast.cpp + sdf_map.cpp compiled unmodified into
+    oracle/_ref/libfuel_ref.so by the Makefile, only where /root/reference exists) or None."""
+    global _ref_rc
+    if _ref_rc is None and os.path.exists(_REF_RAYCAST):
+        _ref_rc = C.CDLL(_REF_RAYCAST)
+        _ref_rc.ref_raycast_ids.restype = C.c_int32
+        _ref_rc.ref_intbound.restype = C.c_double
+        _ref_rc.ref_intbound.argtypes = [C.c_double, C.c_double]
+    return _ref_rc
+
+
+def ref_raycast_ids(g, start, end, max_ids=8192):
+    out = np.zeros((max_ids, 3), np.int32)
+    origin = np.array([g.origin[0], g.origin[1], g.origin[2]], dtype=np.float64)
+    n = ref_raycast().ref_raycast_ids(C.c_double(g.res), _p(origin), _p(np.ascontiguousarray(start, dtype=np.float64)),
+                                      _p(np.ascontiguousarray(end, dtype=np.float64)), _p(out), C.c_int32(max_ids))
+    return out[:n]
+
+
+class RefSDFMap:
+    """The reference's SDFMap object (sdf_map.cpp compiled from /root/reference), driven through
+    oracle/ref_sdfmap_wrap.cpp.  params = the sdf_map/* ROS parameters without the prefix.  The map is centred in
+    x,y: origin = (-size_x/2, -size_y/2, ground_height) (sdf_map.cpp:33)."""
+
+    def __init__(self, **params):
+        R = ref_raycast()
+        keys = [("sdf_map/" + k).encode() for k in params]
+        karr = (C.c_char_p * len(keys))(*keys)
+        vals = np.array([float(v) for v in params.values()], dtype=np.float64)
+        R.ref_map_create.restype = C.c_void_p
+        for fn in ("ref_map_occupancy", "ref_map_inflate", "ref_map_distance"):
+            getattr(R, fn).restype = C.c_void_p
+        R.ref_map_dist_with_grad.restype = C.c_double
+        self.R = R
+        self.h = C.c_void_p(R.ref_map_create(C.c_int32(len(keys)), karr, _p(vals)))
+        n = np.zeros(3, np.int32)
+        o = np.zeros(3)
+        res = C.c_double()
+        R.ref_map_geometry(self.h, _p(n), _p(o), C.byref(res))
+        self.n, self.origin, self.res = tuple(int(v) for v in n), o, res.value
+        nv = int(np.prod(n))
+        self.occupancy = np.ctypeslib.as_array(C.cast(R.ref_map_occupancy(self.h), C.POINTER(C.c_double)), (nv,))
+        self.inflate = np.ctypeslib.as_array(C.cast(R.ref_map_inflate(self.h), C.POINTER(C.c_int8)), (nv,))
+        self.distance = np.ctypeslib.as_array(C.cast(R.ref_map_distance(self.h), C.POINTER(C.c_double)), (nv,))
+
+    def close(self):
+        if self.h:
+            self.occupancy = self.inflate = self.distance = None
+            self.R.ref_map_destroy(self.h)
+            self.h = None
+
+    def grid(self, box_mind=None, box_maxd=None):
+        return make_grid(self.n, self.res, self.origin, box_mind, box_maxd)
+
+    def set_local_bound(self, lo, hi):
+        self.R.ref_map_set_local_bound(self.h, _p(np.ascontiguousarray(lo, dtype=np.int32)),
+                                       _p(np.ascontiguousarray(hi, dtype=np.int32)))
+
+    def get_local_bound(self):
+        lo, hi = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        self.R.ref_map_get_local_bound(self.h, _p(lo), _p(hi))
+        return lo, hi
+
+    def set_modes(self, optimistic, signed_dist):
+        self.R.ref_map_set_modes(self.h, C.c_int(int(optimistic)), C.c_int(int(signed_dist)))
+
+    def update_esdf3d(self):
+        self.R.ref_map_update_esdf3d(self.h)
+
+    def clear_and_inflate(self):
+        self.R.ref_map_clear_and_inflate(self.h)
+
+    def input_point_cloud(self, pts, cam):
+        pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+        self.R.ref_map_input_point_cloud(self.h, _p(pts), C.c_int32(pts.shape[0]),
+                                         _p(np.ascontiguousarray(cam, dtype=np.float64)))
+
+    def updated_box(self, reset=False):
+        a, b = np.zeros(3), np.zeros(3)
+        self.R.ref_map_get_updated_box(self.h, _p(a), _p(b), C.c_int(int(reset)))
+        return a, b
+
+    def dist_with_grad(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        d = np.zeros(pos.shape[0])
+        g = np.zeros((pos.shape[0], 3))
+        for i in range(pos.shape[0]):
+            d[i] = self.R.ref_map_dist_with_grad(self.h, _p(pos[i]), _p(g[i]))
+        return d, g
 
 
 def dist_with_grad(g, dist_buf, pos):

@@ -5,7 +5,9 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, and only as the checker / the timed CPU baseline.
  *
- * PARITY STATUS: "parity unpinned".  The reference (HKUST-Aerial-Robotics/FUEL @ 662dd23)
+ * PARITY STATUS: "parity unpinned", with one exception: the RayCaster restatement (fuel_oracle_fusion.c,
+ * fuel_oracle_viewpoints.c) is checked ray-for-ray against the reference's own plan_env/src/raycast.cpp,
+ * compiled unmodified into oracle/_ref/ (tests/test_oracle_refpin.py).  For everything else:  The reference (HKUST-Aerial-Robotics/FUEL @ 662dd23)
  * ships no golden vectors or unit tests for this path and cannot be
  * compiled here (needs ROS1, Eigen3, PCL, NLopt -- none installed, no network).  This
  * file follows the cited source lines statement by statement (same loop order, same
@@ -104,6 +106,9 @@ typedef struct {
 } OrcCameraParams;
 int32_t orc_process_depth_image(const OrcCameraParams* cp, const uint16_t* depth, int32_t rows, int32_t cols,
                                 const double R[9], const double camera_pos[3], float* points_out);
+
+int32_t orc_raycast_ids(const OrcGrid* g, const double start[3], const double end[3], int32_t* ids, int32_t max);
+double orc_intbound(double s, double ds);
 
 /* sdf_map.cpp:497-536 getDistWithGrad (via EDTEnvironment::evaluateEDTWithGrad,
  * edt_environment.cpp:78-87).  dist_buf = distance_buffer_. */

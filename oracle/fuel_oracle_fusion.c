@@ -278,3 +278,18 @@ int32_t orc_process_depth_image(const OrcCameraParams* cp, const uint16_t* depth
   }
   return cnt;
 }
+
+/* The RayCaster restatement on its own, for pinning against the reference's raycast.cpp (oracle/_ref): the voxel
+ * indices nextId() reports between input(start, end) and the first `false`. */
+int32_t orc_raycast_ids(const OrcGrid* g, const double start[3], const double end[3], int32_t* ids, int32_t max) {
+  RayCaster r;
+  rc_set_params(&r, g->res, g->origin);
+  rc_input(&r, start, end);
+  int32_t n = 0, idx[3];
+  while (n < max && rc_next_id(&r, idx)) {
+    ids[3 * n] = idx[0], ids[3 * n + 1] = idx[1], ids[3 * n + 2] = idx[2];
+    ++n;
+  }
+  return n;
+}
+double orc_intbound(double s, double ds) { return intbound(s, ds); }

@@ -1,0 +1,208 @@
+"""Pins the oracle's RayCaster restatement (oracle/fuel_oracle_fusion.c, used by the fusion and viewpoint oracles)
+against the REFERENCE's own plan_env/src/raycast.cpp, compiled unmodified into oracle/_ref/libref_raycast.so
+(oracle/Makefile; Eigen is absent from the image, its five 3-vector operations come from oracle/eigen_standin).
+Skipped where the reference library was not built (no /root/reference)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.skipif(O.ref_raycast() is None, reason="oracle/_ref/libref_raycast.so not built (no /root/reference)")
+
+
+def test_intbound_matches_reference():
+    rng = np.random.default_rng(0)
+    L = O.lib()
+    L.orc_intbound.restype = O.C.c_double
+    L.orc_intbound.argtypes = [O.C.c_double, O.C.c_double]
+    R = O.ref_raycast()
+    s = np.concatenate([rng.uniform(-300, 300, 4000), np.round(rng.uniform(-300, 300, 500)), [0.0, -0.0, 1e-17, -1e-17]])
+    ds = np.concatenate([rng.integers(-40, 41, 4000).astype(float), rng.integers(-40, 41, 504).astype(float)])
+    for a, b in zip(s, ds):
+        x, y = L.orc_intbound(a, b), R.ref_intbound(a, b)
+        assert (np.isnan(x) and np.isnan(y)) or x == y, (a, b, x, y)
+
+
+@pytest.mark.parametrize("origin,res", [((-10.0, -6.0, -1.0), 0.1), ((-25.6, -25.6, -1.0), 0.1), ((0.3, -2.7, 0.05), 0.15)])
+def test_ray_traversal_matches_reference(origin, res):
+    """Thousands of rays: random, axis-aligned, starting on voxel faces / corners, zero length, long diagonals."""
+    rng = np.random.default_rng(7)
+    g = O.make_grid((200, 120, 40), res, origin)
+    o = np.array(origin)
+    span = np.array([200, 120, 40]) * res
+    n_rays = 0
+    for k in range(3000):
+        a = o + rng.uniform(-0.1, 1.1, 3) * span
+        b = o + rng.uniform(-0.1, 1.1, 3) * span
+        if k % 5 == 1:
+            b[rng.integers(0, 3)] = a[rng.integers(0, 3)]          # shared coordinate values
+        if k % 7 == 2:
+            a = o + np.round((a - o) / res) * res                  # start on voxel faces / corners
+        if k % 11 == 3:
+            b = a.copy()                                           # zero-length ray
+        if k % 13 == 4:
+            b = a + np.array([rng.uniform(-4.5, 4.5), 0.0, 0.0])   # axis-aligned
+        if k % 17 == 5:
+            a, b = np.float32(a).astype(np.float64), np.float32(b).astype(np.float64)  # float32 points, like pcl
+        got, ref = O.raycast_ids(g, a, b), O.ref_raycast_ids(g, a, b)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (k, a, b)
+        n_rays += 1
+    assert n_rays == 3000
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SDFMap: the reference's own sdf_map.cpp (updateESDF3d / fillESDF, clearAndInflateLocalMap, inputPointCloud,
+# getDistWithGrad) vs the oracle restatement, bit for bit (both are fp64, no FMA contraction).
+# ---------------------------------------------------------------------------------------------------------
+from fuel_b200 import workloads as W  # noqa: E402
+
+BASE = dict(resolution=0.1, map_size_x=8.0, map_size_y=6.0, map_size_z=3.0, ground_height=-0.5, obstacles_inflation=0.199,
+            local_bound_inflate=0.5, local_map_margin=50, default_dist=0.0, optimistic=0, signed_dist=0, p_hit=0.65,
+            p_miss=0.35, p_min=0.12, p_max=0.90, p_occ=0.80, max_ray_length=4.5, virtual_ceil_height=-10.0)
+
+
+def logit(p):
+    return np.log(p / (1 - p))
+
+
+def random_state(ref, seed, p_site=0.02):
+    """random inflate bits + a blobby unknown region written straight into the reference's buffers"""
+    rng = np.random.default_rng(seed)
+    n = ref.n
+    inflate = (rng.random(n) < p_site).astype(np.int8)
+    tri = np.full(n, W.FREE, np.uint8)
+    X, Y, Z = np.meshgrid(*[np.arange(k) for k in n], indexing="ij")
+    for _ in range(5):
+        c = rng.uniform(0, 1, 3) * np.array(n)
+        r = rng.uniform(0.15, 0.4) * min(n)
+        tri[((X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2) < r * r] = W.UNKNOWN
+    tri[(inflate == 1) & (tri == W.FREE)] = W.OCCUPIED
+    lo = np.where(tri == W.UNKNOWN, logit(0.12) - 0.01, np.where(tri == W.OCCUPIED, logit(0.90), logit(0.12)))
+    ref.inflate[:] = inflate.reshape(-1)
+    ref.occupancy[:] = lo.reshape(-1)
+    return inflate, tri
+
+
+@pytest.mark.parametrize("optimistic,signed", [(1, 0), (0, 0), (1, 1), (0, 1)])
+def test_update_esdf3d_matches_reference(optimistic, signed):
+    ref = O.RefSDFMap(**BASE)
+    assert ref.n == (80, 60, 30)
+    g = ref.grid()
+    for seed, (lo, hi) in enumerate([((0, 0, 0), (79, 59, 29)), ((10, 5, 3), (60, 50, 25)), ((33, 20, 7), (33, 40, 7)),
+                                     ((0, 0, 0), (79, 0, 29))]):
+        inflate, tri = random_state(ref, seed)
+        ref.distance[:] = 0.0
+        ref.set_modes(optimistic, signed)
+        ref.set_local_bound(lo, hi)
+        ref.update_esdf3d()
+        want = ref.distance.reshape(ref.n).copy()
+        got = O.update_esdf3d(g, inflate, tri, lo, hi, optimistic, signed)
+        sl = tuple(slice(lo[i], hi[i] + 1) for i in range(3))
+        assert np.array_equal(got[sl], want[sl]), "seed %d: %d voxels differ" % (seed, int((got[sl] != want[sl]).sum()))
+    ref.close()
+
+
+def test_esdf_sentinel_when_the_box_has_no_site():
+    ref = O.RefSDFMap(**BASE)
+    ref.inflate[:] = 0
+    ref.occupancy[:] = logit(0.12)  # all free, no obstacle: every voxel keeps the DBL_MAX envelope
+    ref.set_modes(1, 0)
+    ref.set_local_bound((5, 5, 5), (20, 20, 20))
+    ref.update_esdf3d()
+    want = ref.distance.reshape(ref.n)[5:21, 5:21, 5:21]
+    got = O.update_esdf3d(ref.grid(), np.zeros(ref.n, np.int8), np.full(ref.n, W.FREE, np.uint8), (5, 5, 5), (20, 20, 20), 1, 0)
+    assert np.array_equal(got[5:21, 5:21, 5:21], want) and want.min() > 1e150
+    ref.close()
+
+
+@pytest.mark.parametrize("ceil_h", [-10.0, 1.5])
+def test_clear_and_inflate_matches_reference(ceil_h):
+    ref = O.RefSDFMap(**dict(BASE, virtual_ceil_height=ceil_h))
+    g = ref.grid()
+    for seed, (lo, hi) in enumerate([((0, 0, 0), (79, 59, 29)), ((12, 8, 2), (70, 50, 27)), ((0, 0, 0), (3, 59, 29))]):
+        inflate, tri = random_state(ref, 10 + seed, p_site=0.01)
+        stale = (np.random.default_rng(seed).random(ref.n) < 0.05).astype(np.int8)   # leftovers the call must clear in the box
+        ref.inflate[:] = stale.reshape(-1)
+        ref.set_local_bound(lo, hi)
+        ref.clear_and_inflate()
+        inf_o, tri_o = stale.copy(), tri.copy()
+        ceil_id = int(np.floor((ceil_h - ref.origin[2]) * 10.0)) if ceil_h > -0.5 else -1
+        O.clear_and_inflate(g, tri_o, inf_o, lo, hi, 2, ceil_id)
+        assert np.array_equal(inf_o.reshape(-1), ref.inflate), "seed %d" % seed
+        want_tri = O.tristate_from_logodds(ref.occupancy, logit(0.12), logit(0.80))
+        assert np.array_equal(tri_o.reshape(-1), want_tri)
+    ref.close()
+
+
+def test_input_point_cloud_matches_reference():
+    ref = O.RefSDFMap(**dict(BASE, max_ray_length=2.5))
+    f = O.Fusion(ref.grid(), O.fusion_params(max_ray_length=2.5))
+    assert np.array_equal(f.logodds, ref.occupancy)          # initMap fill, sdf_map.cpp:64
+    rng = np.random.default_rng(3)
+    for frame in range(6):
+        cam = np.array([rng.uniform(-3, 3), rng.uniform(-2, 2), rng.uniform(0.3, 2.0)])
+        pts = cam + rng.normal(size=(4000, 3)) * np.array([2.0, 2.0, 0.8])
+        pts[:60] = np.round(pts[:60])          # coordinates on voxel faces
+        pts[60:120] = pts[60]                  # many points in one voxel
+        pts[120:160] *= 6.0                    # far outside the map
+        pts = pts.astype(np.float32)
+        ref.input_point_cloud(pts, cam)
+        lo, hi = f.input_point_cloud(pts, cam)
+        assert np.array_equal(f.logodds, ref.occupancy), "frame %d: %d voxels differ" % (frame, int((f.logodds != ref.occupancy).sum()))
+        rlo, rhi = ref.get_local_bound()
+        assert np.array_equal(lo, rlo) and np.array_equal(hi, rhi)
+        if frame == 2:
+            a, b = ref.updated_box(reset=True)
+            c, d = f.updated_box(reset=True)
+            assert np.array_equal(a, c) and np.array_equal(b, d)
+    a, b = ref.updated_box()
+    c, d = f.updated_box()
+    assert np.array_equal(a, c) and np.array_equal(b, d)
+    ref.close()
+
+
+def test_depth_frames_then_inflate_then_esdf_chain_matches_reference():
+    """The MapROS::depthPoseCallback + updateESDFCallback chain on synthetic depth frames of a furnished room."""
+    ref = O.RefSDFMap(**BASE)
+    g = ref.grid()
+    rng = np.random.default_rng(5)
+    truth = np.zeros(ref.n, np.int8)
+    truth[:, :, :6] = 1                                   # floor slab
+    for _ in range(25):
+        c = (rng.uniform(0.1, 0.9, 3) * np.array(ref.n)).astype(int)
+        s = rng.integers(2, 8, 3)
+        truth[c[0]:c[0] + s[0], c[1]:c[1] + s[1], 6:6 + 3 * s[2]] = 1
+    wg = W.Grid(ref.n, tuple(ref.origin), ref.res)
+    f = O.Fusion(g, O.fusion_params())
+    inf_o = np.zeros(ref.n, np.int8)
+    for k, yaw in enumerate((0.0, 1.3, 2.9, 4.4)):
+        cam = np.array([0.3 * k - 0.4, 0.2 * k - 0.3, 1.0])
+        pts = W.depth_frame(wg, truth, cam, yaw)
+        ref.input_point_cloud(pts, cam)
+        f.input_point_cloud(pts, cam)
+        assert np.array_equal(f.logodds, ref.occupancy)
+        lo, hi = ref.get_local_bound()
+        ref.clear_and_inflate()
+        tri = f.tristate().reshape(ref.n).copy()
+        O.clear_and_inflate(g, tri, inf_o, lo, hi, 2, -1)
+        assert np.array_equal(inf_o.reshape(-1), ref.inflate)
+        ref.update_esdf3d()
+        got = O.update_esdf3d(g, inf_o, tri, lo, hi, 0, 0)
+        sl = tuple(slice(lo[i], hi[i] + 1) for i in range(3))
+        assert np.array_equal(got[sl], ref.distance.reshape(ref.n)[sl])
+    ref.close()
+
+
+def test_dist_with_grad_matches_reference():
+    ref = O.RefSDFMap(**BASE)
+    inflate, tri = random_state(ref, 42, p_site=0.03)
+    ref.set_modes(1, 0)
+    ref.set_local_bound((0, 0, 0), (79, 59, 29))
+    ref.update_esdf3d()
+    rng = np.random.default_rng(1)
+    pos = ref.origin + rng.uniform(-0.05, 1.05, (3000, 3)) * np.array(ref.n) * ref.res
+    pos[:50] = ref.origin + np.round(rng.uniform(0, 1, (50, 3)) * np.array(ref.n)) * ref.res   # on voxel faces
+    d_ref, g_ref = ref.dist_with_grad(pos)
+    d, gr = O.dist_with_grad(ref.grid(), ref.distance.copy(), pos)
+    assert np.array_equal(d, d_ref) and np.array_equal(gr, g_ref)
+    ref.close()
