@@ -26,7 +26,7 @@ GUIDE_PHASE = SMOOTHNESS | GUIDE | START | END
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc -O3, the reference's flags)."""
     src = [os.path.join(_HERE, f) for f in ("fuel_oracle.c", "fuel_oracle_fusion.c", "fuel_oracle_viewpoints.c",
-                                            "fuel_oracle.h", "Makefile", "ref_raycast_wrap.cpp", "ref_sdfmap_wrap.cpp")]
+                                            "fuel_oracle.h", "Makefile", "ref_raycast_wrap.cpp", "ref_sdfmap_wrap.cpp", "ref_bspline_wrap.cpp")]
     ref_src = "/root/reference/fuel_planner/plan_env/src/raycast.cpp"
     ref_ok = not os.path.exists(ref_src) or os.path.exists(os.path.join(_HERE, "_ref", "libfuel_ref.so"))
     if (not force and os.path.exists(_SO) and ref_ok
@@ -384,6 +384,50 @@ class RefSDFMap:
         for i in range(pos.shape[0]):
             d[i] = self.R.ref_map_dist_with_grad(self.h, _p(pos[i]), _p(g[i]))
         return d, g
+
+
+class RefBsplineOptimizer:
+    """The reference's BsplineOptimizer (bspline_optimizer.cpp compiled from /root/reference) on a RefSDFMap.
+    params = optimization/* ROS parameters without the prefix (+ bspline_degree)."""
+
+    def __init__(self, ref_map, **params):
+        self.R = ref_map.R
+        self.map = ref_map
+        keys = [(("manager/" if k == "bspline_degree" else "optimization/") + k).encode() for k in params]
+        karr = (C.c_char_p * len(keys))(*keys)
+        vals = np.array([float(v) for v in params.values()], dtype=np.float64)
+        self.R.ref_opt_create.restype = C.c_void_p
+        self.R.ref_opt_evaluate.restype = C.c_int32
+        self.h = C.c_void_p(self.R.ref_opt_create(ref_map.h, C.c_int32(len(keys)), karr, _p(vals)))
+
+    def close(self):
+        if self.h:
+            self.R.ref_opt_destroy(self.h)
+            self.h = None
+
+    def evaluate(self, ctrl, dt, cost_function, start, end, guide=None, waypts=None, waypt_idx=None, time_lb=-1.0,
+                 probes=None):
+        """optimize(points, dt, cost_function, 1, 1) with the NLopt stand-in -> dict(f [1+P], grad [1+P,nvar], x0, lb, ub):
+        the reference's objective at its own start point x0 and at the P probe points."""
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64).reshape(-1, 3)
+        n = ctrl.shape[0]
+        nvar = 3 * n + (1 if cost_function & MINTIME else 0)
+        start = np.ascontiguousarray(start, dtype=np.float64).reshape(-1, 3)
+        end = np.ascontiguousarray(end, dtype=np.float64).reshape(-1, 3)
+        guide = np.zeros((0, 3)) if guide is None else np.ascontiguousarray(guide, dtype=np.float64).reshape(-1, 3)
+        waypts = np.zeros((0, 3)) if waypts is None else np.ascontiguousarray(waypts, dtype=np.float64).reshape(-1, 3)
+        widx = np.zeros(0, np.int32) if waypt_idx is None else np.ascontiguousarray(waypt_idx, dtype=np.int32)
+        probes = np.zeros((0, nvar)) if probes is None else np.ascontiguousarray(probes, dtype=np.float64).reshape(-1, nvar)
+        P = probes.shape[0]
+        f = np.zeros(1 + P)
+        grad = np.zeros((1 + P, nvar))
+        x0, lb, ub = np.zeros(nvar), np.zeros(nvar), np.zeros(nvar)
+        rc = self.R.ref_opt_evaluate(self.h, C.c_int32(n), _p(ctrl), C.c_double(dt), C.c_int32(cost_function), _p(start),
+                                     C.c_int32(start.shape[0]), _p(end), C.c_int32(end.shape[0]), _p(guide),
+                                     C.c_int32(guide.shape[0]), _p(waypts), _p(widx), C.c_int32(waypts.shape[0]),
+                                     C.c_double(time_lb), _p(probes), C.c_int32(P), _p(f), _p(grad), _p(x0), _p(lb), _p(ub))
+        assert rc == nvar, rc
+        return dict(f=f, grad=grad, x0=x0, lb=lb, ub=ub)
 
 
 def dist_with_grad(g, dist_buf, pos):

@@ -206,3 +206,94 @@ def test_dist_with_grad_matches_reference():
     d, gr = O.dist_with_grad(ref.grid(), ref.distance.copy(), pos)
     assert np.array_equal(d, d_ref) and np.array_equal(gr, g_ref)
     ref.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BsplineOptimizer::combineCost: the reference's own bspline_optimizer.cpp (every calc*Cost, costFunction, the
+# set-up half of optimize()) vs the oracle restatement.  The NLopt stand-in evaluates the reference's objective
+# at its own start point and at probe points.
+# ---------------------------------------------------------------------------------------------------------
+OPT = dict(ld_smooth=20.0, ld_dist=10.0, ld_feasi=2.0, ld_start=100.0, ld_end=0.5, ld_guide=1.5, ld_waypt=0.3, ld_view=0.0,
+           ld_time=1.0, dist0=0.7, max_vel=2.0, max_acc=2.0, dlmin=0.0, wnl=0.0, max_iteration_num1=2, max_iteration_num2=2000,
+           max_iteration_num3=200, max_iteration_num4=200, max_iteration_time1=0.0001, max_iteration_time2=0.005,
+           max_iteration_time3=0.003, max_iteration_time4=0.003, algorithm1=15, algorithm2=11, bspline_degree=3)
+
+
+@pytest.fixture(scope="module")
+def opt_scene():
+    ref = O.RefSDFMap(**BASE)
+    inflate, tri = random_state(ref, 77, p_site=0.004)
+    ref.set_modes(1, 0)
+    ref.set_local_bound((0, 0, 0), (79, 59, 29))
+    ref.update_esdf3d()
+    opt = O.RefBsplineOptimizer(ref, **OPT)
+    wg = W.Grid(ref.n, tuple(ref.origin), ref.res)
+    tr = W.make_trajectories(wg, inflate, B=12, n_pts=20, seed=31)
+    yield dict(ref=ref, opt=opt, tr=tr, g=ref.grid(), dist=ref.distance.copy(), p=O.opt_params(ld_waypt=0.3))
+    opt.close()
+    ref.close()
+
+
+def _check(sc, b, mask, end, guide=None, waypts=None, widx=None, time_lb=-1.0, n_probe=6, seed=0):
+    tr, N = sc["tr"], 20
+    rng = np.random.default_rng(seed + 100 * b)
+    ctrl, dt, start = tr["ctrl"][b], float(tr["dt"][b]), tr["start"][b]
+    nvar = 3 * N + (1 if mask & O.MINTIME else 0)
+    x_init = np.concatenate([ctrl.reshape(-1), [dt]])[:nvar]
+    probes = x_init + rng.normal(size=(n_probe, nvar)) * 0.25
+    if mask & O.MINTIME:
+        probes[:, -1] = np.abs(probes[:, -1]) + 0.05
+        probes[0, -1] = 0.11      # fast: velocity / acceleration limits active
+    r = sc["opt"].evaluate(ctrl, dt, mask, start, end, guide, waypts, widx, time_lb, probes)
+    # what optimize() hands to NLopt: start point clamped to the box shrunk by 0.1 m, bounds +-10 m clipped to it (:175-217)
+    bmin, bmax = sc["ref"].origin + 0.1, sc["ref"].origin + np.array(sc["ref"].n) * sc["ref"].res - 0.1
+    x0 = x_init.copy()
+    x0[:3 * N] = np.clip(ctrl, bmin, bmax).reshape(-1)
+    assert np.array_equal(r["x0"], x0)
+    lo = np.maximum(x0[:3 * N].reshape(N, 3) - 10.0, bmin).reshape(-1)
+    hi = np.minimum(x0[:3 * N].reshape(N, 3) + 10.0, bmax).reshape(-1)
+    assert np.array_equal(r["lb"][:3 * N], lo) and np.array_equal(r["ub"][:3 * N], hi)
+    if mask & O.MINTIME:
+        assert r["lb"][-1] == 0.0 and r["ub"][-1] == 5.0
+    # the oracle on the same points
+    tc = O.traj_consts(1)
+    O.fill_traj_const(tc[0], O.pt_dist(ctrl), dt, start, end, time_lb, guide, waypts, widx)
+    X = np.concatenate([x0[None, :], probes])
+    f = np.zeros(len(X))
+    g = np.zeros((len(X), nvar))
+    for i in range(len(X)):
+        fi, gi = O.combine_cost_batch(sc["g"], sc["dist"], sc["p"], tc, N, mask, X[i:i + 1])
+        f[i], g[i] = fi[0], gi[0]
+    return f, g, r
+
+
+def test_combine_cost_exploration_objective_matches_reference(opt_scene):
+    """NORMAL_PHASE | MINTIME, the objective of the exploration replan (and of bench.py), bit for bit."""
+    mask = O.NORMAL_PHASE | O.MINTIME
+    for b in range(12):
+        f, g, r = _check(opt_scene, b, mask, opt_scene["tr"]["end_pos"][b][None, :])
+        assert np.array_equal(f, r["f"]), (b, f - r["f"])
+        assert np.array_equal(g, r["grad"]), (b, np.abs(g - r["grad"]).max())
+
+
+def test_combine_cost_other_terms_match_reference(opt_scene):
+    sc = opt_scene
+    tr = sc["tr"]
+    rng = np.random.default_rng(9)
+    for b in range(6):
+        endp = tr["end_pos"][b]
+        # fixed knot span (no MINTIME), end state with 1, 2, 3 rows
+        for n_end in (1, 2, 3):
+            end = np.concatenate([endp[None, :], rng.normal(size=(2, 3)) * 0.5])[:n_end]
+            f, g, r = _check(sc, b, O.NORMAL_PHASE, end, seed=n_end)
+            assert np.array_equal(f, r["f"]) and np.array_equal(g, r["grad"])
+        # GUIDE_PHASE with a guide path (N - 2*order points) and a duration lower bound
+        guide = tr["ctrl"][b][3:17] + rng.normal(size=(14, 3)) * 0.2
+        f, g, r = _check(sc, b, O.GUIDE_PHASE | O.MINTIME, endp[None, :], guide=guide, time_lb=9.0, seed=7)
+        assert np.array_equal(f, r["f"]) and np.array_equal(g, r["grad"])
+        # way points
+        widx = np.array([2, 7, 11], np.int32)
+        wp = tr["ctrl"][b][widx + 1] + rng.normal(size=(3, 3)) * 0.1
+        f, g, r = _check(sc, b, O.SMOOTHNESS | O.WAYPOINTS | O.START | O.END | O.MINTIME, endp[None, :], waypts=wp, widx=widx,
+                         seed=8)
+        assert np.array_equal(f, r["f"]) and np.array_equal(g, r["grad"])
