@@ -26,7 +26,8 @@ GUIDE_PHASE = SMOOTHNESS | GUIDE | START | END
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc -O3, the reference's flags)."""
     src = [os.path.join(_HERE, f) for f in ("fuel_oracle.c", "fuel_oracle_fusion.c", "fuel_oracle_viewpoints.c",
-                                            "fuel_oracle.h", "Makefile", "ref_raycast_wrap.cpp", "ref_sdfmap_wrap.cpp", "ref_bspline_wrap.cpp")]
+                                            "fuel_oracle.h", "Makefile", "ref_raycast_wrap.cpp", "ref_sdfmap_wrap.cpp", "ref_bspline_wrap.cpp",
+                                            "ref_frontier_wrap.cpp")]
     ref_src = "/root/reference/fuel_planner/plan_env/src/raycast.cpp"
     ref_ok = not os.path.exists(ref_src) or os.path.exists(os.path.join(_HERE, "_ref", "libfuel_ref.so"))
     if (not force and os.path.exists(_SO) and ref_ok
@@ -428,6 +429,65 @@ class RefBsplineOptimizer:
                                      C.c_double(time_lb), _p(probes), C.c_int32(P), _p(f), _p(grad), _p(x0), _p(lb), _p(ub))
         assert rc == nvar, rc
         return dict(f=f, grad=grad, x0=x0, lb=lb, ub=ub)
+
+
+class RefFrontierFinder:
+    """The reference's FrontierFinder (frontier_finder.cpp + perception_utils.cpp compiled from /root/reference) on a
+    RefSDFMap.  params: frontier/* keys without prefix; pu_params: perception_utils/* keys without prefix."""
+
+    def __init__(self, ref_map, pu_params=None, **params):
+        self.R = ref_map.R
+        self.map = ref_map
+        kv = {("frontier/" + k): v for k, v in params.items()}
+        kv.update({("perception_utils/" + k): v for k, v in (pu_params or {}).items()})
+        keys = [k.encode() for k in kv]
+        karr = (C.c_char_p * len(keys))(*keys)
+        vals = np.array([float(v) for v in kv.values()], dtype=np.float64)
+        self.R.ref_ff_create.restype = C.c_void_p
+        self.R.ref_ff_flags.restype = C.c_void_p
+        self.R.ref_ff_count.restype = C.c_int32
+        self.R.ref_ff_is_covered.restype = C.c_int32
+        self.h = C.c_void_p(self.R.ref_ff_create(ref_map.h, C.c_int32(len(keys)), karr, _p(vals)))
+        nv = int(np.prod(ref_map.n))
+        self.flags = np.ctypeslib.as_array(C.cast(self.R.ref_ff_flags(self.h), C.POINTER(C.c_int8)), (nv,))
+
+    def close(self):
+        if self.h:
+            self.flags = None
+            self.R.ref_ff_destroy(self.h)
+            self.h = None
+
+    def search(self, upd_min, upd_max):
+        """md_->update_min_/max_ := the given box, then searchFrontiers()"""
+        self.R.ref_map_set_updated_box(self.map.h, _p(np.ascontiguousarray(upd_min, dtype=np.float64)),
+                                       _p(np.ascontiguousarray(upd_max, dtype=np.float64)))
+        self.R.ref_ff_search(self.h)
+        return self.get_list(0)
+
+    def compute_to_visit(self):
+        self.R.ref_ff_compute_to_visit(self.h)
+        return self.get_list(1), self.get_list(2)
+
+    def is_covered(self):
+        return bool(self.R.ref_ff_is_covered(self.h))
+
+    def get_list(self, list_id):
+        """0 tmp_frontiers_, 1 frontiers_, 2 dormant_frontiers_ -> list of dicts"""
+        out = []
+        for i in range(self.R.ref_ff_count(self.h, C.c_int32(list_id))):
+            nc, nf, nvw, fid = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+            self.R.ref_ff_sizes(self.h, C.c_int32(list_id), C.c_int32(i), C.byref(nc), C.byref(nf), C.byref(nvw), C.byref(fid))
+            addr = np.zeros(nc.value, np.int32)
+            filt = np.zeros((nf.value, 3))
+            avg, bmin, bmax = np.zeros(3), np.zeros(3), np.zeros(3)
+            vpos = np.zeros((nvw.value, 3))
+            vyaw = np.zeros(nvw.value)
+            vvis = np.zeros(nvw.value, np.int32)
+            self.R.ref_ff_get(self.h, C.c_int32(list_id), C.c_int32(i), _p(addr), _p(filt), _p(avg), _p(bmin), _p(bmax),
+                              _p(vpos), _p(vyaw), _p(vvis))
+            out.append(dict(addr=addr, filtered=filt, average=avg, box_min=bmin, box_max=bmax, id=fid.value,
+                            view_pos=vpos, view_yaw=vyaw, view_visib=vvis))
+        return out
 
 
 def dist_with_grad(g, dist_buf, pos):

@@ -392,16 +392,15 @@ static int leaf_cmp(const void* a, const void* b) {
   return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
 }
 
-static void downsample(const FCtx* c, const double* cells, int32_t n, double** out, int32_t* m) {
-  const double leaf_size_d = c->g->res * c->p->down_sample; /* frontier_finder.cpp:765 */
-  const float leaf = (float)leaf_size_d;
+/* The filter itself on float32 points (what a pcl::PointCloud<pcl::PointXYZ> holds); out has room for n points.
+ * Exported because oracle/ref_standin/pcl/filters/voxel_grid.h -- the stand-in the reference's frontier_finder.cpp is
+ * compiled against for oracle/_ref -- must run the SAME reconstruction (PCL is third party and absent). */
+int32_t orc_voxelgrid_f32(const float* pf, int32_t n, float leaf, float* out) {
   const float inv = 1.0f / leaf;
   float minp[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, maxp[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-  float* pf = (float*)malloc(sizeof(float) * 3 * (n > 0 ? n : 1));
   for (int32_t i = 0; i < n; ++i)
     for (int k = 0; k < 3; ++k) {
-      float v = (float)cells[3 * i + k];
-      pf[3 * i + k] = v;
+      const float v = pf[3 * i + k];
       if (v < minp[k]) minp[k] = v;
       if (v > maxp[k]) maxp[k] = v;
     }
@@ -420,7 +419,6 @@ static void downsample(const FCtx* c, const double* cells, int32_t n, double** o
     li[i].idx = i;
   }
   qsort(li, n, sizeof(LeafIdx), leaf_cmp);
-  double* o = (double*)malloc(sizeof(double) * 3 * (n > 0 ? n : 1));
   int32_t cnt = 0;
   int32_t i = 0;
   while (i < n) {
@@ -431,12 +429,25 @@ static void downsample(const FCtx* c, const double* cells, int32_t n, double** o
       ++j;
     }
     const float fc = (float)(j - i);
-    for (int k = 0; k < 3; ++k) o[3 * cnt + k] = (double)(s[k] / fc); /* :772-773 float->double */
+    for (int k = 0; k < 3; ++k) out[3 * cnt + k] = s[k] / fc;
     ++cnt;
     i = j;
   }
-  free(pf);
   free(li);
+  return cnt;
+}
+
+static void downsample(const FCtx* c, const double* cells, int32_t n, double** out, int32_t* m) {
+  const double leaf_size_d = c->g->res * c->p->down_sample; /* frontier_finder.cpp:765 */
+  const float leaf = (float)leaf_size_d;
+  float* pf = (float*)malloc(sizeof(float) * 3 * (n > 0 ? n : 1));
+  float* of = (float*)malloc(sizeof(float) * 3 * (n > 0 ? n : 1));
+  for (int32_t i = 0; i < 3 * n; ++i) pf[i] = (float)cells[i];
+  const int32_t cnt = orc_voxelgrid_f32(pf, n, leaf, of);
+  double* o = (double*)malloc(sizeof(double) * 3 * (n > 0 ? n : 1));
+  for (int32_t i = 0; i < 3 * cnt; ++i) o[i] = (double)of[i]; /* :772-773 float->double */
+  free(pf);
+  free(of);
   *out = o;
   *m = cnt;
 }
@@ -486,7 +497,10 @@ static void make_givens(double p, double q, double* c, double* s) {
   }
 }
 
-void orc_principal_axis_2x2(double a, double b, double d, double pc[2]) {
+/* eigenvalues().real() and eigenvectors().real() of EigenSolver<Matrix2d> on [[a,b],[b,d]] under the reconstructed
+ * Eigen 3.3 convention: vals[i], vecs[row][col] (column i = eigenvector i).  Exported for
+ * oracle/ref_standin/Eigen/Eigenvalues (see orc_voxelgrid_f32). */
+void orc_eigen_sym2x2(double a, double b, double d, double vals_out[2], double vecs_out[2][2]) {
   /* T starts as the matrix itself (Hessenberg reduction of a 2x2 is the identity) */
   double T[2][2] = { { a, b }, { b, d } };
   double U[2][2] = { { 1, 0 }, { 0, 1 } };
@@ -551,22 +565,24 @@ void orc_principal_axis_2x2(double a, double b, double d, double pc[2]) {
   double n1 = sqrt(v1[0] * v1[0] + v1[1] * v1[1]);
   if (n0 > 0) { v0[0] /= n0; v0[1] /= n0; }
   if (n1 > 0) { v1[0] /= n1; v1[1] /= n1; }
-  /* eigenvalues = diag(T); pick larger, ties -> index 0 (frontier_finder.cpp:205-212) */
+  vals_out[0] = T[0][0], vals_out[1] = T[1][1];
+  vecs_out[0][0] = v0[0], vecs_out[1][0] = v0[1];
+  vecs_out[0][1] = v1[0], vecs_out[1][1] = v1[1];
+}
+
+void orc_principal_axis_2x2(double a, double b, double d, double pc[2]) {
+  double vals[2], vecs[2][2];
+  orc_eigen_sym2x2(a, b, d, vals, vecs);
+  /* pick the larger eigenvalue, ties -> index 0 (frontier_finder.cpp:205-212) */
   int max_idx = 0;
   double max_ev = -1000000;
-  double vals[2] = { T[0][0], T[1][1] };
   for (int i = 0; i < 2; ++i)
     if (vals[i] > max_ev) {
       max_idx = i;
       max_ev = vals[i];
     }
-  if (max_idx == 0) {
-    pc[0] = v0[0];
-    pc[1] = v0[1];
-  } else {
-    pc[0] = v1[0];
-    pc[1] = v1[1];
-  }
+  pc[0] = vecs[0][max_idx];
+  pc[1] = vecs[1][max_idx];
 }
 
 /* splitHorizontally, frontier_finder.cpp:179-242.  Returns 1 and appends the pieces

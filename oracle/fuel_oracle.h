@@ -5,17 +5,19 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, and only as the checker / the timed CPU baseline.
  *
- * PARITY STATUS: "parity unpinned", with one exception: the RayCaster restatement (fuel_oracle_fusion.c,
- * fuel_oracle_viewpoints.c) is checked ray-for-ray against the reference's own plan_env/src/raycast.cpp,
- * compiled unmodified into oracle/_ref/ (tests/test_oracle_refpin.py).  For everything else:  The reference (HKUST-Aerial-Robotics/FUEL @ 662dd23)
- * ships no golden vectors or unit tests for this path and cannot be
- * compiled here (needs ROS1, Eigen3, PCL, NLopt -- none installed, no network).  This
- * file follows the cited source lines statement by statement (same loop order, same
- * DBL_MAX sentinel arithmetic, fp64) and is pinned instead against independent ground
- * truths in tests/ (brute-force EDT, scipy.ndimage EDT and label, finite differences).
- * Third-party arithmetic reconstructed from published algorithms (unpinned):
- *   - PCL >= 1.7 VoxelGrid<PointXYZ>::applyFilter   (frontier_finder.cpp:757-774)
- *   - Eigen 3.3 EigenSolver<Matrix2d>               (frontier_finder.cpp:202-213)
+ * PARITY STATUS: pinned against the reference's own code for everything except two third-party algorithms.
+ * The reference (HKUST-Aerial-Robotics/FUEL @ 662dd23) ships no golden vectors or unit tests for this path (SURVEY.md
+ * section 4) and its build needs ROS1, Eigen3, PCL, NLopt (absent, no network) -- but its hot-path sources compile
+ * UNMODIFIED from /root/reference against the interface stand-ins of oracle/ref_standin/ (oracle/Makefile ->
+ * oracle/_ref/libfuel_ref.so): plan_env/src/{sdf_map,raycast}.cpp, bspline_opt/src/bspline_optimizer.cpp,
+ * active_perception/src/{frontier_finder,perception_utils}.cpp.  tests/test_oracle_refpin.py compares this oracle
+ * with that code bit for bit (ESDF all modes, inflation, fusion, getDistWithGrad, RayCaster, combineCost for every
+ * term combination, frontier search / split / flags, viewpoint sampling, isFrontierCovered).
+ * "parity unpinned" remains for the third-party arithmetic reconstructed from published algorithms (the stand-ins
+ * call these very functions, so the comparison does not cover them):
+ *   - PCL >= 1.7 VoxelGrid<PointXYZ>::applyFilter   (frontier_finder.cpp:757-774)  -> orc_voxelgrid_f32
+ *   - Eigen 3.3 EigenSolver<Matrix2d>               (frontier_finder.cpp:202-213)  -> orc_eigen_sym2x2
+ * and for NLopt's iterate sequence (not restated; orc_optimize_batch is the twin of OUR solver).
  *
  * All file:line citations are relative to /root/reference/fuel_planner/.
  */
@@ -154,6 +156,9 @@ int orc_is_frontier_cell(const OrcGrid* g, const uint8_t* tri, const int32_t id[
 /* principal axis of a symmetric 2x2 matrix under the reconstructed Eigen 3.3
  * EigenSolver convention (:202-213); exposed for its own tests */
 void orc_principal_axis_2x2(double a, double b, double d, double pc[2]);
+/* the two third-party reconstructions on their own (also used by oracle/ref_standin, see fuel_oracle.c) */
+void orc_eigen_sym2x2(double a, double b, double d, double vals[2], double vecs[2][2]);
+int32_t orc_voxelgrid_f32(const float* pts, int32_t n, float leaf, float* out);
 
 /* ---- viewpoint sampling; fuel_oracle_viewpoints.c ------------------------------- */
 typedef struct {

@@ -15,6 +15,7 @@
 #define ROS_WARN(...) do {} while (0)
 #define ROS_INFO(...) do {} while (0)
 #define ROS_INFO_STREAM(x) do {} while (0)
+#define ROS_WARN_THROTTLE(...) do {} while (0)
 
 namespace ros {
 struct Duration {

@@ -1,13 +1,17 @@
-"""Pins the oracle's RayCaster restatement (oracle/fuel_oracle_fusion.c, used by the fusion and viewpoint oracles)
-against the REFERENCE's own plan_env/src/raycast.cpp, compiled unmodified into oracle/_ref/libref_raycast.so
-(oracle/Makefile; Eigen is absent from the image, its five 3-vector operations come from oracle/eigen_standin).
-Skipped where the reference library was not built (no /root/reference)."""
+"""Pins the oracle against the REFERENCE's own code: plan_env/src/{raycast,sdf_map}.cpp,
+bspline_opt/src/bspline_optimizer.cpp and active_perception/src/{frontier_finder,perception_utils}.cpp are compiled
+UNMODIFIED from /root/reference into oracle/_ref/libfuel_ref.so (oracle/Makefile) against interface stand-ins for the
+headers the image lacks (oracle/ref_standin: Eigen small vectors/matrices, ros::NodeHandle::param, pcl containers, the
+NLopt API, ...).  Every comparison below is bit-exact.  Not covered, by construction: pcl::VoxelGrid and
+Eigen::EigenSolver (third-party algorithms; the stand-ins call the oracle's own reconstructions) and NLopt's iterates.
+Skipped where the reference library was not built (no /root/reference, e.g. on the GPU box)."""
 import numpy as np
 import pytest
 
 import oracle as O
 
-pytestmark = pytest.mark.skipif(O.ref_raycast() is None, reason="oracle/_ref/libref_raycast.so not built (no /root/reference)")
+O.build()  # also builds oracle/_ref/libfuel_ref.so where /root/reference exists (it is git-ignored)
+pytestmark = pytest.mark.skipif(O.ref_raycast() is None, reason="oracle/_ref/libfuel_ref.so not built (no /root/reference)")
 
 
 def test_intbound_matches_reference():
@@ -297,3 +301,130 @@ def test_combine_cost_other_terms_match_reference(opt_scene):
         f, g, r = _check(sc, b, O.SMOOTHNESS | O.WAYPOINTS | O.START | O.END | O.MINTIME, endp[None, :], waypts=wp, widx=widx,
                          seed=8)
         assert np.array_equal(f, r["f"]) and np.array_equal(g, r["grad"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# FrontierFinder: the reference's own frontier_finder.cpp + perception_utils.cpp (searchFrontiers, expandFrontier,
+# computeFrontierInfo, splitLargeFrontiers, computeFrontiersToVisit / sampleViewpoints / countVisibleCells,
+# isFrontierCovered) vs the oracle.  pcl::VoxelGrid and Eigen::EigenSolver are the oracle's reconstructions on BOTH
+# sides (ref_standin), so they are not what is being checked here.
+# ---------------------------------------------------------------------------------------------------------
+FF = dict(cluster_min=20, cluster_size_xy=1.0, cluster_size_z=10.0, min_candidate_dist=0.75, min_candidate_clearance=0.21,
+          candidate_dphi=15 * 3.1415926 / 180.0, candidate_rmax=2.5, candidate_rmin=1.5, candidate_rnum=3, down_sample=3,
+          min_visib_num=8, min_view_finish_fraction=0.2)
+PU = dict(top_angle=0.56125, left_angle=0.69222, right_angle=0.68901, max_dist=4.5, vis_dist=1.0)
+
+
+def frontier_scene(seed, box=None):
+    params = dict(BASE)
+    if box is not None:
+        for ax, lo, hi in zip("xyz", box[0], box[1]):
+            params["box_min_" + ax], params["box_max_" + ax] = lo, hi
+    ref = O.RefSDFMap(**params)
+    rng = np.random.default_rng(seed)
+    n = ref.n
+    inflate = (rng.random(n) < 0.003).astype(np.int8)
+    # known region: a few camera balls; the rest unknown
+    X, Y, Z = np.meshgrid(*[np.arange(k) for k in n], indexing="ij")
+    known = np.zeros(n, bool)
+    for _ in range(5):
+        c = rng.uniform(0.2, 0.8, 3) * np.array(n)
+        r = rng.uniform(0.2, 0.45) * min(n[0], n[1])
+        known |= ((X - c[0]) ** 2 + (Y - c[1]) ** 2 + 4.0 * (Z - c[2]) ** 2) < r * r
+    tri = np.where(known, W.FREE, W.UNKNOWN).astype(np.uint8)
+    tri[known & (inflate == 1)] = W.OCCUPIED
+    inflate[~known] = 0
+    lo = np.where(tri == W.UNKNOWN, logit(0.12) - 0.01, np.where(tri == W.OCCUPIED, logit(0.90), logit(0.12)))
+    ref.inflate[:] = inflate.reshape(-1)
+    ref.occupancy[:] = lo.reshape(-1)
+    return ref, inflate, tri
+
+
+def assert_clusters_equal(got, ref):
+    assert len(got) == len(ref), "cluster count %d vs %d" % (len(got), len(ref))
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert np.array_equal(a["addr"], b["addr"]), "cluster %d: cells / BFS order differ" % i
+        assert np.array_equal(a["filtered"], b["filtered"]), "cluster %d: filtered cells differ" % i
+        assert np.array_equal(a["average"], b["average"]) and np.array_equal(a["box_min"], b["box_min"]) \
+            and np.array_equal(a["box_max"], b["box_max"]), "cluster %d: info differs" % i
+
+
+@pytest.mark.parametrize("seed,box,upd", [
+    (1, None, ((-4.0, -3.0, -0.5), (4.0, 3.0, 2.5))),
+    (2, ((-3.5, -2.5, -0.3), (3.5, 2.5, 2.2)), ((-4.0, -3.0, -0.5), (4.0, 3.0, 2.5))),
+    (3, ((-3.5, -2.5, -0.3), (3.5, 2.5, 2.2)), ((-1.0, -2.0, 0.0), (2.5, 1.0, 1.5))),
+    (4, None, ((0.5, -1.0, 0.2), (3.0, 2.5, 1.8))),
+])
+def test_search_frontiers_matches_reference(seed, box, upd):
+    ref, inflate, tri = frontier_scene(seed, box)
+    ff = O.RefFrontierFinder(ref, PU, **FF)
+    want = ff.search(*upd)
+    g = ref.grid(*(box if box is not None else (None, None)))
+    flag = np.zeros(ref.n, np.int8)
+    p = O.frontier_params(cluster_min=FF["cluster_min"], cluster_size_xy=FF["cluster_size_xy"], down_sample=FF["down_sample"],
+                          cell_order=0)
+    got = O.frontier_search(g, tri, flag, upd[0], upd[1], p)
+    assert len(want) >= 3
+    assert_clusters_equal(got, want)
+    assert np.array_equal(flag.reshape(-1), ff.flags)
+    # a second search over a different updated box keeps the flags of the first (persistent frontier_flag_)
+    upd2 = ((-4.0, -3.0, -0.5), (0.0, 3.0, 2.5))
+    want2 = ff.search(*upd2)
+    got2 = O.frontier_search(g, tri, flag, upd2[0], upd2[1], p)
+    assert_clusters_equal(got2, want2)
+    assert np.array_equal(flag.reshape(-1), ff.flags)
+    ff.close()
+    ref.close()
+
+
+def test_viewpoints_and_coverage_match_reference():
+    """computeFrontiersToVisit (sampleViewpoints / countVisibleCells / isNearUnknown, PerceptionUtils) and
+    isFrontierCovered.  Same libm on both sides here, so yaw and counts are compared exactly."""
+    ref, inflate, tri = frontier_scene(6, ((-3.6, -2.6, -0.3), (3.6, 2.6, 2.2)))
+    ff = O.RefFrontierFinder(ref, PU, **FF)
+    upd = ((-4.0, -3.0, -0.5), (4.0, 3.0, 2.5))
+    tmp = ff.search(*upd)
+    visit, dormant = ff.compute_to_visit()
+    assert len(visit) + len(dormant) == len(tmp) and len(visit) >= 2
+    g = ref.grid((-3.6, -2.6, -0.3), (3.6, 2.6, 2.2))
+    vp = O.view_params()
+    n_vis = n_dor = 0
+    for t in tmp:
+        r = O.sample_viewpoints(g, tri, inflate, vp, t["average"], t["filtered"])
+        keep = np.nonzero(r["visib"] > FF["min_visib_num"])[0]
+        if len(keep) == 0:
+            assert np.array_equal(dormant[n_dor]["addr"], t["addr"])
+            n_dor += 1
+            continue
+        v = visit[n_vis]
+        n_vis += 1
+        assert np.array_equal(v["addr"], t["addr"]) and v["id"] == n_vis - 1
+        # the reference sorts by visib_num_ (std::sort, tie order unspecified): compare as sorted multisets
+        mine = sorted(zip(-r["visib"][keep], r["yaw"][keep], map(tuple, r["pos"][keep])))
+        theirs = sorted(zip(-v["view_visib"], v["view_yaw"], map(tuple, v["view_pos"])))
+        assert len(mine) == len(theirs)
+        for a, b in zip(mine, theirs):
+            assert a[0] == b[0] and a[2] == b[2] and (a[1] == b[1] or (np.isnan(a[1]) and np.isnan(b[1]))), (a, b)
+        assert list(v["view_visib"]) == sorted(v["view_visib"], reverse=True)
+    assert n_vis == len(visit) and n_dor == len(dormant)
+    # isFrontierCovered: nothing changed -> False; reveal the surroundings of the first cluster -> True
+    ref.R.ref_map_set_updated_box(ref.h, O._p(np.array(upd[0])), O._p(np.array(upd[1])))
+    assert not ff.is_covered()
+    first = visit[0]["addr"]
+    cnt0 = O.frontier_changed_count(g, tri, first)
+    assert cnt0 == 0
+    idx = np.stack(np.unravel_index(first, ref.n), axis=1)
+    occ = ref.occupancy.reshape(ref.n)
+    tri2 = tri.copy()
+    for d in (-1, 1):
+        for ax in range(3):
+            j = idx.copy()
+            j[:, ax] = np.clip(j[:, ax] + d, 0, ref.n[ax] - 1)
+            sel = tri2[j[:, 0], j[:, 1], j[:, 2]] == W.UNKNOWN
+            tri2[j[sel, 0], j[sel, 1], j[sel, 2]] = W.FREE
+            occ[j[sel, 0], j[sel, 1], j[sel, 2]] = logit(0.12)
+    cnt = O.frontier_changed_count(g, tri2, first)
+    assert cnt >= max(int(FF["min_view_finish_fraction"] * len(first)), 1)
+    assert ff.is_covered()
+    ff.close()
+    ref.close()
