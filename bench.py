@@ -134,13 +134,105 @@ def cpu_replan(S, evals, threads):
     return dict(esdf=t1 - t0, frontier=t2 - t1, bspline=t3 - t2, total=t3 - t0, n_clusters=len(fr))
 
 
+# the reference's own code (oracle/_ref/libfuel_ref.so: its sdf_map.cpp, frontier_finder.cpp, bspline_optimizer.cpp
+# compiled unmodified in the build container; prebuilt here) -- used for the CPU numbers whenever it is present
+REF_OPT = dict(ld_smooth=20.0, ld_dist=10.0, ld_feasi=2.0, ld_start=100.0, ld_end=0.5, ld_guide=1.5, ld_waypt=0.3,
+               ld_view=0.0, ld_time=1.0, dist0=0.7, max_vel=2.0, max_acc=2.0, dlmin=0.0, wnl=0.0, max_iteration_num1=2,
+               max_iteration_num2=2000, max_iteration_num3=200, max_iteration_num4=200, max_iteration_time1=0.0001,
+               max_iteration_time2=0.005, max_iteration_time3=0.003, max_iteration_time4=0.003, algorithm1=15,
+               algorithm2=11, bspline_degree=3)  # exploration_manager/launch/algorithm.xml:170-192
+
+
+class _Quiet:
+    """The reference prints to std::cout from its hot path; keep bench.py's stdout to the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self._saved, 1)
+        os.close(self._null)
+        os.close(self._saved)
+
+
+def ref_available():
+    import oracle
+    oracle.build()
+    return oracle.ref_raycast() is not None
+
+
+def ref_replan_setup(batch, evals):
+    """The same workload on the reference's own classes (the office map is centred, as SDFMap::initMap requires)."""
+    import oracle
+    g, inflate, tri, tr = build_workload(batch)
+    size = np.array(g.n) * g.res
+    assert np.allclose(np.asarray(g.origin)[:2], -size[:2] / 2)
+    params = dict(resolution=g.res, map_size_x=size[0], map_size_y=size[1], map_size_z=size[2], ground_height=g.origin[2],
+                  obstacles_inflation=0.199, local_bound_inflate=0.5, local_map_margin=50, default_dist=0.0, optimistic=1,
+                  signed_dist=0, p_hit=0.65, p_miss=0.35, p_min=0.12, p_max=0.90, p_occ=0.80, max_ray_length=4.5,
+                  virtual_ceil_height=-10.0)
+    for ax, lo, hi in zip("xyz", g.box_min, g.box_max):
+        params["box_min_" + ax], params["box_max_" + ax] = float(lo), float(hi)
+    with _Quiet():
+        ref = oracle.RefSDFMap(**params)
+    assert ref.n == tuple(g.n)
+    lg = lambda p: float(np.log(p / (1 - p)))  # noqa: E731
+    ref.inflate[:] = inflate.reshape(-1)
+    ref.occupancy[:] = np.where(tri == 0, lg(0.12) - 0.01, np.where(tri == 2, lg(0.90), lg(0.12))).reshape(-1)
+    ref.set_modes(1, 0)
+    ref.set_local_bound((0, 0, 0), np.array(g.n) - 1)
+    with _Quiet():
+        ff = oracle.RefFrontierFinder(ref, dict(top_angle=0.56125, left_angle=0.69222, right_angle=0.68901, max_dist=4.5,
+                                                vis_dist=1.0),
+                                      cluster_min=100, cluster_size_xy=2.0, cluster_size_z=10.0, min_candidate_dist=0.75,
+                                      min_candidate_clearance=0.21, candidate_dphi=15 * 3.1415926 / 180.0, candidate_rmax=2.5,
+                                      candidate_rmin=1.5, candidate_rnum=3, down_sample=3, min_visib_num=15,
+                                      min_view_finish_fraction=0.2)
+    from fuel_b200 import workloads as W
+    x = W.pack_x(tr["ctrl"], tr["dt"])
+    rng = np.random.default_rng(5)
+    # the K-1 further points at which the objective is evaluated: small steps around the start, like a line search
+    probes = x[:, None, :] + rng.normal(size=(batch, evals - 1, x.shape[1])) * 0.03
+    probes[:, :, -1] = np.abs(probes[:, :, -1]) + 1e-3
+    return dict(oracle=oracle, g=g, ref=ref, ff=ff, tr=tr, probes=np.ascontiguousarray(probes), B=batch)
+
+
+def ref_replan(S, evals, threads):
+    """One replan on the reference's own code: updateESDF3d, searchFrontiers, K combineCost calls per trajectory."""
+    oracle, g, ref, ff, tr = S["oracle"], S["g"], S["ref"], S["ff"], S["tr"]
+    with _Quiet():
+        t0 = time.perf_counter()
+        ref.update_esdf3d()
+        t1 = time.perf_counter()
+        ff.flags[:] = 0
+        ref.R.ref_map_set_updated_box(ref.h, oracle._p(np.asarray(g.origin, dtype=np.float64)),
+                                      oracle._p(np.asarray(g.map_max, dtype=np.float64)))
+        ref.R.ref_ff_search(ff.h)
+        t2 = time.perf_counter()
+        mask = oracle.NORMAL_PHASE | oracle.MINTIME
+        oracle.ref_combine_cost_batch(ref, REF_OPT, tr["ctrl"], tr["dt"], mask, tr["start"], tr["end_pos"],
+                                      S["probes"][:, :evals - 1], threads=threads)
+        t3 = time.perf_counter()
+        ncl = ref.R.ref_ff_count(ff.h, 0)
+    return dict(esdf=t1 - t0, frontier=t2 - t1, bspline=t3 - t2, total=t3 - t0, n_clusters=ncl)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")  # idle OpenMP workers must not spin beside the 1-thread BFS
     ncpu = os.cpu_count() or 1
-    S = cpu_replan_setup(args.batch)
+    use_ref = ref_available()
+    if use_ref:
+        S = ref_replan_setup(args.batch, args.evals)
+        cpu_replan = ref_replan  # noqa: F811  (the port below is the fallback when oracle/_ref was not built)
+    else:
+        S = cpu_replan_setup(args.batch)
+        cpu_replan = globals()["cpu_replan"]
     # "all the host threads it can use": OpenMP over independent ESDF lines / trajectories.  On a
     # many-core host the small office map stops scaling long before all cores are busy, so the
     # thread count is calibrated once (fastest of a few candidates) and reported as `cores`.
@@ -167,10 +259,15 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
         "config": workload_config(args),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d full replans (B=%d x K=%d evals each), OpenMP over ESDF lines and "
-                                   "trajectories, frontier BFS single-threaded as in the reference"
-                                   % (args.steps, args.batch, args.evals)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
+                         "sample": ("%d full replans on the reference's own code (oracle/_ref: sdf_map.cpp, frontier_finder.cpp, "
+                                    "bspline_optimizer.cpp compiled unmodified): updateESDF3d and searchFrontiers single-threaded "
+                                    "as written, B=%d trajectories x K=%d combineCost evaluations over %d threads with one "
+                                    "BsplineOptimizer each (NLopt itself absent: the objective is evaluated at K points)"
+                                    % (args.steps, args.batch, args.evals, threads)) if use_ref else
+                                   ("%d full replans (B=%d x K=%d evals each), OpenMP over ESDF lines and "
+                                    "trajectories, frontier BFS single-threaded as in the reference"
+                                    % (args.steps, args.batch, args.evals))},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "stage_ms": {k: 1e3 * float(np.mean([s[k] for s in stages])) for k in ("esdf", "frontier", "bspline")},
         "gpu_launches": 0,
@@ -530,14 +627,20 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             extra["next_rows"] = {"error": repr(e)}
 
-    # ---- CPU baseline: the oracle, 1 thread (faithful to the single-threaded reference) ----
-    S = cpu_replan_setup(args.batch)
-    cpu_replan(S, 2, 1)
+    # ---- CPU baseline, 1 thread (the reference is single-threaded): its own code when oracle/_ref is present ----
+    use_ref = ref_available()
+    if use_ref:
+        S = ref_replan_setup(args.batch, args.evals)
+        cpu_fn = ref_replan
+    else:
+        S = cpu_replan_setup(args.batch)
+        cpu_fn = cpu_replan
+    cpu_fn(S, 2, 1)
     t0 = time.perf_counter()
     nrep = 0
     cst = []
     while nrep < 3 or (time.perf_counter() - t0 < 12 and nrep < 50):
-        cst.append(cpu_replan(S, args.evals, 1))
+        cst.append(cpu_fn(S, args.evals, 1))
         nrep += 1
     cpu_dt = time.perf_counter() - t0
     cpu_val = nrep / cpu_dt
@@ -553,9 +656,12 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": "%d full replans of the same workload on 1 host thread (the reference is "
-                                   "single-threaded; its two ros::Time::now() calls per combineCost omitted)" % nrep,
+        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "reference" if use_ref else "port",
+                         "sample": ("%d full replans of the same workload on 1 host thread through the reference's own code "
+                                    "(oracle/_ref: its sdf_map.cpp / frontier_finder.cpp / bspline_optimizer.cpp compiled "
+                                    "unmodified; K combineCost evaluations per trajectory)" % nrep) if use_ref else
+                                   ("%d full replans of the same workload on 1 host thread (the reference is "
+                                    "single-threaded; its two ros::Time::now() calls per combineCost omitted)" % nrep),
                          "stage_ms": {k: 1e3 * float(np.mean([s[k] for s in cst])) for k in
                                       ("esdf", "frontier", "bspline")}},
         "stage_ms": {"esdf": st_ms["esdf"], "frontier": st_ms["frontier"], "bspline": st_ms["bspline"]},

@@ -431,6 +431,29 @@ class RefBsplineOptimizer:
         return dict(f=f, grad=grad, x0=x0, lb=lb, ub=ub)
 
 
+def ref_combine_cost_batch(ref_map, opt_params_dict, ctrl, dt, cost_function, start, end_pos, probes, threads=1):
+    """K = 1 + probes.shape[1] evaluations of the REFERENCE's combineCost per trajectory (its own start point, then the
+    probe points), B trajectories over `threads` host threads with one BsplineOptimizer each
+    (oracle/ref_bspline_wrap.cpp: ref_opt_evaluate_batch).  -> f [B, K]"""
+    R = ref_map.R
+    keys = [(("manager/" if k == "bspline_degree" else "optimization/") + k).encode() for k in opt_params_dict]
+    karr = (C.c_char_p * len(keys))(*keys)
+    vals = np.array([float(v) for v in opt_params_dict.values()], dtype=np.float64)
+    ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+    B, n = ctrl.shape[0], ctrl.shape[1]
+    probes = np.ascontiguousarray(probes, dtype=np.float64)
+    K = probes.shape[1] + 1
+    f = np.zeros((B, K))
+    R.ref_opt_evaluate_batch.restype = C.c_int32
+    bad = R.ref_opt_evaluate_batch(ref_map.h, C.c_int32(len(keys)), karr, _p(vals), C.c_int32(B), C.c_int32(n), _p(ctrl),
+                                   _p(np.ascontiguousarray(dt, dtype=np.float64)), C.c_int32(cost_function),
+                                   _p(np.ascontiguousarray(start, dtype=np.float64)),
+                                   _p(np.ascontiguousarray(end_pos, dtype=np.float64)), _p(probes), C.c_int32(K),
+                                   C.c_int32(threads), _p(f))
+    assert bad == 0
+    return f
+
+
 class RefFrontierFinder:
     """The reference's FrontierFinder (frontier_finder.cpp + perception_utils.cpp compiled from /root/reference) on a
     RefSDFMap.  params: frontier/* keys without prefix; pu_params: perception_utils/* keys without prefix."""

@@ -68,4 +68,50 @@ int32_t ref_opt_evaluate(void* h, int32_t n_pts, const double* ctrl, double dt, 
   return nvar;
 }
 
+// B independent trajectories, K objective evaluations each (the start point + K-1 probe points), `threads` host threads
+// with one BsplineOptimizer each (the reference runs up to 10 optimisers in parallel threads, planner_manager.cpp:444-453).
+// The timed CPU baseline of bench.py: the reference's own combineCost, called the way its NLopt loop calls it.
+//   ctrl [B][n_pts][3], dt [B], start [B][3][3], end_pos [B][3], probes [B][K-1][nvar]  ->  f [B][K]
+int32_t ref_opt_evaluate_batch(void* sdf_map_handle, int32_t n_keys, const char** keys, const double* values, int32_t B,
+                               int32_t n_pts, const double* ctrl, const double* dt, int32_t cost_function, const double* start,
+                               const double* end_pos, const double* probes, int32_t K, int32_t threads, double* f) {
+  const bool opt_time = (cost_function & BsplineOptimizer::MINTIME) != 0;
+  const int nvar = 3 * n_pts + (opt_time ? 1 : 0);
+  int bad = 0;
+#pragma omp parallel num_threads(threads > 0 ? threads : 1) reduction(+ : bad)
+  {
+    ros::NodeHandle nh;
+    for (int i = 0; i < n_keys; ++i) nh.values[keys[i]] = values[i];
+    BsplineOptimizer o;
+    o.setParam(nh);
+    EDTEnvironment::Ptr env(new EDTEnvironment);
+    env->sdf_map_ = std::shared_ptr<SDFMap>((SDFMap*)sdf_map_handle, [](SDFMap*) {});
+    o.setEnvironment(env);
+    nlopt::Recorder& r = nlopt::recorder();
+#pragma omp for schedule(dynamic, 4)
+    for (int b = 0; b < B; ++b) {
+      std::vector<Eigen::Vector3d> st, en;
+      for (int i = 0; i < 3; ++i) st.emplace_back(start[9 * b + 3 * i], start[9 * b + 3 * i + 1], start[9 * b + 3 * i + 2]);
+      en.emplace_back(end_pos[3 * b], end_pos[3 * b + 1], end_pos[3 * b + 2]);
+      o.setBoundaryStates(st, en);
+      Eigen::MatrixXd pts(n_pts, 3);
+      for (int i = 0; i < n_pts; ++i)
+        for (int j = 0; j < 3; ++j) pts(i, j) = ctrl[((size_t)b * n_pts + i) * 3 + j];
+      r.probes.clear();
+      for (int p = 0; p < K - 1; ++p) {
+        const double* q = probes + ((size_t)b * (K - 1) + p) * nvar;
+        r.probes.emplace_back(q, q + nvar);
+      }
+      double dtb = dt[b];
+      o.optimize(pts, dtb, cost_function, 1, 1);
+      if ((int)r.f.size() != K) {
+        ++bad;
+        continue;
+      }
+      for (int p = 0; p < K; ++p) f[(size_t)b * K + p] = r.f[p];
+    }
+  }
+  return bad;
+}
+
 }  // extern "C"

@@ -21,7 +21,7 @@ struct Recorder {
   std::vector<std::vector<double>> grad;     // out
 };
 inline Recorder& recorder() {
-  static Recorder r;
+  static thread_local Recorder r;  // one per thread: the batch driver runs one optimiser per host thread
   return r;
 }
 
