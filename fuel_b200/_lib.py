@@ -24,7 +24,7 @@ class FuelGpuError(RuntimeError):
 
 class FuelGridDesc(C.Structure):
     _fields_ = [("n", C.c_int32 * 3), ("resolution", C.c_double), ("origin", C.c_double * 3),
-                ("box_mind", C.c_double * 3), ("box_maxd", C.c_double * 3)]
+                ("box_mind", C.c_double * 3), ("box_maxd", C.c_double * 3), ("map_size", C.c_double * 3)]
 
 
 class FuelFrontierParams(C.Structure):

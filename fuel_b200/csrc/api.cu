@@ -148,7 +148,8 @@ int fuelgpu_map_create(const FuelGridDesc* grid, int device_id, FuelMap** out) {
   g.res_inv = 1 / grid->resolution;  // sdf_map.cpp:33
   for (int i = 0; i < 3; ++i) {
     g.origin[i] = grid->origin[i];
-    g.map_max[i] = grid->origin[i] + grid->n[i] * grid->resolution;
+    // map_max_boundary_ = map_origin_ + map_size_ (sdf_map.cpp:34-39)
+    g.map_max[i] = grid->origin[i] + (grid->map_size[i] > 0.0 ? grid->map_size[i] : grid->n[i] * grid->resolution);
     g.box_mind[i] = grid->box_mind[i];
     g.box_maxd[i] = grid->box_maxd[i];
     // posToIndex(box_mind_/box_maxd_), sdf_map.cpp:83-84

@@ -17,7 +17,7 @@ struct Geom {
   int nx, ny, nz;
   double res, res_inv;
   double origin[3];
-  double map_max[3];  // origin + n*res (map_max_boundary_, sdf_map.cpp:39)
+  double map_max[3];  // map_origin_ + map_size_ (map_max_boundary_, sdf_map.cpp:34-39)
   int box_min[3];     // posToIndex(box_mind_), sdf_map.cpp:83
   int box_max[3];     // posToIndex(box_maxd_), sdf_map.cpp:84
   double box_mind[3], box_maxd[3];

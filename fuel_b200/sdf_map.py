@@ -23,7 +23,7 @@ class SDFMap:
     UNKNOWN, FREE, OCCUPIED = 0, 1, 2  # sdf_map.h:32
 
     def __init__(self, voxel_num, resolution, origin, box_min=None, box_max=None, optimistic=False,
-                 signed_dist=False, p_min=0.12, p_occ=0.80, default_dist=0.0, device=0):
+                 signed_dist=False, p_min=0.12, p_occ=0.80, default_dist=0.0, device=0, map_size=None):
         """initMap (sdf_map.cpp:12-93) with the ROS parameters passed explicitly.
 
         voxel_num = map_voxel_num_, origin = map_origin_, box_min/box_max = box_mind_/box_maxd_
@@ -33,7 +33,11 @@ class SDFMap:
         self.resolution_inv_ = 1 / self.resolution_
         self.map_origin_ = np.asarray(origin, dtype=np.float64)
         self.map_min_boundary_ = self.map_origin_.copy()
-        self.map_max_boundary_ = self.map_origin_ + self.map_voxel_num_ * self.resolution_
+        # map_size_ (sdf_map/map_size_x,y,z, sdf_map.cpp:34): map_max_boundary_ = origin + map_size_, which need not equal
+        # n * resolution bit for bit (n = ceil(size / resolution)); default: n * resolution
+        self.map_size_ = (self.map_voxel_num_ * self.resolution_ if map_size is None
+                          else np.asarray(map_size, dtype=np.float64))
+        self.map_max_boundary_ = self.map_origin_ + self.map_size_
         self.box_mind_ = np.asarray(self.map_min_boundary_ if box_min is None else box_min, dtype=np.float64)
         self.box_maxd_ = np.asarray(self.map_max_boundary_ if box_max is None else box_max, dtype=np.float64)
         self.box_min_ = self.posToIndex(self.box_mind_)
@@ -64,6 +68,7 @@ class SDFMap:
             d.origin[i] = self.map_origin_[i]
             d.box_mind[i] = self.box_mind_[i]
             d.box_maxd[i] = self.box_maxd_[i]
+            d.map_size[i] = 0.0 if map_size is None else float(self.map_size_[i])
         d.resolution = self.resolution_
         self._desc = d
         h = C.c_void_p()

@@ -52,6 +52,9 @@ typedef struct {
   double origin[3];   /* map_origin_ (= map_min_boundary_)   */
   double box_mind[3]; /* box_mind_  exploration box, metres  */
   double box_maxd[3]; /* box_maxd_                           */
+  double map_size[3]; /* map_size_ (sdf_map/map_size_x,y,z): map_max_boundary_ = origin + map_size_ (sdf_map.cpp:34-39),
+                         which is not always n*resolution in floating point (n = ceil(size/resolution)).
+                         All zero = n * resolution. */
 } FuelGridDesc;
 
 /* Occupancy tri-state of SDFMap::getOccupancy (sdf_map.h:32,194-200). */

@@ -67,6 +67,7 @@ struct MapParam {  // the ROS parameters of initMap (sdf_map.cpp:19-47,79-84) as
   Vector3i map_voxel_num_;
   double resolution_ = 0.1;
   Vector3d map_origin_;
+  Vector3d map_size_;  // sdf_map/map_size_x,y,z; a zero component means n * resolution (sdf_map.cpp:34-39)
   Vector3d box_mind_, box_maxd_;
   bool optimistic_ = false, signed_dist_ = false;
   double p_min_ = 0.12, p_occ_ = 0.80;
@@ -98,7 +99,7 @@ public:
     occupancy_buffer_inflate_.assign(n, 0);
     distance_buffer_.assign(n, mp_.default_dist_);
     for (int i = 0; i < 3; ++i) {
-      map_max_boundary_(i) = mp_.map_origin_(i) + mp_.map_voxel_num_(i) * mp_.resolution_;
+      map_max_boundary_(i) = mp_.map_origin_(i) + (mp_.map_size_(i) > 0.0 ? mp_.map_size_(i) : mp_.map_voxel_num_(i) * mp_.resolution_);
       local_bound_min_(i) = 0;
       local_bound_max_(i) = mp_.map_voxel_num_(i) - 1;
     }
@@ -110,6 +111,7 @@ public:
       d.origin[i] = mp_.map_origin_(i);
       d.box_mind[i] = mp_.box_mind_(i);
       d.box_maxd[i] = mp_.box_maxd_(i);
+      d.map_size[i] = mp_.map_size_(i);
     }
     d.resolution = mp_.resolution_;
     fuelgpu_check(fuelgpu_map_create(&d, mp_.device, &gpu_), nullptr);

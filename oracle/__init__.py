@@ -39,7 +39,7 @@ def build(force=False):
 
 class OrcGrid(C.Structure):
     _fields_ = [("n", C.c_int32 * 3), ("res", C.c_double), ("origin", C.c_double * 3),
-                ("box_mind", C.c_double * 3), ("box_maxd", C.c_double * 3)]
+                ("box_mind", C.c_double * 3), ("box_maxd", C.c_double * 3), ("map_size", C.c_double * 3)]
 
 
 class OrcFrontierParams(C.Structure):
@@ -112,7 +112,8 @@ def _p(a, ty=None):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def make_grid(n, res, origin, box_mind=None, box_maxd=None):
+def make_grid(n, res, origin, box_mind=None, box_maxd=None, map_size=None):
+    """map_size = map_size_ of the reference (map_max_boundary_ = origin + map_size_); None -> n * res"""
     g = OrcGrid()
     for i in range(3):
         g.n[i] = int(n[i])
@@ -125,6 +126,7 @@ def make_grid(n, res, origin, box_mind=None, box_maxd=None):
     for i in range(3):
         g.box_mind[i] = float(box_mind[i])
         g.box_maxd[i] = float(box_maxd[i])
+        g.map_size[i] = 0.0 if map_size is None else float(map_size[i])
     return g
 
 
@@ -336,6 +338,7 @@ class RefSDFMap:
         res = C.c_double()
         R.ref_map_geometry(self.h, _p(n), _p(o), C.byref(res))
         self.n, self.origin, self.res = tuple(int(v) for v in n), o, res.value
+        self.map_size = np.array([float(params["map_size_" + a]) for a in "xyz"])
         nv = int(np.prod(n))
         self.occupancy = np.ctypeslib.as_array(C.cast(R.ref_map_occupancy(self.h), C.POINTER(C.c_double)), (nv,))
         self.inflate = np.ctypeslib.as_array(C.cast(R.ref_map_inflate(self.h), C.POINTER(C.c_int8)), (nv,))
@@ -348,7 +351,9 @@ class RefSDFMap:
             self.h = None
 
     def grid(self, box_mind=None, box_maxd=None):
-        return make_grid(self.n, self.res, self.origin, box_mind, box_maxd)
+        if box_maxd is None:
+            box_maxd = self.origin + self.map_size  # map_max_boundary_ (sdf_map.cpp:39,80-81)
+        return make_grid(self.n, self.res, self.origin, box_mind, box_maxd, map_size=self.map_size)
 
     def set_local_bound(self, lo, hi):
         self.R.ref_map_set_local_bound(self.h, _p(np.ascontiguousarray(lo, dtype=np.int32)),

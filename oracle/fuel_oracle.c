@@ -43,7 +43,9 @@ static inline int64_t to_address(const OrcGrid* g, int x, int y, int z) {
 
 /* map_max_boundary_ = origin + map_size_, sdf_map.cpp:34-39.  map_size_ here is n*res
  * (the reference derives n = ceil(size/res) from size; fixtures give n and res). */
-static inline double map_max(const OrcGrid* g, int i) { return g->origin[i] + g->n[i] * g->res; }
+static inline double map_max(const OrcGrid* g, int i) {
+  return g->origin[i] + (g->map_size[i] > 0.0 ? g->map_size[i] : g->n[i] * g->res);
+}
 
 /* sdf_map.h:153-161 */
 int orc_is_in_map_pos(const OrcGrid* g, const double pos[3]) {

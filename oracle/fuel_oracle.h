@@ -37,6 +37,7 @@ typedef struct {
   double origin[3];   /* map_origin_ = map_min_boundary_ */
   double box_mind[3]; /* box_mind_ (exploration box, metres) */
   double box_maxd[3]; /* box_maxd_ */
+  double map_size[3]; /* map_size_: map_max_boundary_ = origin + map_size_ (sdf_map.cpp:34-39); all zero = n*res */
 } OrcGrid;
 
 /* Occupancy tri-state, sdf_map.h:32 and :194-200 (getOccupancy). */

@@ -98,7 +98,7 @@ static void closest_point_in_map(const OrcGrid* g, const double pt[3], const dou
   double diff[3], max_tc[3], min_tc[3];
   for (int i = 0; i < 3; ++i) {
     diff[i] = pt[i] - cam[i];
-    max_tc[i] = (g->origin[i] + g->n[i] * g->res) - cam[i];
+    max_tc[i] = (g->origin[i] + (g->map_size[i] > 0.0 ? g->map_size[i] : g->n[i] * g->res)) - cam[i];
     min_tc[i] = g->origin[i] - cam[i];
   }
   double min_t = 1000000;

@@ -428,3 +428,32 @@ def test_viewpoints_and_coverage_match_reference():
     assert ff.is_covered()
     ff.close()
     ref.close()
+
+
+def test_map_size_that_is_not_a_multiple_of_the_resolution():
+    """map_voxel_num_ = ceil(size / resolution) but map_max_boundary_ = origin + size (sdf_map.cpp:34-39): with a size of
+    6.45 m the last voxel column lies partly outside the map.  isInMap / closetPointInMap / getDistWithGrad use the
+    metric boundary; the oracle takes it through OrcGrid.map_size (the C ABI through FuelGridDesc.map_size)."""
+    ref = O.RefSDFMap(**dict(BASE, map_size_x=6.45, map_size_y=4.83, map_size_z=2.41, max_ray_length=2.0))
+    assert ref.n == (65, 49, 25)
+    g = ref.grid()
+    f = O.Fusion(g, O.fusion_params(max_ray_length=2.0))
+    rng = np.random.default_rng(8)
+    for frame in range(4):
+        cam = np.array([rng.uniform(1.5, 3.0), rng.uniform(1.0, 2.2), rng.uniform(0.5, 1.6)])   # close to the +x/+y/+z faces
+        pts = (cam + rng.normal(size=(3000, 3)) * np.array([1.5, 1.5, 0.8])).astype(np.float32)
+        ref.input_point_cloud(pts, cam)
+        lo, hi = f.input_point_cloud(pts, cam)
+        assert np.array_equal(f.logodds, ref.occupancy)
+        rlo, rhi = ref.get_local_bound()
+        assert np.array_equal(lo, rlo) and np.array_equal(hi, rhi)
+    ref.set_modes(0, 0)
+    ref.set_local_bound((0, 0, 0), np.array(ref.n) - 1)
+    ref.update_esdf3d()
+    top = ref.origin + ref.map_size
+    pos = top - rng.uniform(-0.02, 0.15, (2000, 3))          # around the upper faces
+    d_ref, g_ref = ref.dist_with_grad(pos)
+    d, gr = O.dist_with_grad(g, ref.distance.copy(), pos)
+    assert np.array_equal(d, d_ref) and np.array_equal(gr, g_ref)
+    assert (d_ref == 0).sum() > 100 and (d_ref != 0).sum() > 100
+    ref.close()
