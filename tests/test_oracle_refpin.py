@@ -457,3 +457,45 @@ def test_map_size_that_is_not_a_multiple_of_the_resolution():
     assert np.array_equal(d, d_ref) and np.array_equal(gr, g_ref)
     assert (d_ref == 0).sum() > 100 and (d_ref != 0).sum() > 100
     ref.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_combine_cost_random_weights_sizes_and_masks(seed):
+    """Random lambda weights / limits, 8..31 control points, random term masks, end-state rows and duration bounds."""
+    rng = np.random.default_rng(seed)
+    ref = O.RefSDFMap(**BASE)
+    inflate, tri = random_state(ref, 300 + seed, p_site=float(rng.choice([0.002, 0.01])))
+    ref.set_modes(int(rng.integers(0, 2)), 0)
+    ref.set_local_bound((0, 0, 0), (79, 59, 29))
+    ref.update_esdf3d()
+    keys = ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide", "ld_waypt", "ld_time", "dist0", "max_vel", "max_acc")
+    lo_hi = dict(ld_smooth=(1, 30), ld_dist=(1, 20), ld_feasi=(0.5, 5), ld_start=(1, 100), ld_end=(0.1, 5), ld_guide=(0.5, 3),
+                 ld_waypt=(0.1, 2), ld_time=(0.5, 3), dist0=(0.3, 1.2), max_vel=(0.5, 3), max_acc=(0.5, 3))
+    w = {k: float(rng.uniform(*lo_hi[k])) for k in keys}
+    opt = O.RefBsplineOptimizer(ref, **dict(OPT, **w))
+    p = O.opt_params(**w)
+    g, dist = ref.grid(), ref.distance.copy()
+    N = int(rng.choice([8, 12, 20, 31]))
+    tr = W.make_trajectories(W.Grid(ref.n, tuple(ref.origin), ref.res), inflate, B=5, n_pts=N, seed=seed)
+    for b in range(5):
+        mask = int(rng.choice([O.NORMAL_PHASE | O.MINTIME, O.NORMAL_PHASE, O.GUIDE_PHASE | O.MINTIME,
+                               O.SMOOTHNESS | O.WAYPOINTS | O.START | O.END, O.DISTANCE | O.FEASIBILITY | O.MINTIME]))
+        ctrl, dt, start = tr["ctrl"][b], float(tr["dt"][b]), tr["start"][b]
+        guide = ctrl[3:N - 3] + rng.normal(size=(N - 6, 3)) * 0.2 if mask & O.GUIDE else None
+        widx = np.array([1, N // 2 - 1, N - 4], np.int32) if mask & O.WAYPOINTS else None
+        wp = ctrl[widx + 1] + rng.normal(size=(3, 3)) * 0.1 if widx is not None else None
+        end = np.concatenate([tr["end_pos"][b][None, :], rng.normal(size=(2, 3)) * 0.5])[:int(rng.integers(1, 4))]
+        tlb = float(rng.choice([-1.0, 6.0, 20.0]))
+        nvar = 3 * N + (1 if mask & O.MINTIME else 0)
+        probes = np.concatenate([ctrl.reshape(-1), [dt]])[:nvar] + rng.normal(size=(4, nvar)) * 0.3
+        if mask & O.MINTIME:
+            probes[:, -1] = np.abs(probes[:, -1]) + 0.03
+        r = opt.evaluate(ctrl, dt, mask, start, end, guide, wp, widx, tlb, probes)
+        tc = O.traj_consts(1)
+        O.fill_traj_const(tc[0], O.pt_dist(ctrl), dt, start, end, tlb, guide, wp, widx)
+        X = np.concatenate([r["x0"][None, :], probes])
+        for i in range(len(X)):
+            fi, gi = O.combine_cost_batch(g, dist, p, tc, N, mask, X[i:i + 1])
+            assert fi[0] == r["f"][i] and np.array_equal(gi[0], r["grad"][i]), (b, mask, i)
+    opt.close()
+    ref.close()
