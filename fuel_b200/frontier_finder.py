@@ -103,16 +103,19 @@ class FrontierFinder:
         check(lib().fuelgpu_frontier_is_changed(h, len(ftrs), ptr(offs), ptr(addr), ptr(changed)), h)
         return changed
 
+    def _clear_flags(self, addr):
+        """frontier_flag_[addr] = 0 on the device"""
+        h = self._map.handle
+        check(lib().fuelgpu_frontier_clear_flags(h, addr.size, ptr(addr)), h)
+
     def _remove_changed(self, ftrs, update_min, update_max, record_ids):
         cand = [i for i, f in enumerate(ftrs)
                 if self.haveOverlap(f.box_min_, f.box_max_, update_min, update_max)]
         changed = self._changed([ftrs[i] for i in cand])
         drop = {cand[j] for j in range(len(cand)) if changed[j]}
         if drop:
-            addr = np.ascontiguousarray(
-                np.concatenate([ftrs[i].cells_addr_ for i in sorted(drop)]).astype(np.int32))
-            h = self._map.handle
-            check(lib().fuelgpu_frontier_clear_flags(h, addr.size, ptr(addr)), h)  # resetFlag :62-69
+            self._clear_flags(np.ascontiguousarray(
+                np.concatenate([ftrs[i].cells_addr_ for i in sorted(drop)]).astype(np.int32)))  # resetFlag :62-69
         kept = []
         rmv_idx = 0
         for i, f in enumerate(ftrs):

@@ -499,6 +499,17 @@ class RefFrontierFinder:
     def is_covered(self):
         return bool(self.R.ref_ff_is_covered(self.h))
 
+    def search_frontiers(self):
+        """searchFrontiers() on whatever updated box the map holds (getUpdatedBox(reset=true) inside)"""
+        self.R.ref_ff_search(self.h)
+        return self.get_list(0)
+
+    def removed_ids(self):
+        out = np.zeros(4096, np.int32)
+        self.R.ref_ff_removed_ids.restype = C.c_int32
+        n = self.R.ref_ff_removed_ids(self.h, _p(out), C.c_int32(4096))
+        return out[:n].tolist()
+
     def get_list(self, list_id):
         """0 tmp_frontiers_, 1 frontiers_, 2 dormant_frontiers_ -> list of dicts"""
         out = []

@@ -62,6 +62,11 @@ void ref_ff_search(void* h) { ((FrontierFinder*)h)->searchFrontiers(); }
 void ref_ff_compute_to_visit(void* h) { ((FrontierFinder*)h)->computeFrontiersToVisit(); }
 int32_t ref_ff_is_covered(void* h) { return ((FrontierFinder*)h)->isFrontierCovered() ? 1 : 0; }
 char* ref_ff_flags(void* h) { return ((FrontierFinder*)h)->frontier_flag_.data(); }
+int32_t ref_ff_removed_ids(void* h, int32_t* out, int32_t max) {  // removed_ids_ of the last searchFrontiers (:75-84)
+  const std::vector<int>& r = ((FrontierFinder*)h)->removed_ids_;
+  for (size_t i = 0; i < r.size() && (int)i < max; ++i) out[i] = r[i];
+  return (int32_t)r.size();
+}
 
 // list_id: 0 tmp_frontiers_, 1 frontiers_, 2 dormant_frontiers_
 int32_t ref_ff_count(void* h, int32_t list_id) { return (int32_t)which(*(FrontierFinder*)h, list_id).size(); }
