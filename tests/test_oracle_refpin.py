@@ -499,3 +499,12 @@ def test_combine_cost_random_weights_sizes_and_masks(seed):
             assert fi[0] == r["f"][i] and np.array_equal(gi[0], r["grad"][i]), (b, mask, i)
     opt.close()
     ref.close()
+
+
+def test_host_mirror_pt_dist_is_the_reference_value(opt_scene):
+    """pt_dist_ (bspline_optimizer.cpp:136-140) as the Python mirror and workloads.make_trajectories compute it ==
+    the oracle's, which the tests above pin to the reference through the smoothness term."""
+    import fuel_b200
+    tr = opt_scene["tr"]
+    for b in range(tr["ctrl"].shape[0]):
+        assert fuel_b200.BsplineOptimizer.pt_dist(tr["ctrl"][b]) == O.pt_dist(tr["ctrl"][b]) == tr["pt_dist"][b]
