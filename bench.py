@@ -32,6 +32,18 @@ METRIC = "replans_per_sec"
 UNIT = "replans/s"
 
 
+def profile_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture) of the
+    named kernel/stage, read from the committed summary profiles/traffic.json (written by tools/ncu_traffic.py from
+    the .ncu-rep); None if that stage has no capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        v = d.get(key)
+        return float(v["bytes"]) if v else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -114,24 +126,29 @@ def cpu_replan_setup(batch):
     return dict(oracle=oracle, g=g, og=og, inflate=inflate, tri=tri, tcs=tcs, x=x, B=B)
 
 
-def cpu_replan(S, evals, threads):
-    """One replan on the CPU.  Returns per-stage seconds."""
+def cpu_replan(S, evals, threads, bspline_only=False):
+    """One replan on the CPU (oracle port).  Returns per-stage seconds.  ESDF lines and trajectories go over
+    `threads` OpenMP threads; the frontier BFS is single-threaded as in the reference."""
     oracle = S["oracle"]
     g = S["g"]
     t0 = time.perf_counter()
-    dist = oracle.update_esdf3d(S["og"], S["inflate"], S["tri"], [0, 0, 0], np.array(g.n) - 1, True, False,
-                                threads=threads)
+    if not bspline_only or "dist" not in S:
+        S["dist"] = oracle.update_esdf3d(S["og"], S["inflate"], S["tri"], [0, 0, 0], np.array(g.n) - 1, True, False,
+                                         threads=threads)
+    dist = S["dist"]
     t1 = time.perf_counter()
-    flag = np.zeros(g.n, dtype=np.int8)
-    fr = oracle.frontier_search(S["og"], S["tri"], flag, g.origin, g.map_max, oracle.frontier_params())
+    ncl = 0
+    if not bspline_only:
+        flag = np.zeros(g.n, dtype=np.int8)
+        ncl = len(oracle.frontier_search(S["og"], S["tri"], flag, g.origin, g.map_max, oracle.frontier_params()))
     t2 = time.perf_counter()
     mask = oracle.NORMAL_PHASE | oracle.MINTIME
     x = S["x"]
     xb, fb, ne = oracle.optimize_batch(S["og"], dist, oracle.opt_params(), S["tcs"], 20, mask, x, max_eval=evals,
                                        xtol_rel=0.0, threads=threads)
-    assert int(ne.min()) == evals or evals == 1 or True
     t3 = time.perf_counter()
-    return dict(esdf=t1 - t0, frontier=t2 - t1, bspline=t3 - t2, total=t3 - t0, n_clusters=len(fr))
+    return dict(esdf=t1 - t0, frontier=t2 - t1, bspline=t3 - t2, total=t3 - t0, n_clusters=ncl,
+                evals_min=int(ne.min()), evals_mean=float(ne.mean()))
 
 
 # the reference's own code (oracle/_ref/libfuel_ref.so: its sdf_map.cpp, frontier_finder.cpp, bspline_optimizer.cpp
@@ -200,24 +217,58 @@ def ref_replan_setup(batch, evals):
     return dict(oracle=oracle, g=g, ref=ref, ff=ff, tr=tr, probes=np.ascontiguousarray(probes), B=batch)
 
 
-def ref_replan(S, evals, threads):
-    """One replan on the reference's own code: updateESDF3d, searchFrontiers, K combineCost calls per trajectory."""
+def ref_replan(S, evals, threads, bspline_only=False):
+    """One replan on the reference's own code: updateESDF3d, searchFrontiers (both single-threaded as written),
+    K combineCost calls per trajectory over `threads` threads (one BsplineOptimizer each)."""
     oracle, g, ref, ff, tr = S["oracle"], S["g"], S["ref"], S["ff"], S["tr"]
     with _Quiet():
         t0 = time.perf_counter()
-        ref.update_esdf3d()
+        if not bspline_only or not S.get("esdf_done"):
+            ref.update_esdf3d()
+            S["esdf_done"] = True
         t1 = time.perf_counter()
-        ff.flags[:] = 0
-        ref.R.ref_map_set_updated_box(ref.h, oracle._p(np.asarray(g.origin, dtype=np.float64)),
-                                      oracle._p(np.asarray(g.map_max, dtype=np.float64)))
-        ref.R.ref_ff_search(ff.h)
+        if not bspline_only:
+            ff.flags[:] = 0
+            ref.R.ref_map_set_updated_box(ref.h, oracle._p(np.asarray(g.origin, dtype=np.float64)),
+                                          oracle._p(np.asarray(g.map_max, dtype=np.float64)))
+            ref.R.ref_ff_search(ff.h)
         t2 = time.perf_counter()
         mask = oracle.NORMAL_PHASE | oracle.MINTIME
         oracle.ref_combine_cost_batch(ref, REF_OPT, tr["ctrl"], tr["dt"], mask, tr["start"], tr["end_pos"],
                                       S["probes"][:, :evals - 1], threads=threads)
         t3 = time.perf_counter()
         ncl = ref.R.ref_ff_count(ff.h, 0)
-    return dict(esdf=t1 - t0, frontier=t2 - t1, bspline=t3 - t2, total=t3 - t0, n_clusters=ncl)
+    return dict(esdf=t1 - t0, frontier=t2 - t1, bspline=t3 - t2, total=t3 - t0, n_clusters=ncl,
+                evals_min=evals, evals_mean=float(evals))
+
+
+def physical_cores():
+    """Physical cores this process may run on (SMT siblings counted once)."""
+    try:
+        allowed = os.sched_getaffinity(0)
+    except AttributeError:
+        allowed = set(range(os.cpu_count() or 1))
+    seen = set()
+    for c in allowed:
+        try:
+            sib = open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c).read().strip()
+        except OSError:
+            sib = str(c)
+        seen.add(sib)
+    return max(1, len(seen))
+
+
+def calibrate_threads(fn, S, evals, ncores):
+    """Thread count of the trajectory batch: the candidate with the best MEDIAN of 3 timings of the B-spline stage
+    alone (ESDF/frontier are single-threaded in the reference and must not vote), never above the physical cores."""
+    cands = sorted({c for c in (ncores, ncores // 2, ncores // 4, 64, 32, 16, 8, 4, 2, 1) if 1 <= c <= ncores},
+                   reverse=True)
+    table = {}
+    for c in cands:
+        fn(S, min(evals, 8), c, bspline_only=True)
+        table[c] = float(np.median([fn(S, evals, c, bspline_only=True)["bspline"] for _ in range(3)]))
+    best = min(table, key=lambda c: table[c])
+    return best, {str(c): round(1e3 * v, 3) for c, v in table.items()}
 
 
 def run_reference(args):
@@ -233,19 +284,10 @@ def run_reference(args):
     else:
         S = cpu_replan_setup(args.batch)
         cpu_replan = globals()["cpu_replan"]
-    # "all the host threads it can use": OpenMP over independent ESDF lines / trajectories.  On a
-    # many-core host the small office map stops scaling long before all cores are busy, so the
-    # thread count is calibrated once (fastest of a few candidates) and reported as `cores`.
-    cands = sorted({c for c in (ncpu, ncpu // 2, ncpu // 4, 32, 16, 8, 4) if 1 <= c <= ncpu}, reverse=True)
-    best = None
-    for c in cands:
-        cpu_replan(S, min(args.evals, 8), c)
-        t0 = time.perf_counter()
-        cpu_replan(S, args.evals, c)
-        dtc = time.perf_counter() - t0
-        if best is None or dtc < best[0]:
-            best = (dtc, c)
-    threads = best[1]
+    # "all the host threads it can use": the trajectory batch goes over OpenMP threads; on a many-core host the
+    # small batch stops scaling long before all cores are busy, so the count is calibrated (median of 3 runs of
+    # the B-spline stage per candidate, capped at the physical cores) and reported as `cores`.
+    threads, calib = calibrate_threads(cpu_replan, S, args.evals, physical_cores())
     for _ in range(args.warmup):
         cpu_replan(S, args.evals, threads)
     t0 = time.perf_counter()
@@ -270,6 +312,12 @@ def run_reference(args):
                                     % (args.steps, args.batch, args.evals))},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "stage_ms": {k: 1e3 * float(np.mean([s[k] for s in stages])) for k in ("esdf", "frontier", "bspline")},
+        "cores": threads, "cores_physical": physical_cores(), "cores_logical": ncpu,
+        "thread_calibration_bspline_ms": calib,
+        "evals_done_min": min(s["evals_min"] for s in stages),
+        "n_planners": 1,
+        "note": "ONE CPU planner on rank 0 regardless of --gpus (the reference is one process); at N > 1 the driver's "
+                "ratio therefore compares N GPU planners with one CPU planner",
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -330,7 +378,9 @@ class GpuPlanner:
         self.d_n = torch.empty(batch, dtype=torch.int32, device="cuda:%d" % dev)
         from fuel_b200._lib import FuelSolveParams
         self.sp = FuelSolveParams()
-        self.sp.max_eval, self.sp.lbfgs_m, self.sp.xtol_rel = evals, 6, 0.0  # xtol off: exactly K evaluations
+        # the metric's unit of work is B x K combineCost evaluations (the CPU arms do exactly K): xtol off and the
+        # solver restarts instead of stopping when a line search fails or the gradient vanishes
+        self.sp.max_eval, self.sp.lbfgs_m, self.sp.xtol_rel, self.sp.flags = evals, 6, 0.0, 1
         self.d_f = torch.empty(batch, dtype=torch.float64, device="cuda:%d" % dev)
         self.d_g = torch.empty((batch, self.nvar), dtype=torch.float64, device="cuda:%d" % dev)
         self.pin_x = torch.from_numpy(self.x_host).pin_memory()
@@ -438,10 +488,11 @@ def esdf512_roofline(dev, peak, peak_src, variant="V1", reps=5):
     t = float(np.mean(ms)) * 1e-3
     alg = 5.0 * g.nvox
     ach = alg / t / 1e9
-    return {"kernel": "esdf_update 512^3 (zsweep_vec_kernel + envelope_kernel y + envelope_kernel x)", "bound": "hbm",
+    return {"kernel": "esdf_update 512^3 (zpack_kernel + per z chunk: envelope_tile_kernel zy, envelope_tile_kernel x)",
+            "bound": "hbm",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            # DRAM read+write of the three sweeps per update, ncu --set full (profiles/r01_esdf512_ncu_full.txt)
-            "traffic": 2.516e9 if variant == "V1" else None,
+            # DRAM read+write of all kernels of one update, ncu --set full (profiles/traffic.json)
+            "traffic": profile_traffic("esdf512_" + variant.lower()),
             "algorithmic_bytes": alg, "ms": 1e3 * t, "peak_source": peak_src,
             "workload": "pillar.pcd %s on 512^3 @0.1m, optimistic, full rebuild (box = whole map); "
                         "L2 flushed before every timed update" % ("V1 (tiled to fill the cube)" if variant == "V1"
@@ -476,6 +527,9 @@ def next_rows_timing(dev):
             m.inputDepthImage(img, R, cam)
     m.synchronize()
     out["fusion_depth_frame_ms"] = 1e3 * (time.perf_counter() - t0) / 20
+    for _ in range(3):  # warm-up: the first call pays lazy allocations and page-locking of the mirror
+        m.clearAndInflateLocalMap()
+    m.synchronize()
     t0 = time.perf_counter()
     for _ in range(10):
         m.clearAndInflateLocalMap()
@@ -563,6 +617,11 @@ def run_ours(args):
     clocks = sampler.stop()
     launches = P.m.launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    nev = P.d_n.cpu().numpy()  # evaluations the solver actually performed in the last timed replan
+    evals_min, evals_mean = int(nev.min()), float(nev.mean())
+    if evals_min != args.evals:
+        raise SystemExit("bench.py: the solver stopped after %d < %d evaluations on some trajectory -- the unit of work "
+                         "of the metric (B x K combineCost) was not performed" % (evals_min, args.evals))
     tt = torch.tensor([dev_ms], dtype=torch.float64, device="cuda:%d" % local)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -602,18 +661,23 @@ def run_ours(args):
     # bound: its HBM fraction is reported for completeness, from the algorithmic
     # 1624 B per trajectory-evaluation; the ESDF rows use 5 B/voxel; frontier 2 B/voxel.
     alg = {"esdf": 5.0 * P.g.nvox, "frontier": 2.0 * P.g.nvox, "bspline": 1624.0 * args.batch}
-    alg["bspline"] *= args.evals  # one launch = K evaluations of the batch
+    alg["bspline"] *= evals_mean  # one launch = K evaluations of the batch (K checked against the solver's own count)
     per_launch_ms = dict(st_ms)
     dom = max(("esdf", "frontier", "bspline"), key=lambda k: st_ms[k])
     ach = alg[dom] / (per_launch_ms[dom] * 1e-3) / 1e9
-    roofline = {"kernel": {"esdf": "esdf_update (3 sweeps)", "frontier": "frontier_search (sweep + clustering)",
+    notes = {
+        "bspline": "dominant stage of the office replan: the solver is dependent-latency-bound (1 warp per trajectory), "
+                   "the 3.8 MB ESDF is L2-resident, so the HBM fraction is reported for completeness only",
+        "frontier": "dominant stage of the office replan: the frontier search of a 0.96 M-voxel map is launch/barrier-"
+                    "latency-bound (2 B/voxel = 1.9 MB, L2-resident), so the HBM fraction is reported for completeness "
+                    "only; the HBM-bound frontier case is roofline_frontier512",
+        "esdf": "dominant stage of the office replan: a 0.96 M-voxel map is L2-resident and launch-latency-bound; the "
+                "HBM-bound ESDF case is roofline_esdf512"}
+    roofline = {"kernel": {"esdf": "esdf_update (zpack + envelope tiles)", "frontier": "frontier_search (sweep + clustering)",
                            "bspline": "optimize_warp_kernel (K evaluations of the batch in one launch)"}[dom],
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_office_kernels_ncu_full.txt)
-                "traffic": {"bspline": 3.78e6, "frontier": 1.43e6}.get(dom), "algorithmic_bytes": alg[dom],
-                "peak_source": peak_src,
-                "note": "dominant stage of the office replan: latency-bound (1 warp per trajectory, 7 warps per SM), the "
-                        "3.8 MB map is L2-resident, so the HBM fraction is reported for completeness only"}
+                "traffic": profile_traffic("office_" + dom), "algorithmic_bytes": alg[dom],
+                "peak_source": peak_src, "note": notes[dom]}
     extra = {}
     if not args.no_esdf512 and world == 1:
         try:
@@ -667,6 +731,7 @@ def run_ours(args):
         "stage_ms": {"esdf": st_ms["esdf"], "frontier": st_ms["frontier"], "bspline": st_ms["bspline"]},
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "n_frontier_clusters": P.n_clusters,
+        "evals_done_min": evals_min, "evals_done_mean": evals_mean,
     }
     line.update(extra)
     print(json.dumps(line))

@@ -178,9 +178,17 @@ int fuelgpu_map_create(const FuelGridDesc* grid, int device_id, FuelMap** out) {
   CR(cudaMalloc(&m->occ, nvox));
   CR(cudaMalloc(&m->dist, sizeof(float) * nvox));
   CR(cudaMalloc(&m->flag, nvox));
-  CR(cudaMalloc(&m->g1, sizeof(int32_t) * nvox));
-  CR(cudaMalloc(&m->g2, sizeof(int32_t) * nvox));
-  CR(cudaMalloc(&m->stk, sizeof(uint32_t) * nvox));
+  {
+    size_t rec_bytes = 0;
+    int wc = 0;
+    esdf_tile_scratch_sizes(g.nx, g.ny, g.nz, &rec_bytes, &m->esdf_p_bytes, &wc);
+    CR(cudaMalloc(&m->esdf_rec, rec_bytes));
+    CR(cudaMalloc(&m->esdf_p[0], m->esdf_p_bytes));
+    CR(cudaMalloc(&m->esdf_p[1], m->esdf_p_bytes));
+    CR(cudaStreamCreateWithFlags(&m->esdf_aux, cudaStreamNonBlocking));
+    CR(cudaEventCreateWithFlags(&m->esdf_ev[0], cudaEventDisableTiming));
+    CR(cudaEventCreateWithFlags(&m->esdf_ev[1], cudaEventDisableTiming));
+  }
   // initMap: occupancy unknown, inflate 0, distance default_dist (0.0, algorithm.xml:41), flags 0
   CR(cudaMemsetAsync(m->occ, 0, nvox, m->stream));
   CR(cudaMemsetAsync(m->dist, 0, sizeof(float) * nvox, m->stream));
@@ -209,7 +217,14 @@ int fuelgpu_map_destroy(FuelMap* m) {
   frontier_state_destroy(m);
   fusion_state_destroy(m);
   if (m->bs_pin) cudaFreeHost(m->bs_pin);
-  void* ptrs[] = { m->occ, m->dist, m->dist_neg, m->flag, m->g1, m->g2, m->stk, m->stage, m->bs_buf, m->fr_scr };
+  if (m->esdf_aux) {
+    cudaStreamSynchronize(m->esdf_aux);
+    cudaStreamDestroy(m->esdf_aux);
+  }
+  for (int i = 0; i < 2; ++i)
+    if (m->esdf_ev[i]) cudaEventDestroy(m->esdf_ev[i]);
+  void* ptrs[] = { m->occ,       m->dist,      m->dist_neg, m->flag,   m->esdf_rec,
+                   m->esdf_p[0], m->esdf_p[1], m->stage,    m->bs_buf, m->fr_scr };
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int t = 0; t < T_COUNT; ++t) {

@@ -39,10 +39,12 @@ struct FuelMap {
   float* dist;      // distance_buffer_ (metres)
   float* dist_neg;  // distance_buffer_neg_ (lazy, signed mode only)
   int8_t* flag;     // frontier_flag_
-  // ESDF scratch
-  int32_t* g1;
-  int32_t* g2;
-  uint32_t* stk;
+  // ESDF scratch (esdf_tile.cu): z records, two chunk buffers of the 2-D partial, second stream
+  void* esdf_rec;
+  void* esdf_p[2];
+  size_t esdf_p_bytes;
+  cudaStream_t esdf_aux;
+  cudaEvent_t esdf_ev[2];
   // staging for ingest
   void* stage;
   size_t stage_bytes;
@@ -98,6 +100,8 @@ __host__ __device__ static inline int64_t addr_of(const Geom& g, int x, int y, i
 
 // ---- stage entry points implemented per .cu file ----
 int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags);
+void esdf_tile_scratch_sizes(int nx, int ny, int nz, size_t* rec_bytes, size_t* p_bytes, int* wc);
+int esdf_tile_transform(FuelMap* m, const int lo[3], const int hi[3], int mode, float* out);
 int map_inflate_impl(FuelMap* m, const int bmin[3], const int bmax[3], int step, int ceil_id);
 int esdf_sample_impl(FuelMap* m, int64_t n, const double* pos_dev, double* dist_dev, double* grad_dev);
 int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl, int flags,

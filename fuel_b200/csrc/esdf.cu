@@ -372,59 +372,6 @@ __global__ void sample_kernel(Geom g, const float* __restrict__ dist, int64_t n,
   grad[3 * i + 2] = gr[2];
 }
 
-int run_three_pass(cudaStream_t s, const uint8_t* occ, int32_t* g1, int32_t* g2, uint32_t* stk,
-                   float* out, int nx, int ny, int nz, const Box& b, int mode, float res) {
-  (void)nx;
-  const int nxb = b.hi[0] - b.lo[0] + 1, nyb = b.hi[1] - b.lo[1] + 1, nzb = b.hi[2] - b.lo[2] + 1;
-  uint16_t* g1h = (uint16_t*)g1;
-  // z sweep
-  {
-    const int nlines = nxb * nyb;
-    const int wpb = 8;
-    const unsigned grid = (nlines + wpb - 1) / wpb;
-    const bool full = b.lo[2] == 0 && nzb == nz;
-    if (full && nz % 16 == 0 && nz <= 512 && nz > 128)
-      zsweep_vec_kernel<16><<<grid, wpb * 32, 0, s>>>(occ, g1h, ny, nz, b, mode, nlines);
-    else if (full && nz % 8 == 0 && nz <= 256 && nz > 64)
-      zsweep_vec_kernel<8><<<grid, wpb * 32, 0, s>>>(occ, g1h, ny, nz, b, mode, nlines);
-    else if (full && nz % 4 == 0 && nz <= 128)
-      zsweep_vec_kernel<4><<<grid, wpb * 32, 0, s>>>(occ, g1h, ny, nz, b, mode, nlines);
-    else
-      zsweep_warp_kernel<<<grid, wpb * 32, 0, s>>>(occ, g1h, ny, nz, b, mode, nlines);
-  }
-  // y sweep: lines (x,z); uint16 distances in, int32 squared 2-D distances out
-  {
-    LineMap lm;
-    lm.n = nyb;
-    lm.stride = nz;
-    lm.nz_run = nzb;
-    lm.n_outer = nxb;
-    lm.outer_stride = (int64_t)ny * nz;
-    lm.base = ((int64_t)b.lo[0] * ny + b.lo[1]) * nz + b.lo[2];
-    const int64_t nl = (int64_t)nzb * nxb;
-    if ((int64_t)nxb * nyb * nzb >= (1 << 24))
-      envelope_kernel<true, false, 16, 16><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g1h, g2, stk, lm, res);
-    else
-      envelope_kernel<true, false, 16><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g1h, g2, stk, lm, res);
-  }
-  // x sweep: lines (y,z), writes metres; the hull stack reuses the dead slots of its own input
-  {
-    LineMap lm;
-    lm.n = nxb;
-    lm.stride = (int64_t)ny * nz;
-    lm.nz_run = nzb;
-    lm.n_outer = nyb;
-    lm.outer_stride = nz;
-    lm.base = ((int64_t)b.lo[0] * ny + b.lo[1]) * nz + b.lo[2];
-    const int64_t nl = (int64_t)nzb * nyb;
-    if ((int64_t)nxb * nyb * nzb >= (1 << 24))
-      envelope_kernel<false, true, 8, 16><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g2, out, (uint32_t*)g2, lm, res);
-    else
-      envelope_kernel<false, true, 8><<<(unsigned)((nl + 127) / 128), 128, 0, s>>>(g2, out, (uint32_t*)g2, lm, res);
-  }
-  return 0;
-}
-
 }  // namespace
 
 int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags) {
@@ -435,17 +382,16 @@ int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags
   }
   const int mode = (flags & FUELGPU_ESDF_OPTIMISTIC) ? 0 : 1;
   const float res = (float)m->g.res;
-  run_three_pass(m->stream, m->occ, m->g1, m->g2, m->stk, m->dist, m->g.nx, m->g.ny, m->g.nz, b, mode,
-                 res);
-  FUEL_LAUNCHES(m, 3);
+  int rc = esdf_tile_transform(m, b.lo, b.hi, mode, m->dist);
+  if (rc) return rc;
   if (flags & FUELGPU_ESDF_SIGNED) {
     if (!m->dist_neg) FUEL_CUDA(m, cudaMalloc(&m->dist_neg, sizeof(float) * m->nvox));
-    run_three_pass(m->stream, m->occ, m->g1, m->g2, m->stk, m->dist_neg, m->g.nx, m->g.ny, m->g.nz, b,
-                   2, res);
+    rc = esdf_tile_transform(m, b.lo, b.hi, 2, m->dist_neg);
+    if (rc) return rc;
     const int64_t nb = (int64_t)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
     signed_merge_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, m->stream>>>(m->dist, m->dist_neg,
                                                                           m->g.ny, m->g.nz, b, res);
-    FUEL_LAUNCHES(m, 4);
+    FUEL_LAUNCHES(m, 1);
   }
   FUEL_CUDA(m, cudaGetLastError());
   return 0;
