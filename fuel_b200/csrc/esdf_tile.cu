@@ -289,6 +289,13 @@ __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TilePar
     }
     if (band == 0) mbar_wait(bar, 0);
     __syncthreads();
+    // the tile of P is dead once it sits in shared memory: drop its lines from L2 instead of letting them be
+    // written back to HBM later (P is produced and consumed out of L2; only the fp32 result should reach DRAM)
+    {
+      const char* src = reinterpret_cast<const char*>(p.pin + ((int64_t)o * gridDim.x + bx) * n * 32);
+      for (int r = threadIdx.x; r < n; r += blockDim.x)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(src + (size_t)r * 128) : "memory");
+    }
   }
 
   // ---- phase 1: hull of the band's own 32 samples, in place --------------------------------
