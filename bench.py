@@ -499,6 +499,96 @@ def esdf512_roofline(dev, peak, peak_src, variant="V1", reps=5):
                                                                   else "V0 (file as is, mostly empty cube)")}
 
 
+def sharded_esdf_arm(local, rank, world, reps=5):
+    """BASELINE config 4: synthetic 1024x1024x256 map, z-sharded ESDF over all ranks (fuelgpu_sharded_esdf_*,
+    NCCL called inside the library).  Collective: every rank calls it.  Device time = max over ranks.  Also runs
+    the parity check of the sharded path against the single-GPU kernel on a smaller map (the driver's pytest box
+    has one GPU), and times the same update on ONE rank (a 1-rank communicator on rank 0) for reference."""
+    import torch
+    import torch.distributed as dist
+
+    import fuel_b200
+    from fuel_b200 import workloads as W
+    from fuel_b200.dist import ShardedESDF
+    dev = "cuda:%d" % local
+    out = {}
+    # ---- parity: sharded == single GPU, voxel for voxel (finite values to 1e-6 relative, same +inf set) ----
+    npar = (32 * world * 2, 96, 32 * world)
+    g, inflate = W.random_boxes_map(n=npar, seed=11, n_boxes=48, ground_idx=3)
+    sh = ShardedESDF(npar, g.res, optimistic=True, device=local)
+    z0, z1 = sh.z_range()
+    occ = torch.from_numpy(((inflate[:, :, z0:z1] << 2) | 1).astype(np.uint8)).contiguous().to(dev)
+    full = sh.gather_full(sh.update(occ)).cpu().numpy()
+    sh.close()
+    m = fuel_b200.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max, optimistic=True, device=local)
+    m.occupancy_buffer_inflate_[...] = inflate
+    m.occupancy_tri_[...] = 1
+    m.upload()
+    m.updateESDF3d()
+    ref = m.download().copy()
+    m.close()
+    fin = np.isfinite(ref)
+    ok = bool(np.array_equal(np.isinf(full), ~fin) and np.allclose(full[fin], ref[fin], rtol=1e-6, atol=0))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["parity_vs_single_gpu"] = {"map": list(npar), "ok_all_ranks": bool(int(flag.item()) == 1)}
+    # ---- timing on the config-4 map ----
+    n = (1024, 1024, 256)
+    g, inflate = W.random_boxes_map(n=n, seed=11, n_boxes=4096)
+    sh = ShardedESDF(n, g.res, optimistic=True, device=local)
+    z0, z1 = sh.z_range()
+    occ = torch.from_numpy(((inflate[:, :, z0:z1] << 2) | 1).astype(np.uint8)).contiguous().to(dev)
+    st = torch.cuda.current_stream(local)
+    buf = torch.empty((n[0], n[1], sh.nzl), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        sh.update(occ, out=buf)
+    torch.cuda.synchronize(local)
+    ms, stages = [], []
+    for _ in range(reps):
+        dist.barrier()
+        torch.cuda.synchronize(local)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        sh.update(occ, out=buf)
+        e1.record(st)
+        torch.cuda.synchronize(local)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms.append(float(t.item()))
+        stages.append(sh.last_timing())
+    sent = sh.bytes_exchanged()
+    sh.close()
+    out.update({"map": list(n), "n_gpus": world, "ms": float(np.median(ms)), "ms_all": [round(v, 3) for v in ms],
+                "stage_ms_rank0": {k: round(float(np.median([s_[k] for s_ in stages])), 3) for k in stages[0]},
+                "bytes_sent_per_rank": sent, "voxels": int(np.prod(n)),
+                "note": "device time of one whole-map update, max over ranks; stages: occupancy all-to-all (1 B/voxel), "
+                        "z records + zy tiles with the int32 partial's exchange rounds running beside them, wait for the "
+                        "last rounds, x tiles"})
+    # ---- the same update on ONE GPU (rank 0, 1-rank communicator) ----
+    solo = dist.new_group([0]) if world > 1 else None  # collective over the default group
+    if rank == 0:
+        sh1 = ShardedESDF(n, g.res, optimistic=True, device=local, group=solo)
+        occ1 = torch.from_numpy(((inflate << 2) | 1).astype(np.uint8)).contiguous().to(dev)
+        buf1 = torch.empty(n, dtype=torch.float32, device=dev)
+        for _ in range(2):
+            sh1.update(occ1, out=buf1)
+        torch.cuda.synchronize(local)
+        m1 = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            sh1.update(occ1, out=buf1)
+            e1.record(st)
+            torch.cuda.synchronize(local)
+            m1.append(e0.elapsed_time(e1))
+        sh1.close()
+        out["ms_1gpu"] = float(np.median(m1))
+        del occ1, buf1
+    if world > 1:
+        dist.barrier()
+    return out
+
+
 def next_rows_timing(dev):
     """SURVEY 8f rows built on top of the hot path, timed beside it (not part of the metric): one fused depth
     frame (proessDepthImage + inputPointCloud), clearAndInflateLocalMap, and sampleViewpoints for the clusters of
@@ -650,6 +740,14 @@ def run_ours(args):
     e2e_val = world * args.steps / (float(t2.item()) * 1e-3)
     h2d, d2h = P.e2e_bytes()
 
+    # ---- BASELINE config 4 (z-sharded ESDF over all ranks) beside the replica metric, N > 1 only ----
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        try:
+            sharded = sharded_esdf_arm(local, rank, world)
+        except Exception as e:  # noqa: BLE001
+            sharded = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -734,6 +832,8 @@ def run_ours(args):
         "evals_done_min": evals_min, "evals_done_mean": evals_mean,
     }
     line.update(extra)
+    if sharded is not None:
+        line["sharded_esdf"] = sharded
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -748,6 +848,7 @@ def main():
     ap.add_argument("--evals", type=int, default=64)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--no-esdf512", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the config-4 z-sharded ESDF arm at N > 1")
     ap.add_argument("--no-overlap", action="store_true", help="run the frontier search after the ESDF update instead of beside it")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -64,7 +64,11 @@ class FuelTrajConst(C.Structure):
 
 
 class FuelSolveParams(C.Structure):
-    _fields_ = [("max_eval", C.c_int32), ("lbfgs_m", C.c_int32), ("xtol_rel", C.c_double)]
+    _fields_ = [("max_eval", C.c_int32), ("lbfgs_m", C.c_int32), ("xtol_rel", C.c_double), ("flags", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+SOLVE_EXACT_EVALS = 1
 
 
 # every symbol include/fuelgpu.h declares: name -> (restype, argtypes)
@@ -121,8 +125,16 @@ SIGNATURES = {
     "fuelgpu_bspline_optimize_batch_end": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fuelgpu_bspline_optimize_batch_dev": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp,
                                                      C.POINTER(FuelSolveParams), _vp, _vp, _vp]),
-    "fuelgpu_edt_xy_dev": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_int, _vp, _vp]),
-    "fuelgpu_edt_z_chunks_dev": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _dbl, _vp, _vp]),
+    "fuelgpu_comm_get_unique_id": (C.c_int, [_vp]),
+    "fuelgpu_comm_init": (C.c_int, [_i32, _i32, _vp, _i32, C.POINTER(_vp)]),
+    "fuelgpu_comm_info": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
+    "fuelgpu_comm_destroy": (C.c_int, [_vp]),
+    "fuelgpu_sharded_esdf_create": (C.c_int, [_vp, C.POINTER(_i32), _dbl, C.POINTER(_vp)]),
+    "fuelgpu_sharded_esdf_update": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "fuelgpu_sharded_esdf_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "fuelgpu_sharded_esdf_bytes_exchanged": (_i64, [_vp]),
+    "fuelgpu_sharded_esdf_allgather": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "fuelgpu_sharded_esdf_destroy": (C.c_int, [_vp]),
 }
 
 _lib = None

@@ -809,24 +809,6 @@ int fuelgpu_bspline_optimize_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t
   return fuelgpu_bspline_optimize_batch_end(m, x, f_best, n_eval);
 }
 
-int fuelgpu_edt_xy_dev(void* cuda_stream, const void* occ_slab, int32_t nx, int32_t ny, int32_t nzl,
-                       int flags, void* g2_out_i32, void* scratch_i32) {
-  if (!occ_slab || !g2_out_i32 || !scratch_i32) return fuel_fail(nullptr, FUELGPU_EINVAL, "null argument");
-  if (nx < 1 || ny < 1 || nzl < 1 || nx > 1024 || ny > 1024)
-    return fuel_fail(nullptr, FUELGPU_EINVAL, "slab extent out of range");
-  return edt_xy_dev_impl((cudaStream_t)cuda_stream, (const uint8_t*)occ_slab, nx, ny, nzl, flags,
-                         (int32_t*)g2_out_i32, (int32_t*)scratch_i32);
-}
 
-int fuelgpu_edt_z_chunks_dev(void* cuda_stream, const void* g2_chunks_i32, int32_t G, int32_t nxl,
-                             int32_t ny, int32_t nzl, double resolution, void* dist_out_f32,
-                             void* scratch_i32) {
-  if (!g2_chunks_i32 || !dist_out_f32 || !scratch_i32)
-    return fuel_fail(nullptr, FUELGPU_EINVAL, "null argument");
-  if (G < 1 || nxl < 1 || ny < 1 || nzl < 1 || (int64_t)G * nzl > 1024)
-    return fuel_fail(nullptr, FUELGPU_EINVAL, "chunk extent out of range");
-  return edt_z_chunks_dev_impl((cudaStream_t)cuda_stream, (const int32_t*)g2_chunks_i32, G, nxl, ny, nzl,
-                               resolution, (float*)dist_out_f32, (int32_t*)scratch_i32);
-}
 
 }  // extern "C"

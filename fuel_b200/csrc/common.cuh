@@ -102,12 +102,15 @@ __host__ __device__ static inline int64_t addr_of(const Geom& g, int x, int y, i
 int esdf_update_impl(FuelMap* m, const int bmin[3], const int bmax[3], int flags);
 void esdf_tile_scratch_sizes(int nx, int ny, int nz, size_t* rec_bytes, size_t* p_bytes, int* wc);
 int esdf_tile_transform(FuelMap* m, const int lo[3], const int hi[3], int mode, float* out);
+int edt_stage_zpack(cudaStream_t st, const uint8_t* occ, void* rec, int nxl, int ny, int nzc, int G, int64_t chunk_stride,
+                    int mode);
+int edt_stage_zy(cudaStream_t st, const void* rec, int nxl, int ny, int NW, int w0, int wn, int32_t* P, int64_t out_o,
+                 int64_t out_bx, int64_t out_q);
+int edt_stage_x(cudaStream_t st, const int32_t* P, int64_t in_o, int64_t in_bx, int64_t piece_stride, int piece_rows, int nx,
+                int ny, int wn, float* out, int64_t out_o, int64_t out_bx, int64_t out_q, int lanes_total, float res,
+                int discard);
 int map_inflate_impl(FuelMap* m, const int bmin[3], const int bmax[3], int step, int ceil_id);
 int esdf_sample_impl(FuelMap* m, int64_t n, const double* pos_dev, double* dist_dev, double* grad_dev);
-int edt_xy_dev_impl(cudaStream_t s, const uint8_t* occ, int nx, int ny, int nzl, int flags,
-                    int32_t* g2, int32_t* scratch);
-int edt_z_chunks_dev_impl(cudaStream_t s, const int32_t* g2c, int G, int nxl, int ny, int nzl,
-                          double res, float* out, int32_t* scratch);
 
 int fusion_input_impl(FuelMap* m, const float* pts_host, int stride, int n, const double cam[3], const FuelFusionParams* p,
                       int32_t lbmin[3], int32_t lbmax[3]);

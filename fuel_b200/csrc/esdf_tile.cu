@@ -106,9 +106,13 @@ __device__ __forceinline__ uint32_t site_bits4(uint32_t w, int mode) {
 // packs 32/LPR lines.  VEC: the word is two 16-byte loads (box z range a multiple of 32 voxels on a
 // 16-byte boundary); otherwise bytes are gathered with ballots, one line per warp.
 // ---------------------------------------------------------------------------------------
+// The z axis of a line may be split into chunks (z-sharded volume gathered from several ranks): word c lives
+// in chunk c / cw at occ + (c / cw) * chunk_stride, and a chunk holds nz voxels per line (cw = words per chunk;
+// one chunk with cw >= NW is the ordinary contiguous volume).
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256) zpack_kernel(const uint8_t* __restrict__ occ, uint2* __restrict__ rec, int ny,
-                                                    int nz, TBox b, int NW, int NYP, int lpr_log2) {
+                                                    int nz, TBox b, int NW, int NYP, int lpr_log2, int cw,
+                                                    int64_t chunk_stride) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nxb = b.hi[0] - b.lo[0] + 1, nyb = b.hi[1] - b.lo[1] + 1, nzb = b.hi[2] - b.lo[2] + 1;
@@ -125,7 +129,8 @@ __global__ void __launch_bounds__(256) zpack_kernel(const uint8_t* __restrict__ 
   uint32_t word = 0;
   if (VEC) {
     if (rvalid && c < NW) {
-      const uint4* src = reinterpret_cast<const uint4*>(occ + base + (c << 5));
+      const int g = c / cw;
+      const uint4* src = reinterpret_cast<const uint4*>(occ + g * chunk_stride + base + ((c - g * cw) << 5));
       const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
       word = site_bits4(v0.x, MODE) | (site_bits4(v0.y, MODE) << 4) | (site_bits4(v0.z, MODE) << 8) |
              (site_bits4(v0.w, MODE) << 12) | (site_bits4(v1.x, MODE) << 16) | (site_bits4(v1.y, MODE) << 20) |
@@ -134,7 +139,8 @@ __global__ void __launch_bounds__(256) zpack_kernel(const uint8_t* __restrict__ 
   } else {
     for (int k = 0; k < NW; ++k) {
       const int p = (k << 5) + lane;
-      const bool s = p < nzb && is_site(__ldg(occ + base + p), MODE);
+      const int g = k / cw;
+      const bool s = p < nzb && is_site(__ldg(occ + g * chunk_stride + base + p - ((int64_t)g * cw << 5)), MODE);
       const uint32_t mm = __ballot_sync(FULL, s);
       if (lane == k) word = mm;
     }
@@ -156,19 +162,20 @@ __global__ void __launch_bounds__(256) zpack_kernel(const uint8_t* __restrict__ 
 }
 
 template <int MODE>
-void launch_zpack(cudaStream_t st, const uint8_t* occ, uint2* rec, int ny, int nz, const TBox& b, int NW, int NYP) {
+void launch_zpack(cudaStream_t st, const uint8_t* occ, uint2* rec, int ny, int nz, const TBox& b, int NW, int NYP,
+                  int cw = 1 << 20, int64_t chunk_stride = 0) {
   const int nxb = b.hi[0] - b.lo[0] + 1, nyb = b.hi[1] - b.lo[1] + 1, nzb = b.hi[2] - b.lo[2] + 1;
   const int64_t base0 = ((int64_t)b.lo[0] * ny + b.lo[1]) * nz + b.lo[2];
-  const bool vec = (nzb % 32 == 0) && (nz % 16 == 0) && (base0 % 16 == 0);
+  const bool vec = (nzb % 32 == 0) && (nz % 16 == 0) && (base0 % 16 == 0) && (chunk_stride % 16 == 0);
   const int rows = nxb * nyb;
   if (vec) {
     int l2 = 0;
     while ((1 << l2) < NW) ++l2;
     const int rpw = 32 >> l2;  // lines per warp
     const int warps = (rows + rpw - 1) / rpw;
-    zpack_kernel<MODE, true><<<(warps + 7) / 8, 256, 0, st>>>(occ, rec, ny, nz, b, NW, NYP, l2);
+    zpack_kernel<MODE, true><<<(warps + 7) / 8, 256, 0, st>>>(occ, rec, ny, nz, b, NW, NYP, l2, cw, chunk_stride);
   } else {
-    zpack_kernel<MODE, false><<<(rows + 7) / 8, 256, 0, st>>>(occ, rec, ny, nz, b, NW, NYP, 5);
+    zpack_kernel<MODE, false><<<(rows + 7) / 8, 256, 0, st>>>(occ, rec, ny, nz, b, NW, NYP, 5, cw, chunk_stride);
   }
 }
 
@@ -181,11 +188,17 @@ struct TileParams {
   // input
   const uint2* rec;      // FROMBITS: records of (o, w0 + blockIdx.x) start at rec + (o*NW + w0 + bx)*NYP
   int NW, NYP, w0;
-  const int32_t* pin;    // !FROMBITS: the [n][32] tile of (o, bx) is contiguous at pin + (o*gridDim.x + bx)*n*32
+  // !FROMBITS: row q of the tile of (o, bx) at pin + o*in_o + bx*in_bx + (q / piece_rows)*piece_stride +
+  // (q % piece_rows)*32 (int32 units): rows are contiguous inside a piece (piece_rows is a multiple of the band
+  // length, or >= n for one piece)
+  const int32_t* pin;
+  int64_t in_o, in_bx, piece_stride;
+  int piece_rows;
   // output: sample q of lane l at out + out_base + o*out_o + bx*out_bx + q*out_q + l  (int32 or float)
   void* out;
   int64_t out_base, out_o, out_bx, out_q;
   int lanes_total;  // valid z positions counted from bx = 0 (lanes beyond are not stored when FINAL)
+  int discard_input;  // !FROMBITS: drop the tile's lines from L2 once they are in shared memory
   float res;
 };
 
@@ -283,19 +296,19 @@ __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TilePar
   } else {
     // the tile is contiguous in P (K1 writes it that way): every warp brings its own band in with ONE bulk copy
     if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned)n * 128u);
-    if (lane == 0 && j0 < n) {
-      const int32_t* src = p.pin + ((int64_t)o * gridDim.x + bx) * n * 32;
-      bulk_g2s(T + (size_t)j0 * 32, src + (size_t)j0 * 32, (unsigned)(min(n, j0 + M) - j0) * 128u, bar);
-    }
+    const int piece = j0 / p.piece_rows;
+    const int32_t* const bsrc = p.pin + (int64_t)o * p.in_o + (int64_t)bx * p.in_bx + (int64_t)piece * p.piece_stride +
+                                (int64_t)(j0 - piece * p.piece_rows) * 32;
+    if (lane == 0 && j0 < n)
+      bulk_g2s(T + (size_t)j0 * 32, bsrc, (unsigned)(min(n, j0 + M) - j0) * 128u, bar);
     if (band == 0) mbar_wait(bar, 0);
     __syncthreads();
     // the tile of P is dead once it sits in shared memory: drop its lines from L2 instead of letting them be
     // written back to HBM later (P is produced and consumed out of L2; only the fp32 result should reach DRAM)
-    {
-      const char* src = reinterpret_cast<const char*>(p.pin + ((int64_t)o * gridDim.x + bx) * n * 32);
-      for (int r = threadIdx.x; r < n; r += blockDim.x)
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(src + (size_t)r * 128) : "memory");
-    }
+    if (p.discard_input)
+      for (int r = lane; r < min(M, n - j0); r += 32)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<const char*>(bsrc) + (size_t)r * 128)
+                     : "memory");
   }
 
   // ---- phase 1: hull of the band's own 32 samples, in place --------------------------------
@@ -545,16 +558,16 @@ size_t tile_smem_bytes(int nb, int m, bool frombits) {
   return s;
 }
 
-int g_band_log2 = -1;  // FUELGPU_ESDF_BAND=32|64 overrides the default band length
+int g_band_log2 = -1;  // FUELGPU_ESDF_BAND=64 selects 64-sample bands (default 32)
 
 template <bool FROMBITS, bool FINAL>
 cudaError_t launch_tile(cudaStream_t st, TileParams p, int gx, int gy) {
   if (g_band_log2 < 0) {
     const char* e = getenv("FUELGPU_ESDF_BAND");
-    g_band_log2 = (e && atoi(e) == 32) ? 5 : 6;
+    g_band_log2 = (e && atoi(e) == 64) ? 6 : 5;  // 32 measured faster (more warps per tile: 0.66 vs 0.68 ms at 512^3)
   }
-  // bands of 64 samples halve the per-thread fixed work (hull joins, start search); short lines keep 32
-  const int logm = (p.n > 128 && g_band_log2 == 6) ? 6 : 5;
+  // bands of 64 samples halve the per-thread fixed work (hull joins, start search) but also the warps per tile
+  const int logm = (p.n > 128 && g_band_log2 == 6 && (FROMBITS || p.piece_rows % 64 == 0)) ? 6 : 5;
   const int m = 1 << logm;
   const int nb = (p.n + m - 1) / m;
   p.nb = nb;
@@ -665,6 +678,11 @@ int esdf_tile_transform(FuelMap* m, const int lo[3], const int hi[3], int mode, 
     memset(&p2, 0, sizeof(p2));
     p2.n = nxb;
     p2.pin = P;
+    p2.in_o = (int64_t)wn * nxb * 32;
+    p2.in_bx = (int64_t)nxb * 32;
+    p2.piece_rows = 1 << 20;
+    p2.piece_stride = 0;
+    p2.discard_input = 1;
     p2.out = out;
     p2.out_base = ((int64_t)lo[0] * ny + lo[1]) * nz + lo[2] + (int64_t)w0 * 32;
     p2.out_o = nz;
@@ -680,4 +698,66 @@ int esdf_tile_transform(FuelMap* m, const int lo[3], const int hi[3], int mode, 
     FUEL_CUDA(m, cudaStreamWaitEvent(s0, m->esdf_ev[1], 0));
   }
   return 0;
+}
+
+
+// ---- stage launchers for the sharded update (sharded.cu): explicit layouts, caller-owned buffers -------------
+// records of a [nxl][ny][G*nzc] volume whose z axis arrives as G chunks of nzc planes (chunk g at occ + g*chunk_stride)
+int edt_stage_zpack(cudaStream_t st, const uint8_t* occ, void* rec, int nxl, int ny, int nzc, int G, int64_t chunk_stride,
+                    int mode) {
+  TBox b;
+  b.lo[0] = b.lo[1] = b.lo[2] = 0;
+  b.hi[0] = nxl - 1;
+  b.hi[1] = ny - 1;
+  b.hi[2] = G * nzc - 1;
+  const int NW = (G * nzc + 31) / 32, NYP = (ny + 1) & ~1;
+  if (G > 1 && nzc % 32) return FUELGPU_EINVAL;
+  const int cw = G > 1 ? nzc / 32 : 1 << 20;
+  if (mode == 0)
+    launch_zpack<0>(st, occ, (uint2*)rec, ny, nzc, b, NW, NYP, cw, chunk_stride);
+  else if (mode == 1)
+    launch_zpack<1>(st, occ, (uint2*)rec, ny, nzc, b, NW, NYP, cw, chunk_stride);
+  else
+    launch_zpack<2>(st, occ, (uint2*)rec, ny, nzc, b, NW, NYP, cw, chunk_stride);
+  return cudaGetLastError() == cudaSuccess ? 0 : FUELGPU_ECUDA;
+}
+
+// zy tiles of words [w0, w0+wn) for all nxl planes; sample (x, y, w, lane) goes to P[x*out_o + (w-w0)*out_bx + y*out_q + lane]
+int edt_stage_zy(cudaStream_t st, const void* rec, int nxl, int ny, int NW, int w0, int wn, int32_t* P, int64_t out_o,
+                 int64_t out_bx, int64_t out_q) {
+  TileParams p1;
+  memset(&p1, 0, sizeof(p1));
+  p1.n = ny;
+  p1.rec = (const uint2*)rec;
+  p1.NW = NW;
+  p1.NYP = (ny + 1) & ~1;
+  p1.w0 = w0;
+  p1.out = P;
+  p1.out_o = out_o;
+  p1.out_bx = out_bx;
+  p1.out_q = out_q;
+  p1.lanes_total = 1 << 30;
+  return launch_tile<true, false>(st, p1, wn, nxl) == cudaSuccess ? 0 : FUELGPU_ECUDA;
+}
+
+// x tiles: grid (wn, ny); tile rows per TileParams (pieces); result in metres to out[y*out_o + w*out_bx + x*out_q + lane]
+int edt_stage_x(cudaStream_t st, const int32_t* P, int64_t in_o, int64_t in_bx, int64_t piece_stride, int piece_rows, int nx,
+                int ny, int wn, float* out, int64_t out_o, int64_t out_bx, int64_t out_q, int lanes_total, float res,
+                int discard) {
+  TileParams p2;
+  memset(&p2, 0, sizeof(p2));
+  p2.n = nx;
+  p2.pin = P;
+  p2.in_o = in_o;
+  p2.in_bx = in_bx;
+  p2.piece_stride = piece_stride;
+  p2.piece_rows = piece_rows;
+  p2.discard_input = discard;
+  p2.out = out;
+  p2.out_o = out_o;
+  p2.out_bx = out_bx;
+  p2.out_q = out_q;
+  p2.lanes_total = lanes_total;
+  p2.res = res;
+  return launch_tile<false, true>(st, p2, wn, ny) == cudaSuccess ? 0 : FUELGPU_ECUDA;
 }

@@ -1,22 +1,27 @@
 """z-sharded ESDF update across GPUs (BASELINE config 4; DESIGN.md "multi-GPU").
 
-One process per GPU, `torch.distributed` for the plumbing.  The map is sharded on z: rank r
-owns planes [r*nz/G, (r+1)*nz/G) of every (x,y) column, stored z-fastest like the reference
-(`address = x*ny*nzl + y*nzl + z`).  The squared EDT is separable and exact in integers, so
-the sweep order is free:
+One process per GPU.  The map is sharded on z: rank r owns planes [r*nz/G, (r+1)*nz/G) of every (x,y)
+column, stored z-fastest like the reference (`address = x*ny*nzl + y*nzl + z`, sdf_map.h:145-147).  The
+squared EDT is separable and exact in integers, so every sweep may run where its lines are whole:
 
-  1. x and y sweeps on the local z-slab           (fuelgpu_edt_xy_dev; never cross z)
-  2. ONE all-to-all: z-slabs -> x-slabs of the 2-D partial (int32).  x is the slowest axis, so
-     the block a rank sends to rank s is the contiguous chunk g2[s*nx/G:(s+1)*nx/G].
-  3. z sweep over whole columns assembled from the G received chunks, writes metres
-     (fuelgpu_edt_z_chunks_dev).  The result is x-sharded: a contiguous chunk of the full volume.
-  4. optional all-gather: every rank gets the full ESDF (what the trajectory batch samples).
+  1. all-to-all of the occupancy byte: z-slabs -> x-slabs (rank r gets whole z lines of its x range)
+  2. z records + zy tiles on the x-slab
+  3. THE exchange of the 2-D partial (int32): x-slabs -> z-slabs, round by round beside step 2
+  4. x tiles on the own z-slab -> this rank's z-slab of distance_buffer_ (metres)
+  5. optional all-gather: every rank gets the full ESDF (what a trajectory batch split over ranks samples)
+
+The product path is `fuelgpu_sharded_esdf_*` of the C ABI (fuel_b200/csrc/sharded.cu): NCCL is called from
+inside the library, this module only bootstraps the communicator (the 128-byte NCCL id travels over
+torch.distributed) and wraps device tensors.  `stage_fns=(zy_fn, x_fn)` replaces the device stages by
+caller-supplied ones and the NCCL exchanges by torch.distributed collectives, so that the sharding logic
+(slab shapes, both exchanges, the all-gather) is exercised by a world-size-2 gloo test on CPU.
 
 Replaces nothing in the reference (FUEL is single-process); it is the multi-GPU form of
 SDFMap::updateESDF3d (plan_env/src/sdf_map.cpp:152-241) over the whole map.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -25,56 +30,53 @@ from . import _lib
 EDT_INF = _lib.EDT_INF
 
 
-def _gpu_xy(occ_slab, optimistic):
-    """int32 squared 2-D distance of a [nx,ny,nzl] uint8 occupancy slab (device tensor)."""
-    nx, ny, nzl = occ_slab.shape
-    g2 = torch.empty((nx, ny, nzl), dtype=torch.int32, device=occ_slab.device)
-    scratch = torch.empty((2, nx, ny, nzl), dtype=torch.int32, device=occ_slab.device)
-    st = torch.cuda.current_stream(occ_slab.device).cuda_stream
-    rc = _lib.lib().fuelgpu_edt_xy_dev(C.c_void_p(st), C.c_void_p(occ_slab.data_ptr()), nx, ny, nzl,
-                                       _lib.ESDF_OPTIMISTIC if optimistic else 0,
-                                       C.c_void_p(g2.data_ptr()), C.c_void_p(scratch.data_ptr()))
-    _lib.check(rc)
-    return g2
+class Comm:
+    """FuelComm (an NCCL communicator owned by libfuelgpu) bootstrapped over a torch.distributed group."""
+
+    def __init__(self, device, group=None):
+        self.group = group
+        self.nranks = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = int(device)
+        L = _lib.lib()
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            _lib.check(L.fuelgpu_comm_get_unique_id(_lib.ptr(uid)))
+        t = torch.from_numpy(uid)
+        if dist.get_backend(group) == "nccl":
+            t = t.to("cuda:%d" % self.device)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = t.cpu().numpy().copy()
+        h = C.c_void_p()
+        _lib.check(L.fuelgpu_comm_init(self.nranks, self.rank, _lib.ptr(uid), self.device, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            _lib.lib().fuelgpu_comm_destroy(self.handle)
+            self.handle = None
 
 
-def _gpu_z(chunks, resolution):
-    """[G,nxl,ny,nzl] int32 chunks -> [nxl,ny,G*nzl] float32 metres."""
-    G, nxl, ny, nzl = chunks.shape
-    out = torch.empty((nxl, ny, G * nzl), dtype=torch.float32, device=chunks.device)
-    scratch = torch.empty((2, nxl, ny, G * nzl), dtype=torch.int32, device=chunks.device)
-    st = torch.cuda.current_stream(chunks.device).cuda_stream
-    rc = _lib.lib().fuelgpu_edt_z_chunks_dev(C.c_void_p(st), C.c_void_p(chunks.data_ptr()), G, nxl, ny, nzl,
-                                             float(resolution), C.c_void_p(out.data_ptr()),
-                                             C.c_void_p(scratch.data_ptr()))
-    _lib.check(rc)
-    return out
-
-
-def exchange_z_to_x(g2, group=None):
-    """The single exchange step: [nx,ny,nzl] (my z-slab, all x) -> [G,nx/G,ny,nzl] (my x-range, the
-    z-slab of every rank).  NCCL: one all_to_all_single.  gloo (CPU tests): all_gather + slice,
-    same result."""
+def _all_to_all_blocks(blocks, group=None):
+    """blocks[d] goes to rank d; returns the list received (index = source rank).  all_to_all on NCCL,
+    all_gather + pick on gloo (CPU tests)."""
     G = dist.get_world_size(group)
     r = dist.get_rank(group)
-    nx, ny, nzl = g2.shape
-    if nx % G:
-        raise ValueError("nx must be divisible by the world size")
-    nxl = nx // G
-    send = g2.contiguous().view(G, nxl, ny, nzl)
+    blocks = [b.contiguous() for b in blocks]
     if dist.get_backend(group) == "nccl":
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
-        return recv
-    parts = [torch.empty_like(g2) for _ in range(G)]
-    dist.all_gather(parts, g2.contiguous(), group=group)
-    return torch.stack([p.view(G, nxl, ny, nzl)[r] for p in parts], dim=0)
+        out = [torch.empty_like(blocks[s]) for s in range(G)]
+        dist.all_to_all(out, blocks, group=group)
+        return out
+    packed = torch.stack(blocks, dim=0)
+    parts = [torch.empty_like(packed) for _ in range(G)]
+    dist.all_gather(parts, packed, group=group)
+    return [parts[s][r] for s in range(G)]
 
 
 class ShardedESDF:
-    def __init__(self, voxel_num, resolution, optimistic=True, group=None, xy_fn=None, z_fn=None):
-        """xy_fn / z_fn default to the CUDA entry points; tests inject CPU stand-ins to exercise the
-        sharding logic over gloo."""
+    def __init__(self, voxel_num, resolution, optimistic=True, group=None, device=None, stage_fns=None):
+        """stage_fns = (zy_fn, x_fn): zy_fn(occ[nxl,ny,nz] uint8) -> int32 squared 2-D distance [nxl,ny,nz]
+        (EDT_INF = none); x_fn(partial[nx,ny,nzl] int32) -> float32 metres.  Default: the CUDA path."""
         self.n = tuple(int(v) for v in voxel_num)
         self.res = float(resolution)
         self.optimistic = bool(optimistic)
@@ -85,8 +87,26 @@ class ShardedESDF:
             raise ValueError("nx and nz must be divisible by the world size")
         self.nzl = self.n[2] // self.G
         self.nxl = self.n[0] // self.G
-        self.xy_fn = xy_fn or (lambda occ: _gpu_xy(occ, self.optimistic))
-        self.z_fn = z_fn or (lambda ch: _gpu_z(ch, self.res))
+        self.stage_fns = stage_fns
+        self.handle = None
+        self.comm = None
+        if stage_fns is None:
+            if device is None:
+                device = torch.cuda.current_device()
+            self.device = int(device)
+            self.comm = Comm(self.device, group)
+            h = C.c_void_p()
+            n3 = (C.c_int32 * 3)(*self.n)
+            _lib.check(_lib.lib().fuelgpu_sharded_esdf_create(self.comm.handle, n3, self.res, C.byref(h)))
+            self.handle = h
+
+    def close(self):
+        if self.handle:
+            _lib.lib().fuelgpu_sharded_esdf_destroy(self.handle)
+            self.handle = None
+        if self.comm:
+            self.comm.close()
+            self.comm = None
 
     def z_range(self, rank=None):
         r = self.rank if rank is None else rank
@@ -101,26 +121,60 @@ class ShardedESDF:
         z0, z1 = self.z_range()
         return occ_full[:, :, z0:z1].contiguous()
 
-    def update(self, occ_slab):
-        """occ_slab: [nx,ny,nzl] uint8 (bits0-1 tri-state, bit2 inflate).  Returns this rank's x-slab of
-        distance_buffer_: [nxl,ny,nz] float32 metres (+inf where the map has no site)."""
+    def update(self, occ_slab, out=None):
+        """occ_slab: [nx,ny,nzl] uint8 (bits0-1 tri-state, bit2 inflate).  Returns this rank's z-slab of
+        distance_buffer_: [nx,ny,nzl] float32 metres (+inf where the map has no site)."""
         if tuple(occ_slab.shape) != (self.n[0], self.n[1], self.nzl):
             raise ValueError("occupancy slab must be [nx,ny,nz/G]")
-        g2 = self.xy_fn(occ_slab)
-        chunks = exchange_z_to_x(g2, self.group)
-        return self.z_fn(chunks)
+        if self.stage_fns is not None:
+            return self._update_host(occ_slab)
+        if out is None:
+            out = torch.empty((self.n[0], self.n[1], self.nzl), dtype=torch.float32, device=occ_slab.device)
+        st = torch.cuda.current_stream(occ_slab.device).cuda_stream
+        rc = _lib.lib().fuelgpu_sharded_esdf_update(self.handle, C.c_void_p(st), C.c_void_p(occ_slab.data_ptr()),
+                                                    _lib.ESDF_OPTIMISTIC if self.optimistic else 0,
+                                                    C.c_void_p(out.data_ptr()))
+        _lib.check(rc)
+        return out
 
-    def gather_full(self, dist_xslab):
-        """all-gather the x-slabs: every rank gets the full [nx,ny,nz] ESDF (x is the slowest axis, so
-        the gathered buffer IS the full volume)."""
-        full = torch.empty((self.n[0], self.n[1], self.n[2]), dtype=dist_xslab.dtype, device=dist_xslab.device)
-        dist.all_gather_into_tensor(full.view(-1), dist_xslab.contiguous().view(-1), group=self.group) \
-            if dist.get_backend(self.group) == "nccl" else self._gather_gloo(full, dist_xslab)
-        return full
+    def last_timing(self):
+        """device ms of the last update on this rank: occupancy exchange, records + zy tiles (partial exchange
+        beside them), wait for the last rounds, x tiles, total"""
+        ms = (C.c_float * 5)()
+        _lib.check(_lib.lib().fuelgpu_sharded_esdf_last_timing(self.handle, ms))
+        return dict(zip(("occ_exchange", "zy", "exchange_wait", "x", "total"), [float(v) for v in ms]))
 
-    def _gather_gloo(self, full, part):
-        parts = [torch.empty_like(part) for _ in range(self.G)]
-        dist.all_gather(parts, part.contiguous(), group=self.group)
-        for r, p in enumerate(parts):
-            x0, x1 = self.x_range(r)
-            full[x0:x1] = p
+    def bytes_exchanged(self):
+        return int(_lib.lib().fuelgpu_sharded_esdf_bytes_exchanged(self.handle))
+
+    # ---- host-orchestrated twin (CPU tests): same decomposition, torch.distributed collectives ----
+    def _update_host(self, occ_slab):
+        zy_fn, x_fn = self.stage_fns
+        G = self.G
+        nx, ny, nz = self.n
+        # 1. occupancy z-slabs -> x-slabs
+        got = _all_to_all_blocks([occ_slab[d * self.nxl:(d + 1) * self.nxl] for d in range(G)], self.group)
+        occ_x = torch.cat(got, dim=2)  # [nxl, ny, nz]: z lines assembled from the G chunks
+        assert tuple(occ_x.shape) == (self.nxl, ny, nz)
+        # 2. zy stage on the x-slab
+        part = zy_fn(occ_x)
+        # 3. partial x-slabs -> z-slabs
+        got = _all_to_all_blocks([part[:, :, d * self.nzl:(d + 1) * self.nzl] for d in range(G)], self.group)
+        part_z = torch.cat(got, dim=0)  # [nx, ny, nzl]
+        assert tuple(part_z.shape) == (nx, ny, self.nzl)
+        # 4. x stage on the z-slab
+        return x_fn(part_z)
+
+    def gather_full(self, dist_zslab):
+        """all-gather the z-slabs: every rank gets the full [nx,ny,nz] ESDF."""
+        nx, ny, nz = self.n
+        if self.stage_fns is None:
+            buf = torch.empty((self.G, nx, ny, self.nzl), dtype=torch.float32, device=dist_zslab.device)
+            st = torch.cuda.current_stream(dist_zslab.device).cuda_stream
+            _lib.check(_lib.lib().fuelgpu_sharded_esdf_allgather(self.handle, C.c_void_p(st),
+                                                                 C.c_void_p(dist_zslab.contiguous().data_ptr()),
+                                                                 C.c_void_p(buf.data_ptr())))
+            return buf.permute(1, 2, 0, 3).reshape(nx, ny, nz)
+        parts = [torch.empty_like(dist_zslab) for _ in range(self.G)]
+        dist.all_gather(parts, dist_zslab.contiguous(), group=self.group)
+        return torch.cat(parts, dim=2)

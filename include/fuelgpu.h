@@ -318,7 +318,13 @@ typedef struct {
   int32_t max_eval; /* max_iteration_num_[id]  (algorithm.xml:184-187) */
   int32_t lbfgs_m;  /* history pairs, <= 8                              */
   double xtol_rel;  /* 1e-5 (bspline_optimizer.cpp:173)                 */
+  int32_t flags;    /* FUELGPU_SOLVE_*                                   */
+  int32_t reserved;
 } FuelSolveParams;
+/* keep evaluating until max_eval is reached: a failed line search restarts from steepest descent and a vanished
+ * gradient re-evaluates in place (benchmark mode: exactly B x max_eval combineCost evaluations, like a CPU run that
+ * calls the objective max_eval times) */
+#define FUELGPU_SOLVE_EXACT_EVALS 1
 FUELGPU_API int fuelgpu_bspline_optimize_batch(FuelMap* map, int32_t B, int32_t n_pts, int32_t cost_mask,
                                    const FuelOptParams* params, const FuelTrajConst* traj,
                                    const FuelSolveParams* solve, double* x, double* f_best,
@@ -337,18 +343,36 @@ FUELGPU_API int fuelgpu_bspline_optimize_batch_dev(FuelMap* map, int32_t B, int3
                                        const FuelSolveParams* solve, void* x_dev, void* f_best_dev,
                                        void* n_eval_dev);
 
-/* ---- multi-GPU building blocks (z-sharded ESDF, DESIGN.md "multi-GPU") --------------
- * These operate on caller-owned DEVICE buffers so that torch.distributed/NCCL can move
- * them between ranks.  A slab is nx*ny*nzl voxels, z fastest.
- * xy passes: occupancy byte slab -> squared 2-D distance (int32, FUELGPU_EDT_INF = none)
- * z pass   : G received chunks [G][nxl][ny][nzl] -> float32 metres [nxl][ny][G*nzl]
- * scratch  : xy: 2*nx*ny*nzl int32;  z: 2*nxl*ny*(G*nzl) int32                               */
+/* ---- multi-GPU: the z-sharded ESDF update (BASELINE config 4) ---------------------------
+ * Multi-GPU form of SDFMap::updateESDF3d (plan_env/src/sdf_map.cpp:152-241) over the whole map.  One process
+ * (or thread) per GPU; rank r owns planes [r*nz/G, (r+1)*nz/G) of every (x,y) column, z fastest like the
+ * reference (sdf_map.h:145-147).  NCCL is called from inside the library (bound at run time with dlopen, no
+ * link-time dependency).  Bootstrap like any NCCL application: rank 0 calls fuelgpu_comm_get_unique_id, the
+ * host program ships the 128 bytes to the other ranks (ROS topic, MPI, torch.distributed, a file), every rank
+ * calls fuelgpu_comm_init.  nx and nz must be multiples of 32 * ranks. */
+typedef struct FuelComm FuelComm;
+typedef struct FuelShardedEsdf FuelShardedEsdf;
+FUELGPU_API int fuelgpu_comm_get_unique_id(uint8_t id[128]);
+FUELGPU_API int fuelgpu_comm_init(int32_t nranks, int32_t rank, const uint8_t id[128], int32_t device_id, FuelComm** out);
+FUELGPU_API int fuelgpu_comm_info(const FuelComm* comm, int32_t* nranks, int32_t* rank);
+FUELGPU_API int fuelgpu_comm_destroy(FuelComm* comm);
+FUELGPU_API int fuelgpu_sharded_esdf_create(FuelComm* comm, const int32_t n[3], double resolution, FuelShardedEsdf** out);
+/* occ_slab_dev: [nx][ny][nz/G] occupancy byte of this rank (bits0-1 tri-state, bit2 inflate, as the resident
+ * byte of a FuelMap); dist_slab_dev: [nx][ny][nz/G] float32 metres out (+inf where the map has no site).
+ * flags: FUELGPU_ESDF_OPTIMISTIC or 0.  Collective: every rank of the communicator must call it.  Enqueued on
+ * cuda_stream (plus an internal stream for the exchange rounds); returns without waiting. */
+FUELGPU_API int fuelgpu_sharded_esdf_update(FuelShardedEsdf* s, void* cuda_stream, const void* occ_slab_dev, int flags,
+                                            void* dist_slab_dev);
+/* device times (ms) of the last update on this rank: [0] occupancy exchange, [1] z records + zy tiles (the
+ * exchange rounds of the 2-D partial overlap them), [2] wait for the last rounds, [3] x tiles, [4] total */
+FUELGPU_API int fuelgpu_sharded_esdf_last_timing(FuelShardedEsdf* s, float ms[5]);
+FUELGPU_API int64_t fuelgpu_sharded_esdf_bytes_exchanged(const FuelShardedEsdf* s);
+/* every rank gets all z-slabs: out_dev [G][nx][ny][nz/G] float32 (what a trajectory batch split over the ranks
+ * samples) */
+FUELGPU_API int fuelgpu_sharded_esdf_allgather(FuelShardedEsdf* s, void* cuda_stream, const void* dist_slab_dev,
+                                               void* out_dev);
+FUELGPU_API int fuelgpu_sharded_esdf_destroy(FuelShardedEsdf* s);
 #define FUELGPU_EDT_INF 0x3fffffff
-FUELGPU_API int fuelgpu_edt_xy_dev(void* cuda_stream, const void* occ_slab, int32_t nx, int32_t ny,
-                       int32_t nzl, int flags, void* g2_out_i32, void* scratch_i32);
-FUELGPU_API int fuelgpu_edt_z_chunks_dev(void* cuda_stream, const void* g2_chunks_i32, int32_t G, int32_t nxl,
-                             int32_t ny, int32_t nzl, double resolution, void* dist_out_f32,
-                             void* scratch_i32);
 
 /* Library / device info.  Fills name with the device name; returns the SM count or <0. */
 FUELGPU_API int fuelgpu_device_info(int device_id, char* name, int name_len, int* cc_major, int* cc_minor);

@@ -1,6 +1,6 @@
-"""world_size-2 gloo test (CPU) of the z-sharded ESDF orchestration in fuel_b200/dist.py: slab
-shapes, the single z->x exchange, chunk assembly and the final all-gather.  The two CUDA
-entry points are replaced by CPU stand-ins (exact integer EDT passes in numpy) so that the
+"""world_size-2 gloo test (CPU) of the z-sharded ESDF decomposition in fuel_b200/dist.py: slab shapes, the
+occupancy exchange (z-slabs -> x-slabs), the exchange of the 2-D partial (x-slabs -> z-slabs), and the final
+all-gather.  The device stages are replaced by CPU stand-ins (exact integer EDT passes in numpy) so that the
 N>1 host logic is exercised without a GPU; the result must equal the oracle's full-map ESDF."""
 import os
 import socket
@@ -27,23 +27,24 @@ def edt1d_sq(f):
     return np.where(out >= (np.int64(1) << 39), INF, out).reshape(f.shape)
 
 
-def cpu_xy(occ):
+def cpu_zy(occ):
+    """z then y sweep on an x-slab [nxl, ny, nz]: squared 2-D distance in every x plane"""
     o = occ.numpy()
     site = (o & 4) != 0  # optimistic: inflate bit
     f = np.where(site, 0, INF).astype(np.int64)
     nx, ny, nz = f.shape
-    g = edt1d_sq(np.moveaxis(f, 1, 0).reshape(ny, -1)).reshape(ny, nx, nz)
+    g = edt1d_sq(np.moveaxis(f, 2, 0).reshape(nz, -1)).reshape(nz, nx, ny)
+    g = np.moveaxis(g, 0, 2)
+    g = edt1d_sq(np.moveaxis(g, 1, 0).reshape(ny, -1)).reshape(ny, nx, nz)
     g = np.moveaxis(g, 0, 1)
-    g = edt1d_sq(g.reshape(nx, -1)).reshape(nx, ny, nz)
     return torch.from_numpy(g.astype(np.int32))
 
 
-def cpu_z(chunks, res):
-    c = chunks.numpy().astype(np.int64)
-    G, nxl, ny, nzl = c.shape
-    col = np.concatenate([c[s] for s in range(G)], axis=2)  # [nxl, ny, nz]
-    g = edt1d_sq(np.moveaxis(col, 2, 0).reshape(G * nzl, -1)).reshape(G * nzl, nxl, ny)
-    g = np.moveaxis(g, 0, 2)
+def cpu_x(part, res):
+    """x sweep on a z-slab [nx, ny, nzl] of the 2-D partial -> metres"""
+    c = part.numpy().astype(np.int64)
+    nx, ny, nzl = c.shape
+    g = edt1d_sq(c.reshape(nx, -1)).reshape(nx, ny, nzl)
     out = np.where(g >= INF, np.inf, res * np.sqrt(g.astype(np.float64)))
     return torch.from_numpy(out.astype(np.float32))
 
@@ -57,12 +58,12 @@ def worker(rank, world, port, n, ret):
     rng = np.random.default_rng(5)  # same map on every rank
     inflate = (rng.random(n) < 0.01).astype(np.uint8)
     occ = torch.from_numpy((inflate << 2) | 1)
-    sh = ShardedESDF(n, 0.1, optimistic=True, xy_fn=cpu_xy, z_fn=lambda ch: cpu_z(ch, 0.1))
+    sh = ShardedESDF(n, 0.1, optimistic=True, stage_fns=(cpu_zy, lambda p: cpu_x(p, 0.1)))
     assert sh.z_range() == (rank * n[2] // world, (rank + 1) * n[2] // world)
     slab = sh.shard_occupancy(occ)
     assert slab.shape == (n[0], n[1], n[2] // world) and slab.is_contiguous()
     part = sh.update(slab)
-    assert part.shape == (n[0] // world, n[1], n[2])
+    assert part.shape == (n[0], n[1], n[2] // world)
     full = sh.gather_full(part)
     ret[rank] = full.numpy()
     dist.destroy_process_group()
