@@ -440,13 +440,13 @@ class GpuPlanner:
         m.download(wait=not self.overlap)  # overlap: the D2H mirror copy runs beside the solver
         if self.overlap:
             # solver enqueued; the frontier result is marshalled on the host while it runs
-            self.opt.optimizeBatchBegin(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0)
+            self.opt.optimizeBatchBegin(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0, exact_evals=True)
             out = self.ff.search_box_end()
             x, f, ne = self.opt.optimizeBatchEnd(out=self.opt_out)
             m.synchronize()  # ESDF host mirror complete
         else:
             x, f, ne = self.opt.optimizeBatch(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0,
-                                              out=self.opt_out)
+                                              out=self.opt_out, exact_evals=True)
         self.last_neval = ne
         return out, f
 

@@ -12,7 +12,9 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import (MAX_PTS, FuelOptParams, FuelSolveParams, FuelTrajConst, check, lib, ptr)
+from ._lib import (MAX_PTS, SOLVE_EXACT_EVALS, FuelOptParams, FuelSolveParams, FuelTrajConst, check, lib, ptr)
+
+COST_FAST_EVAL = 1 << 30
 
 
 class BsplineOptimizer:
@@ -148,8 +150,9 @@ class BsplineOptimizer:
         return 3 * n_pts + (1 if mask & self.MINTIME else 0)
 
     # ---- cost / gradient --------------------------------------------------------------------
-    def combineCostBatch(self, x, traj_consts, n_pts, cost_function=None):
-        """combineCost (:518-647) for x [B, nvar]; returns (f [B], grad [B, nvar])."""
+    def combineCostBatch(self, x, traj_consts, n_pts, cost_function=None, fast_eval=False):
+        """combineCost (:518-647) for x [B, nvar]; returns (f [B], grad [B, nvar]).  fast_eval=True evaluates with
+        the solver loop's evaluator (FUELGPU_COST_FAST_EVAL): what optimizeBatch runs K times per trajectory."""
         mask = self.cost_function_ if cost_function is None else int(cost_function)
         x = np.ascontiguousarray(x, dtype=np.float64)
         B = x.shape[0]
@@ -159,11 +162,12 @@ class BsplineOptimizer:
         f = np.empty(B, dtype=np.float64)
         g = np.empty((B, nvar), dtype=np.float64)
         h = self.edt_environment_.sdf_map_.handle
-        check(lib().fuelgpu_bspline_cost_batch(h, B, n_pts, mask, C.byref(self.params_), traj_consts, ptr(x),
-                                               ptr(f), ptr(g)), h)
+        check(lib().fuelgpu_bspline_cost_batch(h, B, n_pts, mask | (COST_FAST_EVAL if fast_eval else 0),
+                                               C.byref(self.params_), traj_consts, ptr(x), ptr(f), ptr(g)), h)
         return f, g
 
-    def optimizeBatch(self, x, traj_consts, n_pts, cost_function, max_eval, lbfgs_m=6, xtol_rel=1e-5, out=None):
+    def optimizeBatch(self, x, traj_consts, n_pts, cost_function, max_eval, lbfgs_m=6, xtol_rel=1e-5, out=None,
+                      exact_evals=False):
         """The solver loop of optimize() (:165-253) for B trajectories in one persistent kernel.
         x [B, nvar] initial variables (clamped to the box shrunk by 0.1 m on the device, :196-204).
         Returns (x_best [B, nvar], f_best [B], n_eval [B]); `out` = a tuple of such arrays to reuse (like
@@ -180,12 +184,14 @@ class BsplineOptimizer:
         x = xw
         sp = FuelSolveParams()
         sp.max_eval, sp.lbfgs_m, sp.xtol_rel = int(max_eval), int(lbfgs_m), float(xtol_rel)
+        sp.flags = SOLVE_EXACT_EVALS if exact_evals else 0
         h = self.edt_environment_.sdf_map_.handle
         check(lib().fuelgpu_bspline_optimize_batch(h, B, n_pts, mask, C.byref(self.params_), traj_consts,
                                                    C.byref(sp), ptr(x), ptr(fb), ptr(ne)), h)
         return x, fb, ne
 
-    def optimizeBatchBegin(self, x, traj_consts, n_pts, cost_function, max_eval, lbfgs_m=6, xtol_rel=1e-5):
+    def optimizeBatchBegin(self, x, traj_consts, n_pts, cost_function, max_eval, lbfgs_m=6, xtol_rel=1e-5,
+                           exact_evals=False):
         """First half of optimizeBatch: stage the inputs and enqueue the solver, return at once
         (fuelgpu_bspline_optimize_batch_begin).  Collect with optimizeBatchEnd()."""
         mask = int(cost_function)
@@ -194,6 +200,7 @@ class BsplineOptimizer:
             raise ValueError("x must be [B, %d]" % self.nvar(n_pts, mask))
         sp = FuelSolveParams()
         sp.max_eval, sp.lbfgs_m, sp.xtol_rel = int(max_eval), int(lbfgs_m), float(xtol_rel)
+        sp.flags = SOLVE_EXACT_EVALS if exact_evals else 0
         h = self.edt_environment_.sdf_map_.handle
         check(lib().fuelgpu_bspline_optimize_batch_begin(h, x.shape[0], n_pts, mask, C.byref(self.params_), traj_consts,
                                                          C.byref(sp), ptr(x)), h)

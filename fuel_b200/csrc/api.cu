@@ -38,7 +38,7 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restri
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = in[i];
-  out[i] = isinf(v) ? inf_value : (double)v;
+  out[i] = isinf(v) ? (v > 0 ? inf_value : -inf_value) : (double)v;
 }
 
 __global__ void clear_flags_kernel(int8_t* flag, const int* __restrict__ addr, int n) {
@@ -312,6 +312,7 @@ static int upload_occupancy_impl(FuelMap* m, const int8_t* inflate, const double
   const size_t inf_bytes = ((size_t)cnt + 7) & ~(size_t)7;  // keeps the fp64 region 8-byte aligned
   rc = ensure_stage(m, inf_bytes + (size_t)cnt * (logodds ? 8 : 1));
   if (rc) return rc;
+  frontier_order_writer(m);
   tbegin(m, T_UPLOAD);
   int8_t* d_inf = (int8_t*)m->stage;
   FUEL_CUDA(m, cudaMemcpyAsync(d_inf, inflate + off, cnt, cudaMemcpyHostToDevice, m->stream));
@@ -362,6 +363,7 @@ int fuelgpu_map_inflate(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3]
   int rc = check_box(m, bmin, bmax, lo, hi);
   if (rc) return rc;
   FUEL_CUDA(m, cudaSetDevice(m->dev));
+  frontier_order_writer(m);
   return map_inflate_impl(m, lo, hi, inf_step, virtual_ceil_idx);
 }
 
@@ -377,6 +379,7 @@ int fuelgpu_map_input_point_cloud(FuelMap* m, const float* points, int32_t point
     if (!(v > 0.0 && v < 1.0)) return fuel_fail(m, FUELGPU_EINVAL, "fusion probabilities must lie in (0,1)");
   if (!(p->max_ray_length > 0.0)) return fuel_fail(m, FUELGPU_EINVAL, "max_ray_length must be positive");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
+  frontier_order_writer(m);
   return fusion_input_impl(m, points, point_stride, point_num, camera_pos, p, local_bound_min, local_bound_max);
 }
 
@@ -393,6 +396,7 @@ int fuelgpu_map_input_depth_image(FuelMap* m, const uint16_t* depth, int32_t row
     if (!(v > 0.0 && v < 1.0)) return fuel_fail(m, FUELGPU_EINVAL, "fusion probabilities must lie in (0,1)");
   if (!(p->max_ray_length > 0.0)) return fuel_fail(m, FUELGPU_EINVAL, "max_ray_length must be positive");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
+  frontier_order_writer(m);
   return fusion_input_depth_impl(m, depth, rows, cols, c, camera_R, camera_pos, p, local_bound_min, local_bound_max,
                                  proj_points_cnt);
 }
@@ -407,6 +411,7 @@ int fuelgpu_map_set_logodds(FuelMap* m, const double* logodds, double p_min, dou
   if (!m || !logodds) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   if (!(p_min > 0.0 && p_min < 1.0 && p_occ > 0.0 && p_occ < 1.0)) return fuel_fail(m, FUELGPU_EINVAL, "probability out of (0,1)");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
+  frontier_order_writer(m);
   return fusion_set_logodds(m, logodds, p_min, p_occ);
 }
 
@@ -687,6 +692,8 @@ int fuelgpu_bspline_cost_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mas
   if (rc) return rc;
   if (B == 0) return 0;
   if (!traj || !x || !f || !grad) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (m->bs_pend_B)  // the pending solve owns the device scratch and the pinned result block
+    return fuel_fail(m, FUELGPU_EINVAL, "fuelgpu_bspline_optimize_batch_begin is outstanding: call _end first");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
   const int nvar = (mask & FUELGPU_MINTIME) ? 3 * n_pts + 1 : 3 * n_pts;
   const size_t tcb = sizeof(FuelTrajConst) * (size_t)B;

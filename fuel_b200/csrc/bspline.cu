@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(64) cost_batch_thread_kernel(Geom g, const flo
 
 
 
+// FAST = the evaluator instantiation the solver loop runs (fp32 lerps, reciprocals, one merged reduction);
+// reachable through FUELGPU_COST_FAST_EVAL so that the parity tests cover exactly what the benchmark times.
+template <bool FAST>
 __global__ void __launch_bounds__(WPB * 32) cost_batch_warp_kernel(
     Geom g, const float* __restrict__ dist, FuelOptParams p, const FuelTrajConst* __restrict__ tc, int n,
     int mask, int B, const double* __restrict__ x, double* __restrict__ f, double* __restrict__ grad) {
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(WPB * 32) cost_batch_warp_kernel(
   }
   const double dt = opt_time ? xb[nvar - 1] : t.knot_span;
   double fo, gr[3], gdt;
-  eval_warp<false>(g, dist, p, t, tc + b, n, mask, q, dt, lane, fo, gr, gdt);
+  eval_warp<FAST>(g, dist, p, t, tc + b, n, mask, q, dt, lane, fo, gr, gdt);
   double* gb = grad + (int64_t)b * nvar;
   if (lane < n) {
     gb[3 * lane] = gr[0];
@@ -300,9 +303,16 @@ int bspline_cost_batch_dev_impl(FuelMap* m, int B, int n_pts, int mask, const Fu
                                 const FuelTrajConst* tc_dev, const double* x_dev, double* f_dev,
                                 double* grad_dev) {
   if (B <= 0) return 0;
-  if (n_pts <= 32) {
-    cost_batch_warp_kernel<<<(B + WPB - 1) / WPB, WPB * 32, 0, m->stream>>>(m->g, m->dist, *p, tc_dev, n_pts,
-                                                                        mask, B, x_dev, f_dev, grad_dev);
+  const bool fast = (mask & FUELGPU_COST_FAST_EVAL) != 0;
+  mask &= ~FUELGPU_COST_FAST_EVAL;
+  if (fast && n_pts > 32)
+    return fuel_fail(m, FUELGPU_EUNSUPPORTED, "FUELGPU_COST_FAST_EVAL needs n_pts <= 32 (the solver's evaluator)");
+  if (fast) {
+    cost_batch_warp_kernel<true><<<(B + WPB - 1) / WPB, WPB * 32, 0, m->stream>>>(m->g, m->dist, *p, tc_dev, n_pts,
+                                                                              mask, B, x_dev, f_dev, grad_dev);
+  } else if (n_pts <= 32) {
+    cost_batch_warp_kernel<false><<<(B + WPB - 1) / WPB, WPB * 32, 0, m->stream>>>(m->g, m->dist, *p, tc_dev, n_pts,
+                                                                               mask, B, x_dev, f_dev, grad_dev);
   } else {
     cost_batch_thread_kernel<<<(B + 63) / 64, 64, 0, m->stream>>>(m->g, m->dist, *p, tc_dev, n_pts, mask, B,
                                                                   x_dev, f_dev, grad_dev);

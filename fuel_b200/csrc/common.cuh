@@ -121,6 +121,8 @@ int fusion_set_logodds(FuelMap* m, const double* logodds_host, double p_min, dou
 int fusion_get_logodds(FuelMap* m, double* out);
 void fusion_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int reset);
 void fusion_state_destroy(FuelMap* m);
+double* fusion_logodds_ptr(FuelMap* m, double* clamp_max_log);
+void frontier_order_writer(FuelMap* m);  // main-stream writers of `occ` wait for an enqueued frontier search
 
 int ensure_fr_scratch(FuelMap* m, size_t bytes);
 int frontier_state_create(FuelMap* m);
@@ -160,7 +162,7 @@ __device__ __forceinline__ double dev_get_distance(const Geom& g, const float* _
   // "no site in the box" is +inf on the device; the reference holds resolution*sqrt(DBL_MAX)
   // there (sdf_map.cpp:196 on a DBL_MAX line).  Restore that finite value so the trilinear
   // arithmetic (inf-inf) matches the reference's.
-  if (isinf(v)) return g.res * sqrt(1.7976931348623157e308);
+  if (isinf(v)) return v > 0 ? g.res * sqrt(1.7976931348623157e308) : -(g.res * sqrt(1.7976931348623157e308));
   return (double)v;
 }
 

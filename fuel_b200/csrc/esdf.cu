@@ -110,13 +110,16 @@ __global__ void inflate_stamp_kernel(uint8_t* __restrict__ occ, int ny, int nz, 
         }
       }
 }
-__global__ void ceiling_kernel(uint8_t* __restrict__ occ, int ny, int nz, Box b, int ceil_id) {
+__global__ void ceiling_kernel(uint8_t* __restrict__ occ, double* __restrict__ logodds, double clamp_max_log, int ny,
+                               int nz, Box b, int ceil_id) {
   const int nyb = b.hi[1] - b.lo[1] + 1, nxb = b.hi[0] - b.lo[0] + 1;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nyb * nxb) return;
   const int y = b.lo[1] + t % nyb, x = b.lo[0] + t / nyb;
   const int64_t a = ((int64_t)x * ny + y) * nz + ceil_id;
   occ[a] = (uint8_t)((occ[a] & ~3u) | FUELGPU_OCCUPIED);  // occupancy_buffer_ = clamp_max_log_ (:463-470)
+  // the fused log-odds volume holds the same value, so that the ceiling survives the misses of later frames
+  if (logodds) logodds[a] = clamp_max_log;
 }
 }  // namespace
 
@@ -132,7 +135,9 @@ int map_inflate_impl(FuelMap* m, const int bmin[3], const int bmax[3], int step,
   FUEL_LAUNCHES(m, 2);
   if (ceil_id >= 0 && ceil_id < m->g.nz) {
     const int n2 = (b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1);
-    ceiling_kernel<<<(n2 + 255) / 256, 256, 0, m->stream>>>(m->occ, m->g.ny, m->g.nz, b, ceil_id);
+    double cmax = 0.0;
+    double* lo = fusion_logodds_ptr(m, &cmax);
+    ceiling_kernel<<<(n2 + 255) / 256, 256, 0, m->stream>>>(m->occ, lo, cmax, m->g.ny, m->g.nz, b, ceil_id);
     FUEL_LAUNCHES(m, 1);
   }
   FUEL_CUDA(m, cudaGetLastError());

@@ -1139,6 +1139,8 @@ struct FrontierState {
   HostView pend_hv;
   cudaStream_t stream = nullptr;  // the frontier subsystem's own stream
   cudaEvent_t ev_in = nullptr;
+  cudaEvent_t ev_out = nullptr;  // end of the last enqueued search: writers of `occ` on the main stream wait for it
+  bool ev_out_valid = false;
   char* h_pin = nullptr;  // pinned host staging for the result download
   size_t h_pin_bytes = 0;
   int* d_counters = nullptr;  // [0] n_cand [1] n_roots [2] n_kept [3] n_new [4] small-path status [5] C
@@ -1155,10 +1157,16 @@ cudaStream_t frontier_stream(FuelMap* m) {
   return f->stream;
 }
 
+void frontier_order_writer(FuelMap* m) {
+  FrontierState* f = m->fs;
+  if (f && f->ev_out_valid) cudaStreamWaitEvent(m->stream, f->ev_out, 0);
+}
+
 int frontier_state_create(FuelMap* m) {
   m->fs = new FrontierState();
   FUEL_CUDA(m, cudaStreamCreateWithFlags(&m->fs->stream, cudaStreamNonBlocking));
   FUEL_CUDA(m, cudaEventCreateWithFlags(&m->fs->ev_in, cudaEventDisableTiming));
+  FUEL_CUDA(m, cudaEventCreateWithFlags(&m->fs->ev_out, cudaEventDisableTiming));
   FUEL_CUDA(m, cudaMalloc(&m->fs->cellidx, sizeof(int) * m->nvox));
   FUEL_CUDA(m, cudaMemsetAsync(m->fs->cellidx, 0xff, sizeof(int) * m->nvox, m->stream));
   FUEL_CUDA(m, cudaMalloc(&m->fs->d_counters, sizeof(int) * 8 + sizeof(long long) * 256));
@@ -1177,6 +1185,7 @@ void frontier_state_destroy(FuelMap* m) {
     cudaStreamDestroy(f->stream);
   }
   if (f->ev_in) cudaEventDestroy(f->ev_in);
+  if (f->ev_out) cudaEventDestroy(f->ev_out);
   f->maskE.release(); f->maskS.release(); f->blockcnt.release(); f->blockoff.release();
   f->scan_tot.release(); f->scan_off.release();
   f->cell_addr.release(); f->parent.release(); f->claim.release(); f->csize.release();
@@ -1431,6 +1440,10 @@ int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double um
     f->pend_ndom = ndom;
     f->pend_active = true;
   }
+  // classify / union / claim kernels read `occ` on the frontier stream: a later writer of `occ` on the main
+  // stream (upload, inflate, fusion) must queue behind them (frontier_order_writer)
+  cudaEventRecord(f->ev_out, f->stream);
+  f->ev_out_valid = true;
   return 0;
 }
 

@@ -272,12 +272,27 @@ struct FusionState {
   int cap = 0;
   double update_min[3] = { 0, 0, 0 }, update_max[3] = { 0, 0, 0 };  // md_->update_min_/max_
   bool reset_updated_box = true;
+  double clamp_max_log = 2.1972245773362196;  // logit(p_max = 0.90, algorithm.xml:48) until a frame says otherwise
 };
 
 static double logit(double p) { return log(p / (1 - p)); }
 
-int fusion_state_ensure(FuelMap* m, double p_min) {
-  if (m->fus) return 0;
+// log-odds consistent with an occupancy byte that was uploaded before the first fused frame (setOccupancyBuffer
+// + upload): UNKNOWN -> clamp_min - unknown_flag, FREE -> clamp_min, OCCUPIED -> clamp_max (sdf_map.h:194-200 read
+// backwards); a map that never saw an upload is all UNKNOWN, i.e. exactly initMap (sdf_map.cpp:56,64)
+__global__ void seed_logodds_kernel(double* __restrict__ lo, const uint8_t* __restrict__ occ, int64_t n, double cmin,
+                                    double cmax) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = occ[i] & 3;
+  lo[i] = t == FUELGPU_OCCUPIED ? cmax : (t == FUELGPU_FREE ? cmin : cmin - 0.01);
+}
+
+int fusion_state_ensure(FuelMap* m, double p_min, double p_max) {
+  if (m->fus) {
+    m->fus->clamp_max_log = logit(p_max);
+    return 0;
+  }
   FusionState* f = new FusionState();
   m->fus = f;
   FUEL_CUDA(m, cudaMalloc(&f->logodds, sizeof(double) * m->nvox));
@@ -287,12 +302,20 @@ int fusion_state_ensure(FuelMap* m, double p_min) {
   FUEL_CUDA(m, cudaMalloc(&f->d_count, sizeof(int)));
   const unsigned nb = (unsigned)((m->nvox + 255) / 256);
   // initMap: occupancy_buffer_ = clamp_min_log_ - unknown_flag_ (sdf_map.cpp:56,64)
-  fill_f64_kernel<<<nb, 256, 0, m->stream>>>(f->logodds, m->nvox, logit(p_min) - 0.01);
+  f->clamp_max_log = logit(p_max);
+  seed_logodds_kernel<<<nb, 256, 0, m->stream>>>(f->logodds, m->occ, m->nvox, logit(p_min), logit(p_max));
   fill_i32_kernel<<<nb, 256, 0, m->stream>>>(f->rayend, m->nvox, 0x7fffffff);
   FUEL_CUDA(m, cudaMemsetAsync(f->mark, 0, (m->nvox + 3) / 4 * 4, m->stream));
   FUEL_LAUNCHES(m, 2);
   FUEL_CUDA(m, cudaGetLastError());
   return 0;
+}
+
+// device log-odds volume (nullptr before the first fused frame) and the clamp the virtual ceiling writes
+double* fusion_logodds_ptr(FuelMap* m, double* clamp_max_log) {
+  if (!m->fus) return nullptr;
+  if (clamp_max_log) *clamp_max_log = m->fus->clamp_max_log;
+  return m->fus->logodds;
 }
 
 void fusion_state_destroy(FuelMap* m) {
@@ -306,7 +329,7 @@ void fusion_state_destroy(FuelMap* m) {
 }
 
 int fusion_set_logodds(FuelMap* m, const double* logodds_host, double p_min, double p_occ) {
-  int rc = fusion_state_ensure(m, p_min);
+  int rc = fusion_state_ensure(m, p_min, 0.90);
   if (rc) return rc;
   FusionState* f = m->fus;
   FUEL_CUDA(m, cudaMemcpyAsync(f->logodds, logodds_host, sizeof(double) * m->nvox, cudaMemcpyHostToDevice, m->stream));
@@ -339,7 +362,7 @@ void fusion_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int rese
 static int fusion_frame(FuelMap* m, const float* pts_host, int stride, int n, const uint16_t* img_host,
                         const FuelCameraParams* cp, int rows, int cols, const double* Rm, int32_t* proj_cnt,
                         const double cam[3], const FuelFusionParams* p, int32_t lbmin[3], int32_t lbmax[3]) {
-  int rc = fusion_state_ensure(m, p->p_min);
+  int rc = fusion_state_ensure(m, p->p_min, p->p_max);
   if (rc) return rc;
   FusionState* f = m->fus;
   const Geom& g = m->g;

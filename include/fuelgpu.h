@@ -271,6 +271,10 @@ FUELGPU_API int fuelgpu_frontier_changed_counts(FuelMap* map, int32_t n_clusters
 #define FUELGPU_WAYPOINTS (1 << 6)
 #define FUELGPU_VIEWCONS (1 << 7) /* rejected: ld_view is 0.0 in every launch file (algorithm.xml:177) */
 #define FUELGPU_MINTIME (1 << 8)
+/* not a cost term: evaluate with the solver loop's evaluator (fuelgpu_bspline_optimize_batch runs it: fp32
+ * trilinear lerps on the fp32 ESDF samples, reciprocals, FMA contraction) instead of the faithful one; same
+ * 1e-4 parity bar, n_pts <= 32 */
+#define FUELGPU_COST_FAST_EVAL (1 << 30)
 
 /* BsplineOptimizer::setParam (bspline_optimizer.cpp:25-57) */
 typedef struct {

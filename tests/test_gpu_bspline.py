@@ -239,3 +239,66 @@ def test_optimize_begin_end_equals_one_shot(fuel, orc, scene):
     x2, f2, n2 = opt.optimizeBatchEnd()
     assert np.array_equal(x0, keep)
     assert np.array_equal(x1, x2) and np.array_equal(f1, f2) and np.array_equal(n1, n2)
+
+
+def test_fast_evaluator_is_what_the_parity_bar_covers(fuel, orc, scene):
+    """The solver loop (optimizeBatch, the kernel the benchmark times) evaluates with eval_warp<true>: fp32 trilinear
+    lerps on the fp32 ESDF samples, reciprocals, one merged reduction, FMA contraction.  FUELGPU_COST_FAST_EVAL runs
+    exactly that evaluator once: cost AND gradient against the oracle, same 1e-4 bar, on the config-2 batch, the
+    adversarial positions and a 4096-trajectory batch."""
+    O = fuel.BsplineOptimizer
+    g = scene["g"]
+    og = orc_grid(orc, g)
+    mask = O.NORMAL_PHASE | O.MINTIME
+    for B, seed in ((1024, 20260922), (4096, 101)):
+        tr = W.make_trajectories(g, scene["inflate"], B=B, n_pts=20, seed=seed)
+        x = W.pack_x(tr["ctrl"], tr["dt"])
+        x[::3, -1] *= 0.5  # make feasibility and its dt-gradient bite
+        f, gg = scene["opt"].combineCostBatch(x, gpu_consts(fuel, tr, B), 20, mask, fast_eval=True)
+        fr, gr = orc.combine_cost_batch(og, scene["d64"], orc.opt_params(), orc_consts(orc, tr, B), 20, mask, x, threads=8)
+        check(f, gg, fr, gr)
+        f2, g2 = scene["opt"].combineCostBatch(x, gpu_consts(fuel, tr, B), 20, mask)
+        assert not (np.array_equal(f, f2) and np.array_equal(gg, g2)), "the flag did not switch evaluators"
+    # adversarial positions: map boundary, outside the map, the isInMap margin
+    B = 48
+    tr = W.make_trajectories(g, scene["inflate"], B=B, n_pts=20, seed=13)
+    ctrl = tr["ctrl"].copy()
+    ctrl[0:8, 5] = g.origin + [0.02, 0.5, 0.5]
+    ctrl[8:16, 7] = g.map_max + 0.3
+    ctrl[16:24, 9] = g.map_max - [1e-4, 0.5, 0.5]
+    tr["ctrl"] = ctrl
+    x = W.pack_x(ctrl, tr["dt"])
+    f, gg = scene["opt"].combineCostBatch(x, gpu_consts(fuel, tr, B), 20, mask, fast_eval=True)
+    fr, gr = orc.combine_cost_batch(og, scene["d64"], orc.opt_params(), orc_consts(orc, tr, B), 20, mask, x)
+    check(f, gg, fr, gr)
+    # every single term through the fast evaluator
+    tr = W.make_trajectories(g, scene["inflate"], B=64, n_pts=20, seed=5)
+    for name in ("SMOOTHNESS", "DISTANCE", "FEASIBILITY", "START", "END"):
+        m1 = getattr(O, name)
+        x = W.pack_x(tr["ctrl"], tr["dt"] * 0.6, mintime=False)
+        tr2 = dict(tr)
+        tr2["dt"] = tr["dt"] * 0.6
+        f, gg = scene["opt"].combineCostBatch(x, gpu_consts(fuel, tr2, 64), 20, m1, fast_eval=True)
+        fr, gr = orc.combine_cost_batch(og, scene["d64"], orc.opt_params(), orc_consts(orc, tr2, 64), 20, m1, x)
+        check(f, gg, fr, gr)
+
+
+def test_exact_eval_mode_performs_every_evaluation(fuel, orc, scene):
+    """FUELGPU_SOLVE_EXACT_EVALS (what bench.py times): every trajectory reports exactly max_eval evaluations and
+    the result is never worse than the normal mode's start."""
+    B, N, K = 1024, 20, 64
+    O = fuel.BsplineOptimizer
+    tr = W.make_trajectories(scene["g"], scene["inflate"], B=B, n_pts=N)
+    mask = O.NORMAL_PHASE | O.MINTIME
+    x0 = W.pack_x(tr["ctrl"], tr["dt"])
+    tc = gpu_consts(fuel, tr, B)
+    xe, fe, ne = scene["opt"].optimizeBatch(x0, tc, N, mask, K, xtol_rel=0.0, exact_evals=True)
+    assert np.all(ne == K), (ne.min(), ne.max())
+    xn, fn, nn = scene["opt"].optimizeBatch(x0, tc, N, mask, K, xtol_rel=0.0)
+    assert np.all(nn <= K)
+    print("normal mode evals: min %d mean %.2f" % (nn.min(), nn.mean()))
+    f0, _ = orc.combine_cost_batch(orc_grid(orc, scene["g"]), scene["d64"], orc.opt_params(), orc_consts(orc, tr, B), N,
+                                   mask, x0, threads=8)
+    assert np.all(fe <= f0 * (1 + 1e-9))
+    same = nn == K
+    assert np.array_equal(xe[same], xn[same])  # trajectories that never stop early take the identical path

@@ -50,6 +50,53 @@ def test_esdf_512_slab_matches_oracle(fuel, orc, pillar):
     m.local_bound_min_, m.local_bound_max_ = np.zeros(3, dtype=np.int32), np.array(g.n) - 1
 
 
+@pytest.mark.parametrize("variant", ["V1", "V0"])
+def test_esdf_512_full_box_matches_oracle(fuel, orc, variant):
+    """The update bench.py times as roofline_esdf512 (box = the whole 512^3 map), voxel for voxel against the
+    oracle: V1 (tiled, every line has sites) and V0 (file as is: most lines have none -> the +inf sentinel)."""
+    g, inflate = W.pillar_map(variant)
+    tri = np.where(inflate == 1, W.OCCUPIED, W.FREE).astype(np.uint8)
+    m = make_sdf_map(fuel, g, inflate, tri, optimistic=True)
+    m.updateESDF3d()
+    d = m.download().copy()
+    m.close()
+    ref = orc.update_esdf3d(orc_grid(orc, g), inflate, tri, [0, 0, 0], np.array(g.n) - 1, True, False, threads=16)
+    fin = ref < 1e150
+    assert np.array_equal(np.isinf(d), ~fin)
+    err = np.abs(d[fin].astype(np.float64) - ref[fin])
+    assert np.all(err <= 1e-4 * ref[fin]), float(np.max(err / np.maximum(ref[fin], 1e-12)))
+    del ref
+
+
+def test_frontier_512_matches_oracle(fuel, orc):
+    """BASELINE config 3, second half: the frontier sweep + clustering + split over the 512^3 pillar map (the large
+    multi-kernel path), bit-exact against the oracle: cluster count, order, cell sets, frontier_flag_."""
+    g, inflate = W.pillar_map("V1")
+    tri = W.known_region(g, inflate, seed=7, n_poses=64, radius=4.5)
+    m = fuel.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max)
+    m.occupancy_buffer_inflate_[...] = inflate
+    m.setOccupancyBuffer(tristate=tri)
+    m.upload()
+    env = fuel.EDTEnvironment()
+    env.setMap(m)
+    ff = fuel.FrontierFinder(env)
+    out = ff.search_box(g.origin, g.map_max)
+    fl = ff.download_flags()
+    allc = np.concatenate([c.cells_addr_ for c in out])
+    assert len(out) > 100 and np.unique(allc).size == allc.size and np.all(fl.ravel()[allc] == 1)
+    assert ff.search_box(g.origin, g.map_max) == [] and np.array_equal(ff.download_flags(), fl)  # idempotent
+    og = orc_grid(orc, g)
+    ofl = np.zeros(g.n, dtype=np.int8)
+    ref = orc.frontier_search(og, tri, ofl, g.origin, g.map_max, orc.frontier_params(cell_order=1))
+    assert len(ref) == len(out)
+    for a, b in zip(out, ref):
+        assert np.array_equal(a.cells_addr_, b["addr"])
+        assert np.array_equal(a.filtered_cells_, b["filtered"])  # third-party VoxelGrid restated on both sides (unpinned)
+        assert np.allclose(a.average_, b["average"], rtol=0, atol=1e-12)
+    assert np.array_equal(fl, ofl)
+    m.close()
+
+
 def test_bspline_4096_batch_office3(fuel, orc):
     """BASELINE config 5: office3.pcd 200x300x40, 4096 trajectories."""
     g, inflate = W.office3_map()

@@ -134,3 +134,67 @@ def test_depth_image_path(fuel, orc):
     assert m.inputDepthImage(np.full((480, 640), 50, np.uint16), np.eye(3), np.array([0.0, 0.0, 1.0])) == 0
     assert np.array_equal(before, m.getLogOdds())
     m.close()
+
+
+def test_virtual_ceiling_survives_later_frames(fuel, orc):
+    """Several fuse -> clearAndInflateLocalMap cycles with a virtual ceiling (virtual_ceil_height 1.5, as the
+    kino/topo launch files set 2.5-3.2) against the reference's own sdf_map.cpp (oracle/_ref): the reference writes
+    occupancy_buffer_[ceiling] = clamp_max_log_ (sdf_map.cpp:462-470), so the ceiling voxels stay occupied when later
+    frames register misses on them; log-odds, tri-state and inflation must stay bit-exact after every cycle."""
+    if orc.ref_raycast() is None:
+        pytest.skip("oracle/_ref not built")
+    ceil_h = 1.5
+    ref = orc.RefSDFMap(resolution=0.1, map_size_x=8.0, map_size_y=6.0, map_size_z=3.0, ground_height=-0.5,
+                        obstacles_inflation=0.199, local_bound_inflate=0.5, local_map_margin=50, default_dist=0.0,
+                        optimistic=0, signed_dist=0, p_hit=0.65, p_miss=0.35, p_min=0.12, p_max=0.90, p_occ=0.80,
+                        max_ray_length=4.5, virtual_ceil_height=ceil_h)
+    g = W.Grid(ref.n, tuple(ref.origin), ref.res)
+    m = fuel.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max)
+    m.setFusionParams(max_ray_length=4.5)
+    rng = np.random.default_rng(21)
+    for cycle in range(4):
+        cam = np.array([rng.uniform(-2, 2), rng.uniform(-1.5, 1.5), rng.uniform(0.3, 1.2)])
+        # rays that go up through the ceiling plane (misses on ceiling voxels) and hits below it
+        pts = cam + rng.normal(size=(4000, 3)) * np.array([2.0, 2.0, 1.5])
+        pts[:1500, 2] = np.abs(pts[:1500, 2]) + ceil_h + 0.3
+        pts = pts.astype(np.float32)
+        ref.input_point_cloud(pts, cam)
+        m.inputPointCloud(pts, pts.shape[0], cam)
+        lo, hi = ref.get_local_bound()
+        assert np.array_equal(m.local_bound_min_, lo) and np.array_equal(m.local_bound_max_, hi)
+        ref.clear_and_inflate()
+        m.clearAndInflateLocalMap(obstacles_inflation=0.199, virtual_ceil_height=ceil_h)
+        got = m.getLogOdds().reshape(-1)
+        assert np.array_equal(got, ref.occupancy), "cycle %d: log-odds differ in %d voxels" % (
+            cycle, int((got != ref.occupancy).sum()))
+        assert np.array_equal(m.occupancy_buffer_inflate_.reshape(-1), ref.inflate), "cycle %d: inflation differs" % cycle
+    ref.close()
+    m.close()
+
+
+def test_first_frame_respects_uploaded_occupancy(fuel, orc):
+    """A map whose occupancy was uploaded as tri-state (setOccupancyBuffer + upload) and then receives its first fused
+    frame: the device log-odds are seeded from the resident byte (UNKNOWN / FREE / OCCUPIED -> clamp_min - 0.01 /
+    clamp_min / clamp_max), so one miss does not turn an uploaded OCCUPIED voxel into FREE."""
+    g = W.Grid((40, 30, 20), (-2.0, -1.5, -0.5), 0.1)
+    tri = np.full(g.n, W.FREE, dtype=np.uint8)
+    tri[25, 15, 10] = W.OCCUPIED
+    tri[:, :, 15:] = W.UNKNOWN
+    m = fuel.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max)
+    m.setOccupancyBuffer(tristate=tri)
+    m.upload()
+    m.setFusionParams(max_ray_length=4.5)
+    cam = np.array([-1.0, 0.05, 0.55])
+    # one ray through the occupied voxel (a miss on it), ending well behind it
+    target = np.array([[1.5, 0.05, 0.55]], dtype=np.float32)
+    m.inputPointCloud(target, 1, cam)
+    lo = m.getLogOdds()
+    lg = lambda p: np.log(p / (1 - p))  # noqa: E731
+    assert lo[25, 15, 10] == lg(0.90) + lg(0.35)     # clamp_max + one miss: still above min_occupancy_log
+    assert lo[0, 0, 0] == lg(0.12) and lo[0, 0, 18] == lg(0.12) - 0.01
+    tri2 = np.empty(m.shape, np.uint8)
+    inf = np.empty(m.shape, np.int8)
+    from fuel_b200._lib import check, lib, ptr
+    check(lib().fuelgpu_map_download_occupancy(m._h, ptr(inf), ptr(tri2)), m._h)
+    assert tri2[25, 15, 10] == W.OCCUPIED
+    m.close()
