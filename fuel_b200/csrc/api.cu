@@ -549,6 +549,11 @@ int fuelgpu_frontier_fetch(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr
   return frontier_fetch_impl(m, cell_offsets, cell_addr, filt_offsets, filtered, average, box_min, box_max);
 }
 
+int fuelgpu_frontier_set_cell_order(FuelMap* m, int32_t order) {
+  if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
+  return frontier_set_cell_order(m, order);
+}
+
 int fuelgpu_frontier_clear_flags(FuelMap* m, int32_t n, const int32_t* addr) {
   if (!m || (n > 0 && !addr)) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   if (n <= 0) return 0;

@@ -122,7 +122,8 @@ int fusion_get_logodds(FuelMap* m, double* out);
 void fusion_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int reset);
 void fusion_state_destroy(FuelMap* m);
 double* fusion_logodds_ptr(FuelMap* m, double* clamp_max_log);
-void frontier_order_writer(FuelMap* m);  // main-stream writers of `occ` wait for an enqueued frontier search
+void frontier_order_writer(FuelMap* m);
+int frontier_set_cell_order(FuelMap* m, int order);  // main-stream writers of `occ` wait for an enqueued frontier search
 
 int ensure_fr_scratch(FuelMap* m, size_t bytes);
 int frontier_state_create(FuelMap* m);

@@ -1147,6 +1147,8 @@ struct FrontierState {
   // results of the last search (host side, CSR)
   std::vector<int32_t> h_cell_off, h_cell_addr, h_filt_off;
   std::vector<double> h_filtered, h_avg, h_bmin, h_bmax;
+  int cell_order = FUELGPU_CELLS_BY_ADDRESS;  // fuelgpu_frontier_set_cell_order
+  float last_leaf = 0.f;                      // PCL leaf size of the last search
 };
 
 cudaStream_t frontier_stream_raw(FuelMap* m) { return m->fs->stream; }
@@ -1155,6 +1157,13 @@ cudaStream_t frontier_stream(FuelMap* m) {
   cudaEventRecord(f->ev_in, m->stream);
   cudaStreamWaitEvent(f->stream, f->ev_in, 0);
   return f->stream;
+}
+
+int frontier_set_cell_order(FuelMap* m, int order) {
+  if (order != FUELGPU_CELLS_BY_ADDRESS && order != FUELGPU_CELLS_BFS)
+    return fuel_fail(m, FUELGPU_EINVAL, "unknown cell order");
+  m->fs->cell_order = order;
+  return 0;
 }
 
 void frontier_order_writer(FuelMap* m) {
@@ -1261,6 +1270,138 @@ static int enqueue_download(FuelMap* m, int K, int C, char* base, HostView* v) {
 static int frontier_build_csr(FuelMap* m, int K, int C, const HostView& hv, int32_t* n_clusters,
                               int32_t* n_cells, int32_t* n_filtered);
 
+// ---- optional: the reference's own cell order ---------------------------------------------------------------
+// expandFrontier (frontier_finder.cpp:123-164) appends cells in BFS order from the seed (the first cell of the
+// cluster in scan order = its lowest address), neighbours in allNeighbors order (:848-860: x, y, z from -1 to 1),
+// and splitHorizontally (:217-224) partitions a parent's cells_ keeping their relative order.  The device emits a
+// cluster's cells in ascending address; membership, cluster order and flags do not depend on the order, but the fp64
+// running sum of average_ (:374-385) and the float32 per-leaf sums of the VoxelGrid centroids (:757-774) do, in their
+// last bits.  With FUELGPU_CELLS_BFS the host re-derives the BFS rank of every cell of a root cluster (the BFS only
+// ever moves between cells of that cluster, so the fetched cell set is all it needs), re-orders the cells of its final
+// clusters by it and recomputes average_ and filtered_cells_ in that order: bit-identical with the reference.
+static void frontier_apply_bfs_order(FuelMap* m, const std::vector<int>& out_root) {
+  FrontierState* f = m->fs;
+  const Geom& g = m->g;
+  const int C = (int)out_root.size();
+  const int64_t sy = g.nz, sx = (int64_t)g.ny * g.nz;
+  std::vector<int32_t> new_filt_off(C + 1, 0);
+  std::vector<double> new_filtered;
+  new_filtered.reserve(f->h_filtered.size());
+  std::vector<int> tab;  // open-addressing hash: address -> local index
+  for (int r0 = 0; r0 < C;) {
+    int r1 = r0 + 1;
+    while (r1 < C && out_root[r1] == out_root[r0]) ++r1;
+    const int a0 = f->h_cell_off[r0], a1 = f->h_cell_off[r1], n = a1 - a0;
+    int cap = 16;
+    while (cap < 2 * n) cap <<= 1;
+    tab.assign(cap, -1);
+    auto slot_of = [&](int addr) { return (int)(((uint32_t)addr * 2654435761u) & (uint32_t)(cap - 1)); };
+    // the seed = the first cell of the cluster the scan of the search box meets (:108-116): lowest address inside it
+    int seed = -1;
+    const FParams& sp = f->pend_fp;
+    for (int i = 0; i < n; ++i) {
+      const int addr = f->h_cell_addr[a0 + i];
+      const int cx = (int)(addr / sx), cy = (int)((addr % sx) / sy), cz = (int)(addr % sy);
+      const bool in_search = cx >= sp.s_lo[0] && cx <= sp.s_hi[0] && cy >= sp.s_lo[1] && cy <= sp.s_hi[1] &&
+                             cz >= sp.s_lo[2] && cz <= sp.s_hi[2];
+      if (in_search && (seed < 0 || addr < f->h_cell_addr[a0 + seed])) seed = i;
+      int s = slot_of(addr);
+      while (tab[s] >= 0) s = (s + 1) & (cap - 1);
+      tab[s] = i;
+    }
+    auto find = [&](int addr) {
+      int s = slot_of(addr);
+      while (tab[s] >= 0) {
+        if (f->h_cell_addr[a0 + tab[s]] == addr) return tab[s];
+        s = (s + 1) & (cap - 1);
+      }
+      return -1;
+    };
+    if (seed < 0) seed = 0;  // (cannot happen: every root has its seed inside the search box)
+    std::vector<int> bfs_rank(n, -1), queue;
+    queue.reserve(n);
+    queue.push_back(seed);
+    bfs_rank[seed] = 0;
+    for (size_t qh = 0; qh < queue.size(); ++qh) {
+      const int addr = f->h_cell_addr[a0 + queue[qh]];
+      const int x = (int)(addr / sx), y = (int)((addr % sx) / sy), z = (int)(addr % sy);
+      for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dz = -1; dz <= 1; ++dz) {
+            if (!dx && !dy && !dz) continue;
+            const int xx = x + dx, yy = y + dy, zz = z + dz;
+            if (xx < 0 || yy < 0 || zz < 0 || xx >= g.nx || yy >= g.ny || zz >= g.nz) continue;
+            const int j = find((int)(xx * sx + yy * sy + zz));
+            if (j >= 0 && bfs_rank[j] < 0) {
+              bfs_rank[j] = (int)queue.size();
+              queue.push_back(j);
+            }
+          }
+    }
+    int next = (int)queue.size();
+    for (int i = 0; i < n; ++i)  // (not reachable from the seed: cannot happen for a region-grown cluster)
+      if (bfs_rank[i] < 0) bfs_rank[i] = next++;
+    for (int r = r0; r < r1; ++r) {
+      const int c0 = f->h_cell_off[r] - a0, c1 = f->h_cell_off[r + 1] - a0, cn = c1 - c0;
+      std::vector<std::pair<int, int>> key(cn);
+      for (int i = 0; i < cn; ++i) key[i] = std::make_pair(bfs_rank[c0 + i], f->h_cell_addr[a0 + c0 + i]);
+      std::sort(key.begin(), key.end());
+      // computeFrontierInfo in this order: positions = indexToPos (sdf_map.h:133-136), fp64 running sum
+      std::vector<float> pf((size_t)3 * cn);
+      double sum[3] = { 0, 0, 0 };
+      for (int i = 0; i < cn; ++i) {
+        const int addr = key[i].second;
+        f->h_cell_addr[a0 + c0 + i] = addr;
+        const int id[3] = { (int)(addr / sx), (int)((addr % sx) / sy), (int)(addr % sy) };
+        for (int a = 0; a < 3; ++a) {
+          const double pos = (id[a] + 0.5) * g.res + g.origin[a];
+          sum[a] += pos;
+          pf[(size_t)3 * i + a] = (float)pos;
+        }
+      }
+      for (int a = 0; a < 3; ++a) f->h_avg[(size_t)3 * r + a] = sum[a] / (double)cn;
+      // pcl::VoxelGrid (third party, restated as in DESIGN.md: leaf index from floor(p * inv_leaf) relative to the
+      // cloud's minimum, centroids in ascending leaf index, points of a leaf summed in float32 in input order)
+      const float inv = 1.0f / f->last_leaf;
+      float minp[3] = { pf[0], pf[1], pf[2] }, maxp[3] = { pf[0], pf[1], pf[2] };
+      for (int i = 1; i < cn; ++i)
+        for (int a = 0; a < 3; ++a) {
+          minp[a] = std::min(minp[a], pf[(size_t)3 * i + a]);
+          maxp[a] = std::max(maxp[a], pf[(size_t)3 * i + a]);
+        }
+      int minb[3], divb[3];
+      for (int a = 0; a < 3; ++a) {
+        minb[a] = (int)floorf(minp[a] * inv);
+        divb[a] = (int)floorf(maxp[a] * inv) - minb[a] + 1;
+      }
+      std::vector<std::pair<int, int>> lk(cn);
+      for (int i = 0; i < cn; ++i) {
+        int ijk[3];
+        for (int a = 0; a < 3; ++a) ijk[a] = (int)(floorf(pf[(size_t)3 * i + a] * inv) - (float)minb[a]);
+        lk[i] = std::make_pair(ijk[0] + ijk[1] * divb[0] + ijk[2] * divb[0] * divb[1], i);
+      }
+      std::sort(lk.begin(), lk.end());
+      int nf = 0;
+      for (int i = 0; i < cn;) {
+        int j = i;
+        float acc[3] = { 0.f, 0.f, 0.f };
+        while (j < cn && lk[j].first == lk[i].first) {
+          for (int a = 0; a < 3; ++a) acc[a] += pf[(size_t)3 * lk[j].second + a];
+          ++j;
+        }
+        const float cntf = (float)(j - i);
+        for (int a = 0; a < 3; ++a) new_filtered.push_back((double)(acc[a] / cntf));
+        ++nf;
+        i = j;
+      }
+      new_filt_off[r + 1] = new_filt_off[r] + nf;
+    }
+    r0 = r1;
+  }
+  f->h_filt_off.swap(new_filt_off);
+  f->h_filtered.swap(new_filtered);
+}
+
 static int frontier_marshal(FuelMap* m, int K, int C, int32_t* n_clusters, int32_t* n_cells,
                             int32_t* n_filtered) {
   int rc = ensure_pin(m, view_bytes(K, C));
@@ -1338,6 +1479,12 @@ static int frontier_build_csr(FuelMap* m, int K, int C, const HostView& hv, int3
   *n_clusters = C;
   *n_cells = K;
   *n_filtered = NF;
+  if (f->cell_order == FUELGPU_CELLS_BFS) {
+    std::vector<int> out_root(C);
+    for (int c = 0; c < C; ++c) out_root[rank[c]] = h_meta[c].root;
+    frontier_apply_bfs_order(m, out_root);
+    *n_filtered = f->h_filt_off[C];
+  }
   return 0;
 }
 
@@ -1382,7 +1529,9 @@ int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double um
   fp.cluster_min = p->cluster_min;
   fp.size_xy = p->cluster_size_xy;
   fp.leaf = (float)(g.res * p->down_sample);  // setLeafSize(float) narrowing
+  f->last_leaf = fp.leaf;
   fp.leaf_inv = 1.0f / fp.leaf;
+  f->pend_fp = fp;  // (search box and leaf size are also what the host-side BFS ordering needs)
 
   f->h_cell_off.assign(1, 0);
   f->h_cell_addr.clear();

@@ -90,23 +90,34 @@ __device__ bool ray_is_clear(const Geom& g, const uint8_t* __restrict__ occ, con
 
 constexpr int VP_THREADS = 128;
 
+// HOSTYAW = false: one block per (candidate, cluster); the average yaw comes from the device's acos/atan2 (<= 2 ulp
+// per call, so the yaw and the FOV plane normals are within ~1e-12 of the host's) and cand_unc[out] is raised when a
+// FOV plane test of some cell comes closer to zero than 1e-9: only then could the host's libm decide otherwise.
+// HOSTYAW = true: second pass over the raised candidates (redo[blockIdx.x] = out index) with yaw, cos(yaw), sin(yaw)
+// computed by the host's libm exactly as the reference does, so that the visible count is the reference's integer.
+constexpr double FOV_EPS = 1e-9;
+
+template <bool HOSTYAW>
 __global__ void __launch_bounds__(VP_THREADS)
 sample_viewpoints_kernel(Geom g, const uint8_t* __restrict__ occ, ViewConsts vc, int ncand, const double* __restrict__ off_xy,
                          const int* __restrict__ filt_off, const double* __restrict__ filt, const double* __restrict__ avg,
-                         double* __restrict__ cand_pos, double* __restrict__ cand_yaw, int* __restrict__ cand_visib) {
-  const int c = blockIdx.x, cl = blockIdx.y, t = threadIdx.x;
-  const int out = cl * ncand + c;
+                         double* __restrict__ cand_pos, double* __restrict__ cand_yaw, int* __restrict__ cand_visib,
+                         int* __restrict__ cand_unc, const int* __restrict__ redo, const double* __restrict__ host_yaw) {
+  const int t = threadIdx.x;
+  const int out = HOSTYAW ? redo[blockIdx.x] : (int)(blockIdx.y * ncand + blockIdx.x);
+  const int c = out % ncand, cl = out / ncand;
   const double* cells = filt + 3 * (int64_t)filt_off[cl];
   const int n_cells = filt_off[cl + 1] - filt_off[cl];
   // sample_pos = average_ + rc * (cos phi, sin phi, 0): the products come from the host's libm (api side)
   const double pos[3] = { __dadd_rn(avg[3 * cl], off_xy[2 * c]), __dadd_rn(avg[3 * cl + 1], off_xy[2 * c + 1]),
                           __dadd_rn(avg[3 * cl + 2], 0.0) };
-  __shared__ int s_reject, s_visib;
+  __shared__ int s_reject, s_visib, s_unc;
   __shared__ double s_term[VP_THREADS];
   __shared__ double s_ref[3], s_yaw, s_nrm[4][3];
   if (t == 0) {
     s_reject = 0;
     s_visib = 0;
+    s_unc = 0;
     cand_pos[3 * out] = pos[0], cand_pos[3 * out + 1] = pos[1], cand_pos[3 * out + 2] = pos[2];
     // isInBox(pos) (sdf_map.h:180-187) and getInflateOccupancy(pos) == 1 (:222-226), frontier_finder.cpp:671-672
     bool inbox = true;
@@ -135,47 +146,55 @@ sample_viewpoints_kernel(Geom g, const uint8_t* __restrict__ occ, ViewConsts vc,
     if (t == 0) {
       cand_yaw[out] = 0.0;
       cand_visib[out] = -1;
+      if (!HOSTYAW) cand_unc[out] = 0;
     }
     return;
   }
   // average yaw (:675-685): per-cell terms in parallel, summed by one thread in the reference's order
-  if (t == 0) {
-    const double d0[3] = { cells[0] - pos[0], cells[1] - pos[1], cells[2] - pos[2] };
-    double r[3];
-    normalized3(d0, r);
-    s_ref[0] = r[0], s_ref[1] = r[1], s_ref[2] = r[2];
-    s_yaw = 0.0;
-  }
-  __syncthreads();
-  for (int base = 1; base < n_cells; base += VP_THREADS) {
-    const int i = base + t;
-    if (i < n_cells) {
-      const double d[3] = { cells[3 * i] - pos[0], cells[3 * i + 1] - pos[1], cells[3 * i + 2] - pos[2] };
-      double dir[3];
-      normalized3(d, dir);
-      const double ref[3] = { s_ref[0], s_ref[1], s_ref[2] };
-      double yaw = acos(dot3(dir, ref));
-      if (__dadd_rn(__dmul_rn(ref[0], dir[1]), -__dmul_rn(ref[1], dir[0])) < 0) yaw = -yaw;
-      s_term[t] = yaw;
-    }
-    __syncthreads();
+  if (!HOSTYAW) {
     if (t == 0) {
-      double a = s_yaw;
-      const int m = min(VP_THREADS, n_cells - base);
-      for (int k = 0; k < m; ++k) a = __dadd_rn(a, s_term[k]);
-      s_yaw = a;
+      const double d0[3] = { cells[0] - pos[0], cells[1] - pos[1], cells[2] - pos[2] };
+      double r[3];
+      normalized3(d0, r);
+      s_ref[0] = r[0], s_ref[1] = r[1], s_ref[2] = r[2];
+      s_yaw = 0.0;
     }
     __syncthreads();
+    for (int base = 1; base < n_cells; base += VP_THREADS) {
+      const int i = base + t;
+      if (i < n_cells) {
+        const double d[3] = { cells[3 * i] - pos[0], cells[3 * i + 1] - pos[1], cells[3 * i + 2] - pos[2] };
+        double dir[3];
+        normalized3(d, dir);
+        const double ref[3] = { s_ref[0], s_ref[1], s_ref[2] };
+        double yaw = acos(dot3(dir, ref));
+        if (__dadd_rn(__dmul_rn(ref[0], dir[1]), -__dmul_rn(ref[1], dir[0])) < 0) yaw = -yaw;
+        s_term[t] = yaw;
+      }
+      __syncthreads();
+      if (t == 0) {
+        double a = s_yaw;
+        const int m = min(VP_THREADS, n_cells - base);
+        for (int k = 0; k < m; ++k) a = __dadd_rn(a, s_term[k]);
+        s_yaw = a;
+      }
+      __syncthreads();
+    }
   }
   if (t == 0) {
-    double a = __dadd_rn(s_yaw / n_cells, atan2(s_ref[1], s_ref[0]));
-    const double PI = 3.14159265358979323846;
-    for (int it = 0; it < 64 && a < -PI; ++it) a = __dadd_rn(a, 2 * PI);  // wrapYaw :776-781 (bounded; NaN falls through)
-    for (int it = 0; it < 64 && a > PI; ++it) a = __dadd_rn(a, -(2 * PI));
+    double a, cy, sy;
+    if (HOSTYAW) {
+      a = host_yaw[3 * blockIdx.x], cy = host_yaw[3 * blockIdx.x + 1], sy = host_yaw[3 * blockIdx.x + 2];
+    } else {
+      a = __dadd_rn(s_yaw / n_cells, atan2(s_ref[1], s_ref[0]));
+      const double PI = 3.14159265358979323846;
+      for (int it = 0; it < 64 && a < -PI; ++it) a = __dadd_rn(a, 2 * PI);  // wrapYaw :776-781 (bounded; NaN falls through)
+      for (int it = 0; it < 64 && a > PI; ++it) a = __dadd_rn(a, -(2 * PI));
+      cy = cos(a), sy = sin(a);
+    }
     s_yaw = a;
     cand_yaw[out] = a;
     // setPose (perception_utils.cpp:49-66): normals_ = R_wc * {n_top, n_bottom, n_left, n_right}
-    const double cy = cos(a), sy = sin(a);
     s_nrm[0][0] = __dmul_rn(cy, vc.tb), s_nrm[0][1] = __dmul_rn(sy, vc.tb), s_nrm[0][2] = vc.ta;
     s_nrm[1][0] = __dmul_rn(cy, vc.tb), s_nrm[1][1] = __dmul_rn(sy, vc.tb), s_nrm[1][2] = -vc.ta;
     s_nrm[2][0] = __dadd_rn(__dmul_rn(sy, vc.lc), __dmul_rn(cy, vc.ld));
@@ -195,18 +214,24 @@ sample_viewpoints_kernel(Geom g, const uint8_t* __restrict__ occ, ViewConsts vc,
     if (nn > vc.max_dist) continue;
     double u[3];
     normalized3(dir, u);
-    bool inside = true;
+    bool inside = true, close = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const double nk[3] = { s_nrm[k][0], s_nrm[k][1], s_nrm[k][2] };
-      if (dot3(u, nk) < 0.0) inside = false;
+      const double dk = dot3(u, nk);
+      if (dk < 0.0) inside = false;
+      if (fabs(dk) <= FOV_EPS) close = true;
     }
+    if (!HOSTYAW && close) s_unc = 1;  // benign race: every writer stores 1
     if (!inside) continue;
     if (ray_is_clear(g, occ, cell, pos)) ++mine;
   }
   if (mine) atomicAdd(&s_visib, mine);
   __syncthreads();
-  if (t == 0) cand_visib[out] = s_visib;
+  if (t == 0) {
+    cand_visib[out] = s_visib;
+    if (!HOSTYAW) cand_unc[out] = s_unc;
+  }
 }
 
 }  // namespace
@@ -244,28 +269,79 @@ int sample_viewpoints_impl(FuelMap* m, int ncl, const int32_t* filt_off, const d
   if (vc.clear_vox < 0 || vc.clear_vox > 64) return fuel_fail(m, FUELGPU_EINVAL, "min_candidate_clearance out of range");
   cudaStream_t s = frontier_stream(m);
   const size_t n_out = (size_t)ncl * nc;
-  // one staging allocation: [off 2nc][avg 3ncl][filt 3nfilt][pos 3n_out][yaw n_out] doubles, then ints
-  const size_t nd = 2 * (size_t)nc + 3 * (size_t)ncl + 3 * (size_t)(nfilt > 0 ? nfilt : 1) + 4 * n_out;
-  const size_t ni = (size_t)ncl + 1 + n_out;
+  // one staging allocation: [off 2nc][avg 3ncl][filt 3nfilt][pos 3n_out][yaw n_out][host yaw 3n_out] doubles, then ints
+  const size_t nd = 2 * (size_t)nc + 3 * (size_t)ncl + 3 * (size_t)(nfilt > 0 ? nfilt : 1) + 7 * n_out;
+  const size_t ni = (size_t)ncl + 1 + 3 * n_out;
   const size_t dbytes = (sizeof(double) * nd + 255) & ~(size_t)255;
   int rc = ensure_fr_scratch(m, dbytes + sizeof(int) * ni);
   if (rc) return rc;
   double* d_d = (double*)m->fr_scr;
   int* d_i = (int*)((uint8_t*)m->fr_scr + dbytes);
   double *d_off = d_d, *d_avg = d_off + 2 * nc, *d_filt = d_avg + 3 * ncl, *d_pos = d_filt + 3 * (size_t)(nfilt > 0 ? nfilt : 1),
-         *d_yaw = d_pos + 3 * n_out;
-  int *d_fo = d_i, *d_vis = d_i + ncl + 1;
+         *d_yaw = d_pos + 3 * n_out, *d_hyaw = d_yaw + n_out;
+  int *d_fo = d_i, *d_vis = d_i + ncl + 1, *d_unc = d_vis + n_out, *d_redo = d_unc + n_out;
   FUEL_CUDA(m, cudaMemcpyAsync(d_off, off.data(), sizeof(double) * 2 * nc, cudaMemcpyHostToDevice, s));
   FUEL_CUDA(m, cudaMemcpyAsync(d_avg, avg, sizeof(double) * 3 * ncl, cudaMemcpyHostToDevice, s));
   if (nfilt > 0) FUEL_CUDA(m, cudaMemcpyAsync(d_filt, filt, sizeof(double) * 3 * nfilt, cudaMemcpyHostToDevice, s));
   FUEL_CUDA(m, cudaMemcpyAsync(d_fo, filt_off, sizeof(int) * (ncl + 1), cudaMemcpyHostToDevice, s));
-  sample_viewpoints_kernel<<<dim3(nc, ncl), VP_THREADS, 0, s>>>(m->g, m->occ, vc, nc, d_off, d_fo, d_filt, d_avg, d_pos, d_yaw,
-                                                                d_vis);
+  sample_viewpoints_kernel<false><<<dim3(nc, ncl), VP_THREADS, 0, s>>>(m->g, m->occ, vc, nc, d_off, d_fo, d_filt, d_avg, d_pos,
+                                                                       d_yaw, d_vis, d_unc, nullptr, nullptr);
   FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
+  std::vector<int> unc(n_out);
   FUEL_CUDA(m, cudaMemcpyAsync(cand_pos, d_pos, sizeof(double) * 3 * n_out, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaMemcpyAsync(cand_yaw, d_yaw, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaMemcpyAsync(cand_visib, d_vis, sizeof(int) * n_out, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(unc.data(), d_unc, sizeof(int) * n_out, cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
+  // candidates with a FOV test on the edge: the yaw again, with the host's libm and the reference's operation order
+  // (frontier_finder.cpp:675-685, wrapYaw :776-781), and the visibility count with the normals it implies
+  std::vector<int> redo;
+  std::vector<double> hy;
+  for (size_t o = 0; o < n_out; ++o) {
+    if (!unc[o]) continue;
+    const int cl = (int)(o / nc);
+    const double* cells = filt + 3 * (size_t)filt_off[cl];
+    const int n_cells = filt_off[cl + 1] - filt_off[cl];
+    const double* pos = cand_pos + 3 * o;
+    auto normalized = [](const double v[3], double out[3]) {
+      const double z = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
+      if (z > 0) {
+        const double nrm = sqrt(z);
+        out[0] = v[0] / nrm, out[1] = v[1] / nrm, out[2] = v[2] / nrm;
+      } else
+        out[0] = v[0], out[1] = v[1], out[2] = v[2];
+    };
+    const double d0[3] = { cells[0] - pos[0], cells[1] - pos[1], cells[2] - pos[2] };
+    double ref[3];
+    normalized(d0, ref);
+    double a = 0.0;
+    for (int i = 1; i < n_cells; ++i) {
+      const double d[3] = { cells[3 * i] - pos[0], cells[3 * i + 1] - pos[1], cells[3 * i + 2] - pos[2] };
+      double dir[3];
+      normalized(d, dir);
+      double yaw = acos((dir[0] * ref[0] + dir[1] * ref[1]) + dir[2] * ref[2]);
+      if (ref[0] * dir[1] - ref[1] * dir[0] < 0) yaw = -yaw;
+      a += yaw;
+    }
+    a = a / n_cells + atan2(ref[1], ref[0]);
+    for (int it = 0; it < 64 && a < -M_PI; ++it) a += 2 * M_PI;
+    for (int it = 0; it < 64 && a > M_PI; ++it) a -= 2 * M_PI;
+    redo.push_back((int)o);
+    hy.push_back(a);
+    hy.push_back(cos(a));
+    hy.push_back(sin(a));
+  }
+  if (!redo.empty()) {
+    FUEL_CUDA(m, cudaMemcpyAsync(d_redo, redo.data(), sizeof(int) * redo.size(), cudaMemcpyHostToDevice, s));
+    FUEL_CUDA(m, cudaMemcpyAsync(d_hyaw, hy.data(), sizeof(double) * hy.size(), cudaMemcpyHostToDevice, s));
+    sample_viewpoints_kernel<true><<<(unsigned)redo.size(), VP_THREADS, 0, s>>>(m->g, m->occ, vc, nc, d_off, d_fo, d_filt, d_avg,
+                                                                               d_pos, d_yaw, d_vis, d_unc, d_redo, d_hyaw);
+    FUEL_LAUNCHES(m, 1);
+    FUEL_CUDA(m, cudaGetLastError());
+    FUEL_CUDA(m, cudaMemcpyAsync(cand_yaw, d_yaw, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s));
+    FUEL_CUDA(m, cudaMemcpyAsync(cand_visib, d_vis, sizeof(int) * n_out, cudaMemcpyDeviceToHost, s));
+    FUEL_CUDA(m, cudaStreamSynchronize(s));
+  }
   return 0;
 }

@@ -40,9 +40,13 @@ class Frontier:
 
 
 class FrontierFinder:
-    def __init__(self, edt, cluster_min=100, cluster_size_xy=2.0, down_sample=3, min_z=0.4):
-        """frontier_finder.cpp:23-49; defaults = exploration_manager/launch/algorithm.xml:103-114."""
+    def __init__(self, edt, cluster_min=100, cluster_size_xy=2.0, down_sample=3, min_z=0.4, cell_order="address"):
+        """frontier_finder.cpp:23-49; defaults = exploration_manager/launch/algorithm.xml:103-114.
+        cell_order: "address" (cells of a cluster ascending by toAddress, straight from the device) or "bfs" (the
+        reference's expandFrontier order; average_ / filtered_cells_ then equal the reference's to the last bit)."""
         self.edt_env_ = edt
+        check(lib().fuelgpu_frontier_set_cell_order(edt.sdf_map_.handle, {"address": 0, "bfs": 1}[cell_order]),
+              edt.sdf_map_.handle)
         self.cluster_min_ = int(cluster_min)
         self.cluster_size_xy_ = float(cluster_size_xy)
         self.down_sample_ = int(down_sample)

@@ -218,6 +218,14 @@ FUELGPU_API int fuelgpu_frontier_search_end(FuelMap* map, int32_t* n_clusters, i
 FUELGPU_API int fuelgpu_frontier_fetch(FuelMap* map, int32_t* cell_offsets, int32_t* cell_addr,
                            int32_t* filt_offsets, double* filtered, double* average,
                            double* box_min, double* box_max);
+/* Order of a cluster's cells in fuelgpu_frontier_fetch.  BY_ADDRESS (default): ascending toAddress, straight
+ * from the device.  BFS: the reference's own order (expandFrontier's BFS from the seed, :139-156, kept by
+ * splitHorizontally, :217-224), re-derived on the host from the fetched cell sets; average_ and filtered_cells_ are
+ * then recomputed in that order and equal the reference's to the last bit.  Cluster membership, cluster order and
+ * frontier_flag_ are the same in both modes. */
+#define FUELGPU_CELLS_BY_ADDRESS 0
+#define FUELGPU_CELLS_BFS 1
+FUELGPU_API int fuelgpu_frontier_set_cell_order(FuelMap* map, int32_t order);
 /* Replaces the resetFlag lambda of searchFrontiers (:62-69): frontier_flag_[addr] = 0. */
 FUELGPU_API int fuelgpu_frontier_clear_flags(FuelMap* map, int32_t n, const int32_t* addr);
 /* Replaces FrontierFinder::isFrontierChanged (:365-372) for m stored clusters given in CSR

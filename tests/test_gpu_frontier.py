@@ -79,6 +79,13 @@ def test_random_scene(fuel, orc, n, seed, margin, cmin, sxy, upd, min_z):
     ref_bfs, rfl2 = run_orc(orc, g, tri, upd_min, upd_max, cell_order=0, **kw)
     assert_same(gpu, ref_bfs, exact_order=False)
     assert np.array_equal(gfl, rfl2)
+    # FUELGPU_CELLS_BFS: the reference's order itself, with average_ and filtered_cells_ recomputed in it
+    gpu_bfs, gfl3 = run_gpu(fuel, g, inflate, tri, upd_min, upd_max, cell_order="bfs", **kw)
+    assert len(gpu_bfs) == len(ref_bfs) and np.array_equal(gfl3, rfl2)
+    for i, (a, b) in enumerate(zip(gpu_bfs, ref_bfs)):
+        assert np.array_equal(a.cells_addr_, b["addr"]), "cluster %d BFS order differs" % i
+        assert np.array_equal(a.average_, b["average"]), "cluster %d average_ not bit-exact" % i
+        assert np.array_equal(a.filtered_cells_, b["filtered"]), "cluster %d filtered_cells_ not bit-exact" % i
 
 
 def test_preexisting_flags_and_second_sweep(fuel, orc):

@@ -2,8 +2,8 @@
 FrontierFinder::sampleViewpoints / countVisibleCells / isFrontierCovered
 (active_perception/src/frontier_finder.cpp:662-755,697-719).
 Bar: candidate positions bit-exact (host libm on both sides), yaw <= 1e-9 rad (device vs host acos/atan2 ulps;
-NaN where the reference is NaN), visible-cell counts identical for every candidate whose FOV / range tests are not
-within 1e-9 of their thresholds (the oracle flags those "borderline")."""
+NaN where the reference is NaN), visible-cell counts IDENTICAL for every candidate: the device raises a flag when a
+FOV plane test comes within 1e-9 of zero and those candidates are redone with the yaw from the host's libm."""
 import numpy as np
 import pytest
 
@@ -24,12 +24,9 @@ def compare(orc, og, tri, inflate, vp, ftrs, pos, yaw, vis):
         fin = ok & ~np.isnan(r["yaw"])
         d = np.angle(np.exp(1j * (yaw[i][fin] - r["yaw"][fin])))
         assert np.all(np.abs(d) < 1e-9), "cluster %d yaw differs by %g" % (i, np.abs(d).max())
-        firm = ok & (r["border"] == 0)
-        assert np.array_equal(vis[i][firm], r["visib"][firm]), "cluster %d visible counts differ" % i
-        soft = ok & (r["border"] != 0)
-        assert np.all(np.abs(vis[i][soft] - r["visib"][soft]) <= 2)
-        n_checked += int(firm.sum())
-        n_border += int(soft.sum())
+        assert np.array_equal(vis[i][ok], r["visib"][ok]), "cluster %d visible counts differ" % i
+        n_checked += int(ok.sum())
+        n_border += int((ok & (r["border"] != 0)).sum())
     return n_checked, n_border
 
 
@@ -47,7 +44,7 @@ def test_office_clusters(fuel, orc):
     pos, yaw, vis = ff.sampleViewpointsRaw(ftrs)
     vp = orc.view_params()
     n_checked, n_border = compare(orc, orc_grid(orc, g), tri, inflate, vp, ftrs, pos, yaw, vis)
-    assert n_checked > 200 and n_border < 0.05 * n_checked
+    assert n_checked > 200
     # bookkeeping of computeFrontiersToVisit (:392-423)
     ff.tmp_frontiers_ = ftrs
     ff.computeFrontiersToVisit()
