@@ -499,6 +499,49 @@ def esdf512_roofline(dev, peak, peak_src, variant="V1", reps=5):
                                                                   else "V0 (file as is, mostly empty cube)")}
 
 
+def frontier512_roofline(dev, peak, peak_src, reps=4):
+    """BASELINE config 3, second half: the frontier sweep + clustering + split over the 512^3 pillar map (V1, seeded
+    known region).  Algorithmic bytes = 2 B/voxel (tri-state read + frontier_flag_ read-modify-write)."""
+    import torch
+
+    import fuel_b200
+    from fuel_b200 import workloads as W
+    g, inflate = W.pillar_map("V1")
+    tri = W.known_region(g, inflate, seed=7, n_poses=64, radius=4.5)
+    m = fuel_b200.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max, device=dev)
+    m.occupancy_buffer_inflate_[...] = inflate
+    m.setOccupancyBuffer(tristate=tri)
+    m.upload()
+    env = fuel_b200.EDTEnvironment()
+    env.setMap(m)
+    ff = fuel_b200.FrontierFinder(env)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:%d" % dev)
+    ms, wall = [], []
+    ncl = ncell = 0
+    for i in range(reps + 1):
+        ff.reset_flags()
+        flush.zero_()
+        m.synchronize()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        out = ff.search_box(g.origin, g.map_max)
+        t1 = time.perf_counter()
+        if i >= 1:
+            ms.append(m.last_timing()["frontier"])
+            wall.append(1e3 * (t1 - t0))
+        ncl, ncell = len(out), int(sum(c.cells_addr_.size for c in out))
+    m.close()
+    t = float(np.mean(ms)) * 1e-3
+    alg = 2.0 * g.nvox
+    ach = alg / t / 1e9
+    return {"kernel": "frontier_search 512^3 (classify sweep + union-find + claims + level-synchronous PCA split)",
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": profile_traffic("frontier512"), "algorithmic_bytes": alg, "ms": 1e3 * t,
+            "wall_ms_incl_fetch": float(np.mean(wall)), "n_clusters": ncl, "n_cells": ncell, "peak_source": peak_src,
+            "workload": "pillar.pcd V1 on 512^3 @0.1m, known region = 64 seeded 4.5 m balls, frontier_flag_ reset, search "
+                        "box = whole map; device time of the frontier stream (events), L2 flushed before every search"}
+
+
 def sharded_esdf_arm(local, rank, world, reps=5):
     """BASELINE config 4: synthetic 1024x1024x256 map, z-sharded ESDF over all ranks (fuelgpu_sharded_esdf_*,
     NCCL called inside the library).  Collective: every rank calls it.  Device time = max over ranks.  Also runs
@@ -518,20 +561,44 @@ def sharded_esdf_arm(local, rank, world, reps=5):
     sh = ShardedESDF(npar, g.res, optimistic=True, device=local)
     z0, z1 = sh.z_range()
     occ = torch.from_numpy(((inflate[:, :, z0:z1] << 2) | 1).astype(np.uint8)).contiguous().to(dev)
-    full = sh.gather_full(sh.update(occ)).cpu().numpy()
-    sh.close()
+    slab = sh.update(occ)
+    full = sh.gather_full(slab).cpu().numpy()
     m = fuel_b200.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max, optimistic=True, device=local)
     m.occupancy_buffer_inflate_[...] = inflate
     m.occupancy_tri_[...] = 1
     m.upload()
     m.updateESDF3d()
     ref = m.download().copy()
-    m.close()
     fin = np.isfinite(ref)
     ok = bool(np.array_equal(np.isinf(full), ~fin) and np.allclose(full[fin], ref[fin], rtol=1e-6, atol=0))
-    flag = torch.tensor([1 if ok else 0], device=dev)
+    # one planner, G GPUs: the gathered field installed in a second map, the trajectory batch split
+    # over the ranks, results gathered -- must equal the whole batch solved on this rank's own ESDF, bit for bit
+    from fuel_b200.dist import optimize_batch_split
+    m2 = fuel_b200.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max, optimistic=True, device=local)
+    sh.gather_into_map(slab, m2)
+    tr = W.make_trajectories(g, inflate, B=96, n_pts=20, seed=31)
+    x0 = W.pack_x(tr["ctrl"], tr["dt"])
+    ok_split = True
+    res = []
+    for mm in (m, m2):
+        env = fuel_b200.EDTEnvironment()
+        env.setMap(mm)
+        opt = fuel_b200.BsplineOptimizer()
+        opt.setEnvironment(env)
+        tcs = opt.traj_consts_from_arrays(tr["pt_dist"], tr["dt"], tr["start"], tr["end_pos"])
+        mask = opt.NORMAL_PHASE | opt.MINTIME
+        if mm is m:
+            res.append(tuple(a.copy() for a in opt.optimizeBatch(x0, tcs, 20, mask, 32)))
+        else:
+            res.append(optimize_batch_split(opt, x0, tcs, 20, mask, 32))
+    ok_split = all(np.array_equal(a, b) for a, b in zip(res[0], res[1]))
+    m.close()
+    m2.close()
+    sh.close()
+    flag = torch.tensor([1 if ok else 0, 1 if ok_split else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    out["parity_vs_single_gpu"] = {"map": list(npar), "ok_all_ranks": bool(int(flag.item()) == 1)}
+    out["parity_vs_single_gpu"] = {"map": list(npar), "ok_all_ranks": bool(int(flag[0].item()) == 1),
+                                   "split_batch_equals_whole_batch": bool(int(flag[1].item()) == 1)}
     # ---- timing on the config-4 map ----
     n = (1024, 1024, 256)
     g, inflate = W.random_boxes_map(n=n, seed=11, n_boxes=4096)
@@ -783,6 +850,10 @@ def run_ours(args):
             extra["roofline_esdf512_v0"] = esdf512_roofline(local, peak, peak_src, "V0")
         except Exception as e:  # noqa: BLE001
             extra["roofline_esdf512"] = {"error": repr(e)}
+        try:
+            extra["roofline_frontier512"] = frontier512_roofline(local, peak, peak_src)
+        except Exception as e:  # noqa: BLE001
+            extra["roofline_frontier512"] = {"error": repr(e)}
 
         try:
             extra["next_rows"] = next_rows_timing(local)

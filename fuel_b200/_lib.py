@@ -136,6 +136,7 @@ SIGNATURES = {
     "fuelgpu_sharded_esdf_bytes_exchanged": (_i64, [_vp]),
     "fuelgpu_sharded_esdf_allgather": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fuelgpu_sharded_esdf_destroy": (C.c_int, [_vp]),
+    "fuelgpu_esdf_set_from_slabs_dev": (C.c_int, [_vp, _vp, _i32]),
 }
 
 _lib = None

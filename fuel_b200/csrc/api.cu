@@ -41,6 +41,19 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restri
   out[i] = isinf(v) ? (v > 0 ? inf_value : -inf_value) : (double)v;
 }
 
+// [G][nx][ny][nzl] z-slabs (the all-gather of a z-sharded ESDF) -> [nx][ny][G*nzl]
+__global__ void slabs_to_volume_kernel(const float* __restrict__ slabs, float* __restrict__ dist, int64_t nxy, int nzl,
+                                       int G) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = nxy * nzl * G;
+  if (i >= total) return;
+  const int nz = nzl * G;
+  const int z = (int)(i % nz);
+  const int64_t xy = i / nz;
+  const int gsl = z / nzl;
+  dist[i] = slabs[((int64_t)gsl * nxy + xy) * nzl + (z - gsl * nzl)];
+}
+
 __global__ void clear_flags_kernel(int8_t* flag, const int* __restrict__ addr, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flag[addr[i]] = 0;
@@ -475,6 +488,21 @@ int fuelgpu_esdf_download(FuelMap* m, const int32_t bmin[3], const int32_t bmax[
   }
   tend(m, T_DOWNLOAD);
   FUEL_CUDA(m, cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int fuelgpu_esdf_set_from_slabs_dev(FuelMap* m, const void* slabs_dev, int32_t n_slabs) {
+  if (!m || !slabs_dev) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (n_slabs < 1 || m->g.nz % n_slabs) return fuel_fail(m, FUELGPU_EINVAL, "nz is not a multiple of the slab count");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  if (n_slabs == 1) {
+    FUEL_CUDA(m, cudaMemcpyAsync(m->dist, slabs_dev, sizeof(float) * m->nvox, cudaMemcpyDeviceToDevice, m->stream));
+  } else {
+    slabs_to_volume_kernel<<<(unsigned)((m->nvox + 255) / 256), 256, 0, m->stream>>>(
+        (const float*)slabs_dev, m->dist, (int64_t)m->g.nx * m->g.ny, m->g.nz / n_slabs, n_slabs);
+    FUEL_LAUNCHES(m, 1);
+    FUEL_CUDA(m, cudaGetLastError());
+  }
   return 0;
 }
 

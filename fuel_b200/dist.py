@@ -165,6 +165,19 @@ class ShardedESDF:
         # 4. x stage on the z-slab
         return x_fn(part_z)
 
+    def gather_into_map(self, dist_zslab, sdf_map):
+        """all-gather the z-slabs and install the full field as `sdf_map`'s distance_buffer_ on this rank's device: the
+        one ESDF broadcast of a planner that splits its trajectory batch over the ranks (then no further collective)."""
+        nx, ny, nz = self.n
+        buf = torch.empty((self.G, nx, ny, self.nzl), dtype=torch.float32, device=dist_zslab.device)
+        st = torch.cuda.current_stream(dist_zslab.device).cuda_stream
+        L = _lib.lib()
+        _lib.check(L.fuelgpu_sharded_esdf_allgather(self.handle, C.c_void_p(st), C.c_void_p(dist_zslab.contiguous().data_ptr()),
+                                                    C.c_void_p(buf.data_ptr())))
+        torch.cuda.current_stream(dist_zslab.device).synchronize()  # the map's own stream reads buf next
+        _lib.check(L.fuelgpu_esdf_set_from_slabs_dev(sdf_map.handle, C.c_void_p(buf.data_ptr()), self.G), sdf_map.handle)
+        sdf_map.synchronize()
+
     def gather_full(self, dist_zslab):
         """all-gather the z-slabs: every rank gets the full [nx,ny,nz] ESDF."""
         nx, ny, nz = self.n
@@ -178,3 +191,53 @@ class ShardedESDF:
         parts = [torch.empty_like(dist_zslab) for _ in range(self.G)]
         dist.all_gather(parts, dist_zslab.contiguous(), group=self.group)
         return torch.cat(parts, dim=2)
+
+
+def split_counts(B, G):
+    """even split of a batch of B over G ranks: the first B % G ranks take one more"""
+    base, extra = divmod(int(B), int(G))
+    cnt = [base + (1 if r < extra else 0) for r in range(G)]
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    return cnt, off
+
+
+def split_batch_run(fn, B, group=None, device=None):
+    """One planner, G GPUs: rank r runs fn(lo, hi) on its share [lo, hi) of a batch of B independent
+    trajectories -- fn returns a tuple of numpy arrays whose first axis is hi - lo -- and every rank gets the results
+    of the whole batch in the original order.  The only communication is this gather of the (small) results; the ESDF
+    must already be on every rank (ShardedESDF.gather_into_map)."""
+    G = dist.get_world_size(group)
+    r = dist.get_rank(group)
+    cnt, off = split_counts(B, G)
+    mine = fn(int(off[r]), int(off[r + 1]))
+    out = []
+    nccl = dist.get_backend(group) == "nccl"
+    mx = max(cnt)
+    for a in mine:
+        a = np.ascontiguousarray(a)
+        assert a.shape[0] == cnt[r]
+        pad = np.zeros((mx,) + a.shape[1:], dtype=a.dtype)
+        pad[:cnt[r]] = a
+        t = torch.from_numpy(pad)
+        if nccl:
+            t = t.to("cuda:%d" % (torch.cuda.current_device() if device is None else device))
+        parts = [torch.empty_like(t) for _ in range(G)]
+        dist.all_gather(parts, t, group=group)
+        out.append(np.concatenate([parts[k][:cnt[k]].cpu().numpy() for k in range(G)], axis=0))
+    return tuple(out)
+
+
+def optimize_batch_split(opt, x, traj_consts, n_pts, cost_function, max_eval, group=None, **kw):
+    """BsplineOptimizer.optimizeBatch of a whole batch spread over the ranks of `group` (each rank's optimizer must sit
+    on a map holding the full ESDF).  Returns (x_best, f_best, n_eval) of the whole batch on every rank."""
+    from ._lib import FuelTrajConst
+    x = np.ascontiguousarray(x, dtype=np.float64)
+
+    def run(lo, hi):
+        if hi == lo:
+            return (np.empty((0, x.shape[1])), np.empty(0), np.empty(0, dtype=np.int32))
+        tc = (FuelTrajConst * (hi - lo)).from_buffer(traj_consts, lo * C.sizeof(FuelTrajConst))
+        xb, fb, ne = opt.optimizeBatch(x[lo:hi], tc, n_pts, cost_function, max_eval, **kw)
+        return xb.copy(), fb.copy(), ne.copy()
+
+    return split_batch_run(run, x.shape[0], group)

@@ -384,6 +384,12 @@ FUELGPU_API int64_t fuelgpu_sharded_esdf_bytes_exchanged(const FuelShardedEsdf* 
 FUELGPU_API int fuelgpu_sharded_esdf_allgather(FuelShardedEsdf* s, void* cuda_stream, const void* dist_slab_dev,
                                                void* out_dev);
 FUELGPU_API int fuelgpu_sharded_esdf_destroy(FuelShardedEsdf* s);
+/* Replace the map's distance_buffer_ by a field computed elsewhere: n_slabs == 1: slabs_dev is [nx][ny][nz] float32;
+ * n_slabs == G: slabs_dev is the all-gather buffer [G][nx][ny][nz/G] of fuelgpu_sharded_esdf_allgather.  Device to
+ * device on the map's stream.  This is the "broadcast the ESDF once" step of a planner that splits its trajectory
+ * batch over several GPUs (precedent: the reference's per-thread optimizers share one read-only map,
+ * plan_manage/src/planner_manager.cpp:444-453). */
+FUELGPU_API int fuelgpu_esdf_set_from_slabs_dev(FuelMap* map, const void* slabs_dev, int32_t n_slabs);
 #define FUELGPU_EDT_INF 0x3fffffff
 
 /* Library / device info.  Fills name with the device name; returns the SM count or <0. */

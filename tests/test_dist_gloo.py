@@ -87,3 +87,42 @@ def test_z_sharded_esdf_two_ranks(orc):
         assert got.shape == n
         assert np.allclose(got, ref, rtol=1e-6), "rank %d" % r
     assert np.array_equal(ret[0], ret[1])
+
+
+def split_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fuel_b200.dist import split_batch_run, split_counts
+    B = 11  # uneven split
+    x = np.arange(B * 3, dtype=np.float64).reshape(B, 3)
+    cnt, off = split_counts(B, world)
+    assert sum(cnt) == B and max(cnt) - min(cnt) <= 1 and off[-1] == B
+    calls = []
+
+    def fn(lo, hi):
+        calls.append((lo, hi))
+        return x[lo:hi] * 2.0, x[lo:hi, 0] + 1.0, np.full(hi - lo, rank, dtype=np.int32)
+
+    a, b, c = split_batch_run(fn, B)
+    assert calls == [(int(off[rank]), int(off[rank + 1]))]
+    ret[rank] = (a, b, c)
+    dist.destroy_process_group()
+
+
+def test_batch_split_over_ranks():
+    """One planner on G GPUs: the trajectory batch is cut evenly, each rank runs its share, every rank gets the whole
+    result in the original order (fuel_b200.dist.split_batch_run)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(split_worker, args=(2, port, ret), nprocs=2, join=True)
+    x = np.arange(33, dtype=np.float64).reshape(11, 3)
+    for r in (0, 1):
+        a, b, c = ret[r]
+        assert np.array_equal(a, x * 2.0) and np.array_equal(b, x[:, 0] + 1.0)
+        assert list(c) == [0] * 6 + [1] * 5
