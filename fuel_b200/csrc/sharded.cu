@@ -227,23 +227,22 @@ int fuelgpu_sharded_esdf_update(FuelShardedEsdf* s, void* cuda_stream, const voi
   // 2. records of my x range (z lines assembled from the G chunks)
   int rc = edt_stage_zpack(st, s->occ_x, s->rec, s->nxl, s->ny, s->nzl, G, (int64_t)chunk, mode);
   if (rc) return fuel_fail(nullptr, rc, "zpack stage failed");
-  // 2+3. zy tiles destination by destination; round k's transfer overlaps round k+1's tiles
-  for (int k = 0; k < G; ++k) {
+  // 2+3. zy tiles destination by destination, the peers first and this rank's own block last (it needs no
+  // transfer and is written straight into the receive buffer); round k's transfer overlaps round k+1's tiles
+  for (int kk = 0; kk < G; ++kk) {
+    const int k = (kk + 1) % G;  // 1, 2, ..., G-1, 0
     const int d = (r + k) % G, src = (r - k + G) % G;
-    rc = edt_stage_zy(st, s->rec, s->nxl, s->ny, s->NW, d * s->wl, s->wl, s->psend + (size_t)d * s->blk, 32,
-                      (int64_t)s->ny * s->nxl * 32, (int64_t)s->nxl * 32);
+    int32_t* dstP = d == r ? s->precv + (size_t)r * s->blk : s->psend + (size_t)d * s->blk;
+    rc = edt_stage_zy(st, s->rec, s->nxl, s->ny, s->NW, d * s->wl, s->wl, dstP, 32, (int64_t)s->ny * s->nxl * 32,
+                      (int64_t)s->nxl * 32);
     if (rc) return fuel_fail(nullptr, rc, "zy stage failed");
+    if (d == r) continue;
     FUEL_CUDA(nullptr, cudaEventRecord(s->ev_round[k], st));
     FUEL_CUDA(nullptr, cudaStreamWaitEvent(s->comm_stream, s->ev_round[k], 0));
-    if (d == r) {
-      FUEL_CUDA(nullptr, cudaMemcpyAsync(s->precv + (size_t)r * s->blk, s->psend + (size_t)r * s->blk, s->blk * 4,
-                                         cudaMemcpyDeviceToDevice, s->comm_stream));
-    } else {
-      FUEL_NCCL(g_nccl.GroupStart());
-      FUEL_NCCL(g_nccl.Send(s->psend + (size_t)d * s->blk, s->blk, ncclInt32, d, c->comm, s->comm_stream));
-      FUEL_NCCL(g_nccl.Recv(s->precv + (size_t)src * s->blk, s->blk, ncclInt32, src, c->comm, s->comm_stream));
-      FUEL_NCCL(g_nccl.GroupEnd());
-    }
+    FUEL_NCCL(g_nccl.GroupStart());
+    FUEL_NCCL(g_nccl.Send(s->psend + (size_t)d * s->blk, s->blk, ncclInt32, d, c->comm, s->comm_stream));
+    FUEL_NCCL(g_nccl.Recv(s->precv + (size_t)src * s->blk, s->blk, ncclInt32, src, c->comm, s->comm_stream));
+    FUEL_NCCL(g_nccl.GroupEnd());
   }
   FUEL_CUDA(nullptr, cudaEventRecord(s->ev_t[2], st));
   FUEL_CUDA(nullptr, cudaEventRecord(s->ev_comm_done, s->comm_stream));

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round-2 evidence run (one B200, under gpurun): bench lines, launch lists, ncu --set full of the ESDF kernels.
+# Numbers printed under ncu are never bench values; the bench JSONs come from separate runs.
+mkdir -p gpurun_out
+python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2>> gpurun_out/r02_bench.err
+# every launch of two bench steps with its device time (cold-cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 40 --csv --log-file gpurun_out/r02_launches_office.csv \
+    python bench.py --steps 4 --warmup 3 --no-esdf512 > /dev/null 2>&1
+# one whole 512^3 ESDF update in steady state: every kernel, DRAM bytes, instructions (caches left alone)
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active \
+    --cache-control none --clock-control none -k regex:"zpack|envelope" -s 33 -c 33 --csv --log-file gpurun_out/r02_esdf512_launches.csv \
+    python tools/esdf512.py V1 2 > /dev/null 2>&1
+# ncu --set full of the three ESDF kernels (zpack, zy tile, x tile) of the second update
+ncu --set full --import-source on --cache-control none --clock-control none -k regex:"zpack|envelope" -s 33 -c 3 \
+    -o gpurun_out/r02_esdf512_full python tools/esdf512.py V1 2 > /dev/null 2>&1
+# 512^3 frontier search: every kernel
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --cache-control none --clock-control none \
+    -s 60 -c 200 --csv --log-file gpurun_out/r02_frontier512_launches.csv python tools/frontier512.py > /dev/null 2>&1
+ls -la gpurun_out
