@@ -52,7 +52,7 @@ class FuelViewParams(C.Structure):
 class FuelOptParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in
                 ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide", "ld_waypt",
-                 "ld_view", "ld_time", "dist0", "max_vel", "max_acc")] + [("order", C.c_int32)]
+                 "ld_view", "ld_time", "dist0", "max_vel", "max_acc")] + [("order", C.c_int32), ("wnl", C.c_double)]
 
 
 class FuelTrajConst(C.Structure):
@@ -60,7 +60,8 @@ class FuelTrajConst(C.Structure):
                 ("start", (C.c_double * 3) * 3), ("end", (C.c_double * 3) * 3),
                 ("n_end", C.c_int32), ("time_lb", C.c_double), ("n_guide", C.c_int32),
                 ("guide", (C.c_double * 3) * MAX_PTS), ("n_waypt", C.c_int32),
-                ("waypt", (C.c_double * 3) * MAX_PTS), ("waypt_idx", C.c_int32 * MAX_PTS)]
+                ("waypt", (C.c_double * 3) * MAX_PTS), ("waypt_idx", C.c_int32 * MAX_PTS),
+                ("view_pt", C.c_double * 3), ("view_dir", C.c_double * 3), ("view_idx", C.c_int32)]
 
 
 class FuelSolveParams(C.Structure):

@@ -47,9 +47,10 @@ class BsplineOptimizer:
     def setParam(self, ld_smooth=20.0, ld_dist=10.0, ld_feasi=2.0, ld_start=100.0, ld_end=0.5, ld_guide=1.5,
                  ld_waypt=0.3, ld_view=0.0, ld_time=1.0, dist0=0.7, max_vel=2.0, max_acc=2.0,
                  bspline_degree=3, max_iteration_num=(2, 2000, 200, 200),
-                 max_iteration_time=(0.0001, 0.005, 0.003, 0.003)):
+                 max_iteration_time=(0.0001, 0.005, 0.003, 0.003), wnl=0.0):
         """bspline_optimizer.cpp:25-57; defaults = exploration_manager/launch/algorithm.xml:170-192."""
         p = FuelOptParams()
+        p.wnl = wnl
         (p.ld_smooth, p.ld_dist, p.ld_feasi, p.ld_start, p.ld_end, p.ld_guide, p.ld_waypt, p.ld_view,
          p.ld_time, p.dist0, p.max_vel, p.max_acc, p.order) = (ld_smooth, ld_dist, ld_feasi, ld_start, ld_end,
                                                                ld_guide, ld_waypt, ld_view, ld_time, dist0,
@@ -80,6 +81,10 @@ class BsplineOptimizer:
         self.waypoints_ = [np.asarray(w, dtype=np.float64) for w in waypts]
         self.waypt_idx_ = list(waypt_idx)
 
+    def setViewConstraint(self, pt, direction, idx):
+        """setViewConstraint(vc) (:91-93): the fields calcViewCost reads (vc.pt_, vc.dir_, vc.idx_)."""
+        self.view_cons_ = (np.asarray(pt, dtype=np.float64), np.asarray(direction, dtype=np.float64), int(idx))
+
     # ---- per-trajectory constants (what optimize() freezes, :116-141) ----------------------
     @staticmethod
     def pt_dist(ctrl):
@@ -92,7 +97,13 @@ class BsplineOptimizer:
 
     @staticmethod
     def fill_traj_const(tc, pt_dist, knot_span, start, end, time_lb=-1.0, guide=None, waypt=None,
-                        waypt_idx=None):
+                        waypt_idx=None, view=None):
+        tc.view_idx = -1
+        if view is not None:
+            for k in range(3):
+                tc.view_pt[k] = float(view[0][k])
+                tc.view_dir[k] = float(view[1][k])
+            tc.view_idx = int(view[2])
         tc.pt_dist = float(pt_dist)
         tc.knot_span = float(knot_span)
         start = np.asarray(start, dtype=np.float64).reshape(3, 3)
@@ -144,6 +155,7 @@ class BsplineOptimizer:
         put("end", e, np.float64)
         put("n_end", np.ones(B), np.int32)
         put("time_lb", -np.ones(B) if time_lb is None else time_lb, np.float64)
+        put("view_idx", -np.ones(B), np.int32)
         return arr
 
     def nvar(self, n_pts, mask):
@@ -221,7 +233,8 @@ class BsplineOptimizer:
         for i, s in enumerate(self.start_state_[:3]):
             start[i] = s
         self.fill_traj_const(tc[0], self.pt_dist_, dt, start, np.asarray(self.end_state_).reshape(-1, 3),
-                             self.time_lb_, self.guide_pts_, self.waypoints_, self.waypt_idx_)
+                             self.time_lb_, self.guide_pts_, self.waypoints_, self.waypt_idx_,
+                             getattr(self, "view_cons_", None))
         return tc
 
     def costFunction(self, x):

@@ -673,8 +673,8 @@ int fuelgpu_frontier_upload_flags(FuelMap* m, const int8_t* in) {
 // page-locked bounce buffer, one contiguous DMA, then two strided device-side copies into the records.
 // `pin` = host bounce area of >= B*(head+4) bytes, `d_pack` = device scratch of the same size.
 static cudaError_t upload_traj(FuelMap* m, FuelTrajConst* d_tc, const FuelTrajConst* traj, int B, uint8_t* pin,
-                               uint8_t* d_pack) {
-  bool lean = true;
+                               uint8_t* d_pack, int mask = 0) {
+  bool lean = !(mask & FUELGPU_VIEWCONS);  // the view constraint sits at the end of the record
   for (int b = 0; b < B && lean; ++b) lean = traj[b].n_guide == 0 && traj[b].n_waypt == 0;
   if (!lean) return cudaMemcpyAsync(d_tc, traj, sizeof(FuelTrajConst) * (size_t)B, cudaMemcpyHostToDevice, m->stream);
   const size_t head = offsetof(FuelTrajConst, guide), rec = head + sizeof(int32_t);
@@ -696,9 +696,6 @@ static int check_bspline_args(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask
   if (B < 0) return fuel_fail(m, FUELGPU_EINVAL, "negative batch");
   if (n_pts < 4 || n_pts > FUELGPU_MAX_PTS)
     return fuel_fail(m, FUELGPU_EINVAL, "n_pts must be in 4..64");
-  if (mask & FUELGPU_VIEWCONS)
-    return fuel_fail(m, FUELGPU_EUNSUPPORTED,
-                     "VIEWCONS is not supported (ld_view = 0.0 in every reference launch file)");
   if (p->order < 1 || 2 * p->order >= n_pts) return fuel_fail(m, FUELGPU_EINVAL, "bad spline order");
   return 0;
 }
@@ -748,7 +745,11 @@ int fuelgpu_bspline_cost_batch(FuelMap* m, int32_t B, int32_t n_pts, int32_t mas
   double* h_x = (double*)(pin + packb);
   double* h_g = h_x + (size_t)B * nvar;
   double* h_f = h_g + (size_t)B * nvar;
-  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack));
+  if (mask & FUELGPU_VIEWCONS)
+    for (int b = 0; b < B; ++b)
+      if (traj[b].view_idx < 0 || traj[b].view_idx >= n_pts)
+        return fuel_fail(m, FUELGPU_EINVAL, "VIEWCONS needs FuelTrajConst.view_idx in [0, n_pts) (setViewConstraint)");
+  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack, mask));
   memcpy(h_x, x, xb);
   FUEL_CUDA(m, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, m->stream));
   tbegin(m, T_BSPLINE);
@@ -809,7 +810,11 @@ int fuelgpu_bspline_optimize_batch_begin(FuelMap* m, int32_t B, int32_t n_pts, i
   // host buffers of unknown provenance (pageable or pinned) bounce through the page-locked area
   uint8_t* pin = (uint8_t*)m->bs_pin;
   double* h_x = (double*)(pin + packb);  // x, f_best, n_eval adjacent on both sides: one DMA back
-  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack));
+  if (mask & FUELGPU_VIEWCONS)
+    for (int b = 0; b < B; ++b)
+      if (traj[b].view_idx < 0 || traj[b].view_idx >= n_pts)
+        return fuel_fail(m, FUELGPU_EINVAL, "VIEWCONS needs FuelTrajConst.view_idx in [0, n_pts) (setViewConstraint)");
+  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack, mask));
   memcpy(h_x, x, xb);
   FUEL_CUDA(m, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, m->stream));
   tbegin(m, T_BSPLINE);

@@ -232,6 +232,15 @@ __device__ void combine_cost_thread(const Geom& g, const float* __restrict__ dis
     for (int i = 0; i < n; i++)
       for (int k = 0; k < 3; k++) grad[3 * i + k] += p.ld_waypt * gq[i][k];
   }
+  if (mask & FUELGPU_VIEWCONS) {  // calcViewCost :477-502
+    const int idx = tc.view_idx;
+    if (idx >= 0 && idx < n) {
+      double gv[3];
+      const double c = view_cost_point(q[idx], tc.view_pt, tc.view_dir, p.wnl, gv);
+      f_combine += p.ld_view * c;
+      for (int k = 0; k < 3; k++) grad[3 * idx + k] += p.ld_view * gv[k];
+    }
+  }
   if (mask & FUELGPU_MINTIME) {  // calcTimeCost :504-516
     const double duration = (n - p.order) * dt;
     double cost = duration;

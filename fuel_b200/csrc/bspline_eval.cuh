@@ -76,6 +76,60 @@ __device__ __forceinline__ double up(double v, int d, int lane) {
   return lane >= d ? r : 0.0;
 }
 
+
+// calcViewCost (bspline_optimizer.cpp:477-502) for the constrained control point qi = q[view_idx]: returns the
+// cost and the gradient row of that point (all other rows are zero).  Eigen's expressions evaluated element-wise
+// in written order (v = dir/sqrt(dir.dir); dn = qp - (qp.v) v; g = (2 (I - v vT)) dn; dl = (qp.v) v; if |dl| < |dir|:
+// cost += wnl (|dl| - |dir|)^2, g += ((wnl 2 (|dl| - |dir|)) v vT) dl / |dl|).
+__device__ __forceinline__ double view_cost_point(const double qi[3], const double* __restrict__ pt,
+                                                  const double* __restrict__ dir, double wnl, double g[3]) {
+  const double zz = dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2];
+  double v[3] = { dir[0], dir[1], dir[2] };
+  if (zz > 0) {
+    const double nrm = sqrt(zz);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = dir[k] / nrm;
+  }
+  const double qp[3] = { qi[0] - pt[0], qi[1] - pt[1], qi[2] - pt[2] };
+  const double s = qp[0] * v[0] + qp[1] * v[1] + qp[2] * v[2];
+  double dn[3], dl[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    dl[k] = s * v[k];
+    dn[k] = qp[k] - dl[k];
+  }
+  double cost = dn[0] * dn[0] + dn[1] * dn[1] + dn[2] * dn[2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double ivv = (r == c ? 1.0 : 0.0) - v[r] * v[c];
+      const double term = (2 * ivv) * dn[c];
+      acc = c == 0 ? term : acc + term;
+    }
+    g[r] = acc;
+  }
+  const double norm_dl = sqrt(dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+  const double safe_dist = sqrt(zz);
+  if (norm_dl < safe_dist) {
+    const double e = norm_dl - safe_dist;
+    cost += wnl * (e * e);
+    const double cc = wnl * 2 * e;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double term = (cc * (v[r] * v[c])) * dl[c];
+        acc = c == 0 ? term : acc + term;
+      }
+      g[r] += acc / norm_dl;
+    }
+  }
+  return cost;
+}
+
 struct TrajRegs {  // loop-invariant per-trajectory constants, loaded once
   double pt_dist, knot_span, time_lb;
   double start[3][3];
@@ -456,6 +510,20 @@ __device__ __forceinline__ void eval_warp(const Geom& g, const float* __restrict
     f += p.ld_waypt * cost;
 #pragma unroll
     for (int k = 0; k < 3; ++k) gr[k] += p.ld_waypt * gq[k];
+  }
+  if (mask & FUELGPU_VIEWCONS) {  // calcViewCost :477-502: one control point, every lane evaluates it (no reduction)
+    const int idx = tc->view_idx;
+    if (idx >= 0 && idx < n) {
+      double qi[3], gv[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) qi[k] = __shfl_sync(0xffffffffu, q[k], idx);
+      const double c = view_cost_point(qi, tc->view_pt, tc->view_dir, p.wnl, gv);
+      f += p.ld_view * c;
+      if (lane == idx) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gr[k] += p.ld_view * gv[k];
+      }
+    }
   }
   if (mask & FUELGPU_MINTIME) {  // calcTimeCost :504-516
     const double duration = (n - p.order) * dt;

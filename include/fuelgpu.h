@@ -277,7 +277,7 @@ FUELGPU_API int fuelgpu_frontier_changed_counts(FuelMap* map, int32_t n_clusters
 #define FUELGPU_END (1 << 4)
 #define FUELGPU_GUIDE (1 << 5)
 #define FUELGPU_WAYPOINTS (1 << 6)
-#define FUELGPU_VIEWCONS (1 << 7) /* rejected: ld_view is 0.0 in every launch file (algorithm.xml:177) */
+#define FUELGPU_VIEWCONS (1 << 7) /* calcViewCost :477-502; needs FuelTrajConst.view_idx >= 0 */
 #define FUELGPU_MINTIME (1 << 8)
 /* not a cost term: evaluate with the solver loop's evaluator (fuelgpu_bspline_optimize_batch runs it: fp32
  * trilinear lerps on the fp32 ESDF samples, reciprocals, FMA contraction) instead of the faithful one; same
@@ -289,6 +289,7 @@ typedef struct {
   double ld_smooth, ld_dist, ld_feasi, ld_start, ld_end, ld_guide, ld_waypt, ld_view, ld_time;
   double dist0, max_vel, max_acc;
   int32_t order; /* order_ = bspline_degree_ */
+  double wnl;    /* wnl_ (optimization/wnl, :44): weight of the parallel part of calcViewCost */
 } FuelOptParams;
 
 #define FUELGPU_MAX_PTS 64
@@ -306,6 +307,9 @@ typedef struct {
   int32_t n_waypt;    /* waypoints_.size()                        */
   double waypt[FUELGPU_MAX_PTS][3];
   int32_t waypt_idx[FUELGPU_MAX_PTS];
+  double view_pt[3];  /* view_cons_.pt_  (setViewConstraint :91-93)  */
+  double view_dir[3]; /* view_cons_.dir_ (its length = safe distance) */
+  int32_t view_idx;   /* view_cons_.idx_; < 0: none set (VIEWCONS then returns FUELGPU_EINVAL) */
 } FuelTrajConst;
 
 /* Replaces BsplineOptimizer::combineCost (bspline_optimizer.cpp:518-647) and the calc*Cost

@@ -496,6 +496,12 @@ public:
     waypoints_ = waypts;
     waypt_idx_ = waypt_idx;
   }
+  // setViewConstraint (:91-93): the fields of ViewConstraint (traj_visibility.h:18-24) that calcViewCost reads
+  void setViewConstraint(const Vector3d& pt, const Vector3d& dir, int idx) {
+    view_pt_ = pt;
+    view_dir_ = dir;
+    view_idx_ = idx;
+  }
 
   // optimize (:110-163): points = N x 3 control points, row-major; dt in/out.  The NLopt driver
   // loop (:165-253) runs on the device (fuelgpu_bspline_optimize_batch, B = 1).
@@ -555,6 +561,11 @@ public:
       for (int k = 0; k < 3; ++k) tc_.waypt[i][k] = waypoints_[i](k);
       tc_.waypt_idx[i] = waypt_idx_[i];
     }
+    tc_.view_idx = view_idx_;
+    for (int k = 0; k < 3; ++k) {
+      tc_.view_pt[k] = view_pt_(k);
+      tc_.view_dir[k] = view_dir_(k);
+    }
   }
   int iter_num_ = 0;
   double min_cost_ = 0;
@@ -566,6 +577,8 @@ private:
   int max_iteration_num_[4] = { 2, 2000, 200, 200 };
   std::vector<Vector3d> start_state_, end_state_, guide_pts_, waypoints_;
   std::vector<int> waypt_idx_;
+  Vector3d view_pt_, view_dir_;
+  int view_idx_ = -1;
   double time_lb_ = -1;
 };
 

@@ -74,7 +74,7 @@ class OrcOptParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in
                 ("ld_smooth", "ld_dist", "ld_feasi", "ld_start", "ld_end", "ld_guide",
                  "ld_waypt", "ld_view", "ld_time", "dist0", "max_vel", "max_acc")] + [
-                     ("order", C.c_int32)]
+                     ("order", C.c_int32), ("wnl", C.c_double)]
 
 
 class OrcTrajConst(C.Structure):
@@ -82,7 +82,8 @@ class OrcTrajConst(C.Structure):
                 ("start", (C.c_double * 3) * 3), ("end", (C.c_double * 3) * 3),
                 ("n_end", C.c_int32), ("time_lb", C.c_double), ("n_guide", C.c_int32),
                 ("guide", (C.c_double * 3) * ORC_MAX_PTS), ("n_waypt", C.c_int32),
-                ("waypt", (C.c_double * 3) * ORC_MAX_PTS), ("waypt_idx", C.c_int32 * ORC_MAX_PTS)]
+                ("waypt", (C.c_double * 3) * ORC_MAX_PTS), ("waypt_idx", C.c_int32 * ORC_MAX_PTS),
+                ("view_pt", C.c_double * 3), ("view_dir", C.c_double * 3), ("view_idx", C.c_int32)]
 
 
 class OrcSolveParams(C.Structure):
@@ -412,7 +413,7 @@ class RefBsplineOptimizer:
             self.h = None
 
     def evaluate(self, ctrl, dt, cost_function, start, end, guide=None, waypts=None, waypt_idx=None, time_lb=-1.0,
-                 probes=None):
+                 probes=None, view=None):
         """optimize(points, dt, cost_function, 1, 1) with the NLopt stand-in -> dict(f [1+P], grad [1+P,nvar], x0, lb, ub):
         the reference's objective at its own start point x0 and at the P probe points."""
         ctrl = np.ascontiguousarray(ctrl, dtype=np.float64).reshape(-1, 3)
@@ -428,6 +429,9 @@ class RefBsplineOptimizer:
         f = np.zeros(1 + P)
         grad = np.zeros((1 + P, nvar))
         x0, lb, ub = np.zeros(nvar), np.zeros(nvar), np.zeros(nvar)
+        if view is not None:  # setViewConstraint (:91-93)
+            self.R.ref_opt_set_view(self.h, _p(np.ascontiguousarray(view[0], dtype=np.float64)),
+                                    _p(np.ascontiguousarray(view[1], dtype=np.float64)), C.c_int32(int(view[2])))
         rc = self.R.ref_opt_evaluate(self.h, C.c_int32(n), _p(ctrl), C.c_double(dt), C.c_int32(cost_function), _p(start),
                                      C.c_int32(start.shape[0]), _p(end), C.c_int32(end.shape[0]), _p(guide),
                                      C.c_int32(guide.shape[0]), _p(waypts), _p(widx), C.c_int32(waypts.shape[0]),
@@ -580,9 +584,10 @@ def principal_axis_2x2(a, b, d):
 
 
 def opt_params(ld_smooth=20.0, ld_dist=10.0, ld_feasi=2.0, ld_start=100.0, ld_end=0.5, ld_guide=1.5,
-               ld_waypt=0.3, ld_view=0.0, ld_time=1.0, dist0=0.7, max_vel=2.0, max_acc=2.0, order=3):
+               ld_waypt=0.3, ld_view=0.0, ld_time=1.0, dist0=0.7, max_vel=2.0, max_acc=2.0, order=3, wnl=0.0):
     """Defaults = exploration_manager/launch/algorithm.xml:170-181 and exploration.launch max_vel/acc."""
     p = OrcOptParams()
+    p.wnl = wnl
     (p.ld_smooth, p.ld_dist, p.ld_feasi, p.ld_start, p.ld_end, p.ld_guide, p.ld_waypt, p.ld_view,
      p.ld_time, p.dist0, p.max_vel, p.max_acc, p.order) = (ld_smooth, ld_dist, ld_feasi, ld_start,
                                                            ld_end, ld_guide, ld_waypt, ld_view,
@@ -595,7 +600,14 @@ def traj_consts(B):
 
 
 def fill_traj_const(tc, pt_dist, knot_span, start, end, time_lb=-1.0, guide=None, waypt=None,
-                    waypt_idx=None):
+                    waypt_idx=None, view=None):
+    """view = (pt_ [3], dir_ [3], idx_) of setViewConstraint (bspline_optimizer.cpp:91-93), or None"""
+    tc.view_idx = -1
+    if view is not None:
+        for k in range(3):
+            tc.view_pt[k] = float(view[0][k])
+            tc.view_dir[k] = float(view[1][k])
+        tc.view_idx = int(view[2])
     tc.pt_dist = float(pt_dist)
     tc.knot_span = float(knot_span)
     start = np.asarray(start, dtype=np.float64).reshape(3, 3)

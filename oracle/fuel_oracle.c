@@ -998,6 +998,48 @@ static void calc_waypoints(const V3* q, int n, const OrcTrajConst* tc, double* c
   }
 }
 
+/* calcViewCost, :477-502.  Eigen expressions evaluated element-wise in written order: v = dir/sqrt(dir.dir);
+ * dn = (q-p) - ((q-p).v) v; g += (2*(I - v vT)) dn; dl = ((q-p).v) v; if |dl| < |dir|: cost += wnl*(|dl|-|dir|)^2,
+ * g += ((wnl*2*(|dl|-|dir|)) * v vT) dl / |dl|. */
+static void calc_view(const V3* q, int n, const OrcTrajConst* tc, double wnl, double* cost, V3* gq) {
+  *cost = 0.0;
+  v3zero(gq, n);
+  const double* p = tc->view_pt;
+  const double* dir = tc->view_dir;
+  const double zz = dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2];
+  double v[3] = { dir[0], dir[1], dir[2] };
+  if (zz > 0) {
+    const double nrm = sqrt(zz);
+    for (int k = 0; k < 3; ++k) v[k] = dir[k] / nrm;
+  }
+  double vvT[3][3], I_vvT[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      vvT[i][j] = v[i] * v[j];
+      I_vvT[i][j] = (i == j ? 1.0 : 0.0) - vvT[i][j];
+    }
+  const int i = tc->view_idx;
+  const double qp[3] = { q[i][0] - p[0], q[i][1] - p[1], q[i][2] - p[2] };
+  const double s = qp[0] * v[0] + qp[1] * v[1] + qp[2] * v[2];
+  double dn[3], dl[3];
+  for (int k = 0; k < 3; ++k) {
+    dl[k] = s * v[k];
+    dn[k] = qp[k] - dl[k];
+  }
+  *cost += dn[0] * dn[0] + dn[1] * dn[1] + dn[2] * dn[2];
+  for (int r = 0; r < 3; ++r)
+    gq[i][r] += (2 * I_vvT[r][0]) * dn[0] + (2 * I_vvT[r][1]) * dn[1] + (2 * I_vvT[r][2]) * dn[2];
+  const double norm_dl = sqrt(dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+  const double safe_dist = sqrt(zz);
+  if (norm_dl < safe_dist) {
+    const double e = norm_dl - safe_dist;
+    *cost += wnl * (e * e);
+    const double c = wnl * 2 * e;
+    for (int r = 0; r < 3; ++r)
+      gq[i][r] += ((c * vvT[r][0]) * dl[0] + (c * vvT[r][1]) * dl[1] + (c * vvT[r][2]) * dl[2]) / norm_dl;
+  }
+}
+
 /* calcGuideCost, :462-475 */
 static void calc_guide(const V3* q, int n, int order, const OrcTrajConst* tc, double* cost, V3* gq) {
   *cost = 0.0;
@@ -1102,8 +1144,13 @@ void orc_combine_cost(const OrcGrid* g, const double* dist_buf, const OrcOptPara
     for (int i = 0; i < n; i++)
       for (int j = 0; j < 3; j++) grad[3 * i + j] += p->ld_waypt * gt_[i][j];
   }
-  /* VIEWCONS (:619-626): ld_view is 0.0 in every launch file (algorithm.xml:177); not
-   * restated -- the mask bit is rejected by the product as unsupported. */
+  if (mask & ORC_VIEWCONS) { /* :631-638 */
+    double f = 0.0;
+    calc_view((const V3*)q, n, tc, p->wnl, &f, gt_);
+    *f_combine += p->ld_view * f;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < 3; j++) grad[3 * i + j] += p->ld_view * gt_[i][j];
+  }
   if (mask & ORC_MINTIME) {
     double f = 0.0, gt = 0.0;
     calc_time(n, p->order, dt, tc->time_lb, &f, &gt);

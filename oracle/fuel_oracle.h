@@ -186,6 +186,7 @@ typedef struct {
   double ld_smooth, ld_dist, ld_feasi, ld_start, ld_end, ld_guide, ld_waypt, ld_view, ld_time;
   double dist0, max_vel, max_acc;
   int32_t order; /* order_ = bspline_degree_ (3) */
+  double wnl;    /* wnl_ (optimization/wnl, :44): weight of the parallel part of calcViewCost */
 } OrcOptParams;   /* setParam :25-57 */
 
 #define ORC_MAX_PTS 64
@@ -201,6 +202,9 @@ typedef struct {
   int32_t n_waypt;
   double waypt[ORC_MAX_PTS][3];
   int32_t waypt_idx[ORC_MAX_PTS];
+  double view_pt[3];       /* view_cons_.pt_  (setViewConstraint :91-93; active_perception/traj_visibility.h:18-24) */
+  double view_dir[3];      /* view_cons_.dir_ (length = safe distance) */
+  int32_t view_idx;        /* view_cons_.idx_; < 0: no constraint set */
 } OrcTrajConst;
 
 /* combineCost (:518-647) for dim_ == 3.  x has 3N (+1 if MINTIME) entries. */

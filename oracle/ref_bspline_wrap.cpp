@@ -26,6 +26,17 @@ void* ref_opt_create(void* sdf_map_handle, int32_t n, const char** keys, const d
 }
 void ref_opt_destroy(void* h) { delete (BsplineOptimizer*)h; }
 
+// setViewConstraint (bspline_optimizer.cpp:91-93): only pt_, dir_, idx_ are read by calcViewCost (:477-502)
+void ref_opt_set_view(void* h, const double* pt, const double* dir, int32_t idx) {
+  ViewConstraint vc;
+  vc.pt_ = Eigen::Vector3d(pt[0], pt[1], pt[2]);
+  vc.pc_ = vc.pt_;
+  vc.dir_ = Eigen::Vector3d(dir[0], dir[1], dir[2]);
+  vc.pcons_ = vc.pt_;
+  vc.idx_ = idx;
+  ((BsplineOptimizer*)h)->setViewConstraint(vc);
+}
+
 // One optimize(points, dt, cost_function, max_num_id, max_time_id) call (bspline_optimizer.cpp:110-163).
 //   ctrl [n_pts][3], start [n_start<=3][3], end [n_end<=3][3], guide [n_guide][3], waypts [n_wp][3] + idx, time_lb
 //   probes [n_probe][nvar]: extra points at which the objective is evaluated

@@ -302,3 +302,51 @@ def test_exact_eval_mode_performs_every_evaluation(fuel, orc, scene):
     assert np.all(fe <= f0 * (1 + 1e-9))
     same = nn == K
     assert np.array_equal(xe[same], xn[same])  # trajectories that never stop early take the identical path
+
+
+def test_view_cost(fuel, orc, scene):
+    """calcViewCost (bspline_optimizer.cpp:477-502, the VIEWCONS bit): both sides of the |dl| < |dir| switch, alone and
+    inside the full objective, through the faithful AND the solver's evaluator; missing constraint -> EINVAL."""
+    O = fuel.BsplineOptimizer
+    g = scene["g"]
+    og = orc_grid(orc, g)
+    B, N = 64, 20
+    tr = W.make_trajectories(g, scene["inflate"], B=B, n_pts=N, seed=23)
+    rng = np.random.default_rng(23)
+    opt = fuel.BsplineOptimizer()
+    opt.setEnvironment(scene["opt"].edt_environment_)
+    opt.setParam(ld_view=2.5, wnl=1.3)
+    po = orc.opt_params(ld_view=2.5, wnl=1.3)
+    tg = gpu_consts(fuel, tr, B)
+    to = orc_consts(orc, tr, B)
+    n_par = 0
+    for b in range(B):
+        idx = int(rng.integers(0, N))
+        pt = tr["ctrl"][b, idx] + rng.normal(size=3) * 0.4
+        d = (tr["ctrl"][b, idx] - pt) * float(rng.choice([-1.0, 1.0])) + rng.normal(size=3) * 0.1
+        d = d / np.linalg.norm(d) * float(rng.choice([0.2, 1.5]))
+        for t in (tg[b], to[b]):
+            for k in range(3):
+                t.view_pt[k], t.view_dir[k] = pt[k], d[k]
+            t.view_idx = idx
+        n_par += int(abs(np.dot(tr["ctrl"][b, idx] - pt, d / np.linalg.norm(d))) < np.linalg.norm(d))
+    assert 5 < n_par < B - 5
+    for mask in (O.VIEWCONS, O.NORMAL_PHASE | O.VIEWCONS | O.MINTIME):
+        x = W.pack_x(tr["ctrl"], tr["dt"], mintime=bool(mask & O.MINTIME))
+        fr, gr = orc.combine_cost_batch(og, scene["d64"], po, to, N, mask, x)
+        for fast in (False, True):
+            f, gg = opt.combineCostBatch(x, tg, N, mask, fast_eval=fast)
+            check(f, gg, fr, gr)
+        if mask == O.VIEWCONS:
+            assert np.all(np.count_nonzero(gg, axis=1) <= 3)
+    # the solver accepts the bit as well and does not make things worse
+    x0 = W.pack_x(tr["ctrl"], tr["dt"])
+    mask = O.NORMAL_PHASE | O.VIEWCONS | O.MINTIME
+    f0, _ = orc.combine_cost_batch(og, scene["d64"], po, to, N, mask, x0)
+    xs, fs, ns = opt.optimizeBatch(x0, tg, N, mask, 32)
+    assert np.all(fs <= f0 * (1 + 1e-9))
+    fchk, _ = orc.combine_cost_batch(og, scene["d64"], po, to, N, mask, xs)
+    assert np.all(np.abs(fchk - fs) <= 1e-4 * np.abs(fs) + 1e-9)
+    # no constraint set (view_idx = -1): refused
+    with pytest.raises(fuel.FuelGpuError):
+        opt.combineCostBatch(x0, gpu_consts(fuel, tr, B), N, mask)

@@ -508,3 +508,49 @@ def test_host_mirror_pt_dist_is_the_reference_value(opt_scene):
     tr = opt_scene["tr"]
     for b in range(tr["ctrl"].shape[0]):
         assert fuel_b200.BsplineOptimizer.pt_dist(tr["ctrl"][b]) == O.pt_dist(tr["ctrl"][b]) == tr["pt_dist"][b]
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_view_cost_matches_reference(seed):
+    """calcViewCost (bspline_optimizer.cpp:477-502, VIEWCONS): the perpendicular part, the parallel part on both sides of
+    its |dl| < |dir| switch, random ld_view / wnl, alone and inside a full objective -- bit for bit."""
+    rng = np.random.default_rng(40 + seed)
+    ref = O.RefSDFMap(**BASE)
+    inflate, tri = random_state(ref, 500 + seed)
+    ref.set_modes(1, 0)
+    ref.set_local_bound((0, 0, 0), (79, 59, 29))
+    ref.update_esdf3d()
+    w = dict(ld_view=float(rng.uniform(0.5, 5)), wnl=float(rng.uniform(0.2, 3)))
+    opt = O.RefBsplineOptimizer(ref, **dict(OPT, **w))
+    p = O.opt_params(**w)
+    g, dist = ref.grid(), ref.distance.copy()
+    N = 20
+    tr = W.make_trajectories(W.Grid(ref.n, tuple(ref.origin), ref.res), inflate, B=6, n_pts=N, seed=seed)
+    n_par = 0
+    for b in range(6):
+        ctrl, dt, start = tr["ctrl"][b], float(tr["dt"][b]), tr["start"][b]
+        idx = int(rng.integers(3, N - 3))
+        pt = ctrl[idx] + rng.normal(size=3) * 0.4
+        # direction roughly along / against (pt -> control point), short or long safe distance
+        d = (ctrl[idx] - pt) * float(rng.choice([-1.0, 1.0])) + rng.normal(size=3) * 0.1
+        d = d / np.linalg.norm(d) * float(rng.choice([0.2, 1.5]))
+        view = (pt, d, idx)
+        for mask in (O.VIEWCONS, O.NORMAL_PHASE | O.VIEWCONS | O.MINTIME):
+            nvar = 3 * N + (1 if mask & O.MINTIME else 0)
+            probes = np.concatenate([ctrl.reshape(-1), [dt]])[:nvar] + rng.normal(size=(3, nvar)) * 0.2
+            if mask & O.MINTIME:
+                probes[:, -1] = np.abs(probes[:, -1]) + 0.03
+            r = opt.evaluate(ctrl, dt, mask, start, tr["end_pos"][b][None, :], probes=probes, view=view)
+            tc = O.traj_consts(1)
+            O.fill_traj_const(tc[0], O.pt_dist(ctrl), dt, start, tr["end_pos"][b][None, :], view=view)
+            X = np.concatenate([r["x0"][None, :], probes])
+            for i in range(len(X)):
+                fi, gi = O.combine_cost_batch(g, dist, p, tc, N, mask, X[i:i + 1])
+                assert fi[0] == r["f"][i] and np.array_equal(gi[0], r["grad"][i]), (b, mask, i)
+            if mask == O.VIEWCONS:
+                q = X[0][:3 * N].reshape(N, 3)[idx] - pt
+                n_par += int(abs(np.dot(q, d / np.linalg.norm(d))) < np.linalg.norm(d))
+                assert np.count_nonzero(r["grad"][0]) <= 3  # one control point only
+    assert n_par >= 1  # the wnl branch was taken at least once
+    opt.close()
+    ref.close()
