@@ -45,8 +45,10 @@ class FrontierFinder:
         cell_order: "address" (cells of a cluster ascending by toAddress, straight from the device) or "bfs" (the
         reference's expandFrontier order; average_ / filtered_cells_ then equal the reference's to the last bit)."""
         self.edt_env_ = edt
-        check(lib().fuelgpu_frontier_set_cell_order(edt.sdf_map_.handle, {"address": 0, "bfs": 1}[cell_order]),
-              edt.sdf_map_.handle)
+        self.cell_order_ = {"address": 0, "bfs": 1}[cell_order]
+        h = getattr(edt.sdf_map_, "handle", None)
+        if h is not None:  # (host-only stand-ins of the map, as in the bookkeeping tests, have no device handle)
+            check(lib().fuelgpu_frontier_set_cell_order(h, self.cell_order_), h)
         self.cluster_min_ = int(cluster_min)
         self.cluster_size_xy_ = float(cluster_size_xy)
         self.down_sample_ = int(down_sample)
