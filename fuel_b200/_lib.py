@@ -127,6 +127,11 @@ SIGNATURES = {
     "fuelgpu_bspline_optimize_batch_dev": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(FuelOptParams), _vp,
                                                      C.POINTER(FuelSolveParams), _vp, _vp, _vp]),
     "fuelgpu_frontier_set_cell_order": (C.c_int, [_vp, _i32]),
+    "fuelgpu_frontier_candidates": (C.c_int, [_vp, _vp, _vp, C.POINTER(FuelFrontierParams), _i32, _i32, C.POINTER(_i32)]),
+    "fuelgpu_frontier_candidates_fetch": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "fuelgpu_frontier_search_from_candidates": (C.c_int, [_vp, _vp, _vp, C.POINTER(FuelFrontierParams), _i32, _vp, _vp,
+                                                          C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "fuelgpu_map_occupancy_plane_dev": (C.c_int, [_vp, _i32, _vp, _i32]),
     "fuelgpu_comm_get_unique_id": (C.c_int, [_vp]),
     "fuelgpu_comm_init": (C.c_int, [_i32, _i32, _vp, _i32, C.POINTER(_vp)]),
     "fuelgpu_comm_info": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),

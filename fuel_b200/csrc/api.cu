@@ -577,6 +577,53 @@ int fuelgpu_frontier_fetch(FuelMap* m, int32_t* cell_offsets, int32_t* cell_addr
   return frontier_fetch_impl(m, cell_offsets, cell_addr, filt_offsets, filtered, average, box_min, box_max);
 }
 
+int fuelgpu_frontier_candidates(FuelMap* m, const double upd_min[3], const double upd_max[3], const FuelFrontierParams* p,
+                                int32_t z_lo, int32_t z_hi, int32_t* n_candidates) {
+  if (!m || !upd_min || !upd_max || !p || !n_candidates) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (z_lo < 0 || z_hi >= m->g.nz || z_lo > z_hi) return fuel_fail(m, FUELGPU_EINVAL, "bad z range");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return frontier_candidates_impl(m, upd_min, upd_max, p, z_lo, z_hi, n_candidates);
+}
+
+int fuelgpu_frontier_candidates_fetch(FuelMap* m, int32_t n, int32_t* addr, uint8_t* cls) {
+  if (!m || (n > 0 && (!addr || !cls))) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return frontier_candidates_fetch_impl(m, n, addr, cls);
+}
+
+int fuelgpu_frontier_search_from_candidates(FuelMap* m, const double upd_min[3], const double upd_max[3],
+                                            const FuelFrontierParams* p, int32_t n, const int32_t* addr, const uint8_t* cls,
+                                            int32_t* n_clusters, int32_t* n_cells, int32_t* n_filtered) {
+  if (!m || !upd_min || !upd_max || !p || !n_clusters || !n_cells || !n_filtered || (n > 0 && (!addr || !cls)))
+    return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  return frontier_search_from_candidates_impl(m, upd_min, upd_max, p, n, addr, cls, n_clusters, n_cells, n_filtered);
+}
+
+// one z plane of the occupancy byte <-> a contiguous [nx][ny] device buffer (the halo planes of a z-sharded map)
+namespace {
+__global__ void occ_plane_kernel(uint8_t* occ, uint8_t* plane, int64_t nxy, int nz, int z, int set) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nxy) return;
+  if (set)
+    occ[i * nz + z] = plane[i];
+  else
+    plane[i] = occ[i * nz + z];
+}
+}  // namespace
+
+int fuelgpu_map_occupancy_plane_dev(FuelMap* m, int32_t z, void* plane_dev, int32_t set) {
+  if (!m || !plane_dev) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  if (z < 0 || z >= m->g.nz) return fuel_fail(m, FUELGPU_EINVAL, "z outside the map");
+  FUEL_CUDA(m, cudaSetDevice(m->dev));
+  if (set) frontier_order_writer(m);
+  const int64_t nxy = (int64_t)m->g.nx * m->g.ny;
+  occ_plane_kernel<<<(unsigned)((nxy + 255) / 256), 256, 0, m->stream>>>(m->occ, (uint8_t*)plane_dev, nxy, m->g.nz, z, set);
+  FUEL_LAUNCHES(m, 1);
+  FUEL_CUDA(m, cudaGetLastError());
+  return 0;
+}
+
 int fuelgpu_frontier_set_cell_order(FuelMap* m, int32_t order) {
   if (!m) return fuel_fail(nullptr, FUELGPU_EINVAL, "null map");
   return frontier_set_cell_order(m, order);

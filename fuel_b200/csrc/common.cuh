@@ -123,7 +123,13 @@ void fusion_get_updated_box(FuelMap* m, double bmin[3], double bmax[3], int rese
 void fusion_state_destroy(FuelMap* m);
 double* fusion_logodds_ptr(FuelMap* m, double* clamp_max_log);
 void frontier_order_writer(FuelMap* m);
-int frontier_set_cell_order(FuelMap* m, int order);  // main-stream writers of `occ` wait for an enqueued frontier search
+int frontier_set_cell_order(FuelMap* m, int order);
+int frontier_candidates_impl(FuelMap* m, const double umin[3], const double umax[3], const FuelFrontierParams* p, int z_lo,
+                             int z_hi, int32_t* n_out);
+int frontier_candidates_fetch_impl(FuelMap* m, int32_t n, int32_t* addr, uint8_t* cls);
+int frontier_search_from_candidates_impl(FuelMap* m, const double umin[3], const double umax[3], const FuelFrontierParams* p,
+                                         int32_t n, const int32_t* addr, const uint8_t* cls, int32_t* n_clusters,
+                                         int32_t* n_cells, int32_t* n_filtered);  // main-stream writers of `occ` wait for an enqueued frontier search
 
 int ensure_fr_scratch(FuelMap* m, size_t bytes);
 int frontier_state_create(FuelMap* m);

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(CLS_BLOCK) compact_kernel(Geom g, FParams fp,
     const int a = (int)addr_of(g, x, y, z);
     cell_addr[idx] = a;
     cell_cls[idx] = ((mE >> lane) & 1u) ? 1 : 2;  // 1 = E, 2 = S
-    cellidx[a] = idx;
+    if (cellidx) cellidx[a] = idx;
   }
 }
 
@@ -1488,13 +1488,15 @@ static int frontier_build_csr(FuelMap* m, int K, int C, const HostView& hv, int3
   return 0;
 }
 
-int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double umax[3],
-                               const FuelFrontierParams* p) {
+// search box, sweep domain and the per-search constants (frontier_finder.cpp:94-104,152)
+static int frontier_cluster_large(FuelMap* m, const FParams& fp, int n_cand, int32_t* n_clusters, int32_t* n_cells,
+                                  int32_t* n_filtered);
+
+static void frontier_make_params(FuelMap* m, const double umin[3], const double umax[3], const FuelFrontierParams* p,
+                                 FParams* out) {
   FrontierState* f = m->fs;
   const Geom& g = m->g;
-  cudaStream_t s = m->fs->stream;
   const int nmax[3] = { g.nx, g.ny, g.nz };
-
   // search box: updated box inflated by (1,1,0.5) m, clamped to the exploration box, then
   // posToIndex (frontier_finder.cpp:94-104)
   FParams fp;
@@ -1532,6 +1534,28 @@ int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double um
   f->last_leaf = fp.leaf;
   fp.leaf_inv = 1.0f / fp.leaf;
   f->pend_fp = fp;  // (search box and leaf size are also what the host-side BFS ordering needs)
+  *out = fp;
+}
+
+static void frontier_clear_results(FrontierState* f) {
+  f->h_cell_off.assign(1, 0);
+  f->h_cell_addr.clear();
+  f->h_filt_off.assign(1, 0);
+  f->h_filtered.clear();
+  f->h_avg.clear();
+  f->h_bmin.clear();
+  f->h_bmax.clear();
+  f->pend_active = false;
+  f->pend_empty = true;
+}
+
+int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double umax[3],
+                               const FuelFrontierParams* p) {
+  FrontierState* f = m->fs;
+  const Geom& g = m->g;
+  cudaStream_t s = m->fs->stream;
+  FParams fp;
+  frontier_make_params(m, umin, umax, p, &fp);
 
   f->h_cell_off.assign(1, 0);
   f->h_cell_addr.clear();
@@ -1640,6 +1664,20 @@ int frontier_search_end_impl(FuelMap* m, int32_t* n_clusters, int32_t* n_cells, 
   compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p,
                                           f->cell_cls.p, f->cellidx, ndom, n_cand);
   FUEL_LAUNCHES(m, 1);
+  return frontier_cluster_large(m, fp, n_cand, n_clusters, n_cells, n_filtered);
+}
+
+// the multi-kernel clustering + split over n_cand compacted candidate cells (cell_addr / cell_cls ascending by
+// address, cellidx[addr] = index already set): union-find, claims, flags, kept-cell gather, split levels, marshal
+static int frontier_cluster_large(FuelMap* m, const FParams& fp, int n_cand, int32_t* n_clusters, int32_t* n_cells,
+                                  int32_t* n_filtered) {
+  FrontierState* f = m->fs;
+  const Geom& g = m->g;
+  cudaStream_t s = m->fs->stream;
+  ENSURE(f->parent, n_cand);
+  ENSURE(f->claim, n_cand); ENSURE(f->csize, n_cand); ENSURE(f->seed, n_cand);
+  ENSURE(f->is_root, n_cand); ENSURE(f->is_kept, n_cand); ENSURE(f->root_rank, n_cand);
+  ENSURE(f->kept_off, n_cand);
   const unsigned cb = nblk(n_cand, 256);
   init_parent_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->claim.p, f->csize.p, n_cand);
   FUEL_LAUNCHES(m, 1);
@@ -1716,6 +1754,93 @@ int frontier_search_end_impl(FuelMap* m, int32_t* n_clusters, int32_t* n_cells, 
   FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
   return frontier_marshal(m, K, C, n_clusters, n_cells, n_filtered);
+}
+
+
+// ---- sharded sweep --------------------------------------------------------------------
+// The voxel sweep (2 B/voxel, the HBM-bound part) shards on z; the clustering is O(frontier cells) and runs on the
+// union of the candidates.  A rank classifies the voxels of ITS z planes [z_lo, z_hi] (it needs the tri-state of
+// those planes plus one halo plane on each side) and hands back its candidate cells; the host program gathers the
+// lists of all ranks (ascending address), and every rank clusters the full list -- same kernels, same result as the
+// single-GPU search, bit for bit.
+__global__ void set_cellidx_kernel(const int* __restrict__ cell_addr, int* __restrict__ cellidx, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cellidx[cell_addr[i]] = i;
+}
+
+int frontier_candidates_impl(FuelMap* m, const double umin[3], const double umax[3], const FuelFrontierParams* p, int z_lo,
+                             int z_hi, int32_t* n_out) {
+  FrontierState* f = m->fs;
+  const Geom& g = m->g;
+  cudaStream_t s = frontier_stream(m);
+  FParams fp;
+  frontier_make_params(m, umin, umax, p, &fp);
+  *n_out = 0;
+  const int dz0 = fp.dom_lo[2] > z_lo ? fp.dom_lo[2] : z_lo;
+  const int dz1 = (fp.dom_lo[2] + fp.dom_n[2] - 1) < z_hi ? (fp.dom_lo[2] + fp.dom_n[2] - 1) : z_hi;
+  if (dz1 < dz0) return 0;
+  fp.dom_lo[2] = dz0;
+  fp.dom_n[2] = dz1 - dz0 + 1;
+  const int64_t ndom = (int64_t)fp.dom_n[0] * fp.dom_n[1] * fp.dom_n[2];
+  if (ndom <= 0) return 0;
+  const unsigned nb = nblk(ndom, CLS_BLOCK);
+  const size_t nwords = (size_t)nb * (CLS_BLOCK / 32);
+  ENSURE(f->maskE, nwords);
+  ENSURE(f->maskS, nwords);
+  ENSURE(f->blockcnt, nb);
+  ENSURE(f->blockoff, nb);
+  classify_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, m->occ, m->flag, f->maskE.p, f->maskS.p, f->blockcnt.p, ndom);
+  FUEL_LAUNCHES(m, 1);
+  if (scan_ints(m, f->blockcnt.p, f->blockoff.p, (int)nb, f->d_counters + 0)) return FUELGPU_ENOMEM;
+  int n = 0;
+  FUEL_CUDA(m, cudaMemcpyAsync(&n, f->d_counters, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaStreamSynchronize(s));
+  if (n > 0) {
+    ENSURE(f->cell_addr, n);
+    ENSURE(f->cell_cls, n);
+    compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p, f->cell_cls.p,
+                                            nullptr, ndom, n);
+    FUEL_LAUNCHES(m, 1);
+    FUEL_CUDA(m, cudaGetLastError());
+  }
+  *n_out = n;
+  return 0;
+}
+
+int frontier_candidates_fetch_impl(FuelMap* m, int32_t n, int32_t* addr, uint8_t* cls) {
+  FrontierState* f = m->fs;
+  if (n <= 0) return 0;
+  cudaStream_t s = f->stream;
+  FUEL_CUDA(m, cudaMemcpyAsync(addr, f->cell_addr.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(cls, f->cell_cls.p, n, cudaMemcpyDeviceToHost, s));
+  FUEL_CUDA(m, cudaStreamSynchronize(s));
+  return 0;
+}
+
+int frontier_search_from_candidates_impl(FuelMap* m, const double umin[3], const double umax[3], const FuelFrontierParams* p,
+                                         int32_t n, const int32_t* addr, const uint8_t* cls, int32_t* n_clusters,
+                                         int32_t* n_cells, int32_t* n_filtered) {
+  FrontierState* f = m->fs;
+  cudaStream_t s = frontier_stream(m);
+  FParams fp;
+  frontier_make_params(m, umin, umax, p, &fp);
+  frontier_clear_results(f);
+  *n_clusters = *n_cells = *n_filtered = 0;
+  if (n <= 0) return 0;
+  for (int i = 1; i < n; ++i)
+    if (addr[i] <= addr[i - 1]) return fuel_fail(m, FUELGPU_EINVAL, "candidate addresses must be strictly ascending");
+  if (addr[0] < 0 || (int64_t)addr[n - 1] >= m->nvox) return fuel_fail(m, FUELGPU_EINVAL, "candidate address outside the map");
+  ENSURE(f->cell_addr, n);
+  ENSURE(f->cell_cls, n);
+  FUEL_CUDA(m, cudaMemcpyAsync(f->cell_addr.p, addr, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  FUEL_CUDA(m, cudaMemcpyAsync(f->cell_cls.p, cls, n, cudaMemcpyHostToDevice, s));
+  set_cellidx_kernel<<<nblk(n, 256), 256, 0, s>>>(f->cell_addr.p, f->cellidx, n);
+  FUEL_LAUNCHES(m, 1);
+  FUEL_CUDA(m, cudaMemcpyAsync(f->d_counters, &n, sizeof(int), cudaMemcpyHostToDevice, s));
+  const int rc = frontier_cluster_large(m, fp, n, n_clusters, n_cells, n_filtered);
+  cudaEventRecord(f->ev_out, f->stream);
+  f->ev_out_valid = true;
+  return rc;
 }
 
 int frontier_search_impl(FuelMap* m, const double umin[3], const double umax[3],

@@ -241,3 +241,71 @@ def optimize_batch_split(opt, x, traj_consts, n_pts, cost_function, max_eval, gr
         return xb.copy(), fb.copy(), ne.copy()
 
     return split_batch_run(run, x.shape[0], group)
+
+
+def merge_candidates(parts):
+    """[(addr, cls), ...] of all ranks -> one list ascending by address (z-slabs interleave in a z-fastest address)"""
+    addr = np.concatenate([np.asarray(a, dtype=np.int32) for a, _ in parts])
+    cls = np.concatenate([np.asarray(c, dtype=np.uint8) for _, c in parts])
+    order = np.argsort(addr, kind="stable")
+    addr, cls = addr[order], cls[order]
+    if addr.size > 1 and np.any(addr[1:] == addr[:-1]):
+        raise ValueError("a voxel was swept by two ranks: the z ranges overlap")
+    return addr, cls
+
+
+def gather_candidates(addr, cls, group=None, device=None):
+    """all-gather of the per-rank candidate lists (variable length, KBs) -> the merged list on every rank"""
+    G = dist.get_world_size(group)
+    nccl = dist.get_backend(group) == "nccl"
+    dev = "cuda:%d" % (torch.cuda.current_device() if device is None else device) if nccl else "cpu"
+    n = torch.tensor([addr.size], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(G)]
+    dist.all_gather(ns, n, group=group)
+    ns = [int(v.item()) for v in ns]
+    mx = max(max(ns), 1)
+    pack = np.zeros((mx, 2), dtype=np.int32)
+    pack[:addr.size, 0] = addr
+    pack[:addr.size, 1] = cls
+    t = torch.from_numpy(pack).to(dev)
+    parts = [torch.empty_like(t) for _ in range(G)]
+    dist.all_gather(parts, t, group=group)
+    out = []
+    for k in range(G):
+        a = parts[k][:ns[k]].cpu().numpy()
+        out.append((a[:, 0].copy(), a[:, 1].astype(np.uint8)))
+    return merge_candidates(out)
+
+
+def exchange_halo_planes(sdf_map, z_lo, z_hi, group=None):
+    """One plane of the occupancy byte each way (the 6-neighbour unknown test reaches +-1): every rank
+    publishes its two boundary planes, then installs plane z_lo-1 from the rank below and z_hi+1 from the rank above.
+    Device buffers; NCCL all_gather of 2*nx*ny bytes per rank."""
+    G = dist.get_world_size(group)
+    r = dist.get_rank(group)
+    nx, ny, nz = sdf_map.shape
+    dev = "cuda:%d" % sdf_map.device
+    L = _lib.lib()
+    mine = torch.empty((2, nx, ny), dtype=torch.uint8, device=dev)
+    _lib.check(L.fuelgpu_map_occupancy_plane_dev(sdf_map.handle, int(z_lo), C.c_void_p(mine[0].data_ptr()), 0), sdf_map.handle)
+    _lib.check(L.fuelgpu_map_occupancy_plane_dev(sdf_map.handle, int(z_hi), C.c_void_p(mine[1].data_ptr()), 0), sdf_map.handle)
+    sdf_map.synchronize()
+    parts = [torch.empty_like(mine) for _ in range(G)]
+    dist.all_gather(parts, mine, group=group)
+    torch.cuda.synchronize(sdf_map.device)
+    if r > 0:
+        _lib.check(L.fuelgpu_map_occupancy_plane_dev(sdf_map.handle, int(z_lo) - 1, C.c_void_p(parts[r - 1][1].data_ptr()), 1),
+                   sdf_map.handle)
+    if r < G - 1:
+        _lib.check(L.fuelgpu_map_occupancy_plane_dev(sdf_map.handle, int(z_hi) + 1, C.c_void_p(parts[r + 1][0].data_ptr()), 1),
+                   sdf_map.handle)
+    sdf_map.synchronize()
+
+
+def search_frontiers_sharded(ff, update_min, update_max, z_lo, z_hi, group=None):
+    """The z-sharded frontier search: this rank sweeps its planes, the candidate cells of all ranks are
+    gathered and merged, every rank clusters the full list.  Returns the same Frontier list as ff.search_box on one GPU
+    holding the whole map.  The caller has installed the halo planes (exchange_halo_planes)."""
+    addr, cls = ff.candidates(update_min, update_max, z_lo, z_hi)
+    addr, cls = gather_candidates(addr, cls, group, device=ff.edt_env_.sdf_map_.device)
+    return ff.search_from_candidates(update_min, update_max, addr, cls)

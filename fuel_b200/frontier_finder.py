@@ -157,13 +157,44 @@ class FrontierFinder:
         p = self._params()
         check(lib().fuelgpu_frontier_search_begin(h, ptr(umin), ptr(umax), C.byref(p)), h)
 
+    def candidates(self, update_min, update_max, z_lo, z_hi):
+        """The sweep of the planes [z_lo, z_hi] only (fuelgpu_frontier_candidates): this rank's candidate cells of a
+        z-sharded search -> (addr int32 ascending, cls uint8).  Needs the tri-state of those planes +- one halo plane."""
+        h = self._map.handle
+        umin = np.ascontiguousarray(update_min, dtype=np.float64)
+        umax = np.ascontiguousarray(update_max, dtype=np.float64)
+        p = self._params()
+        n = C.c_int32()
+        check(lib().fuelgpu_frontier_candidates(h, ptr(umin), ptr(umax), C.byref(p), int(z_lo), int(z_hi), C.byref(n)), h)
+        addr = np.empty(n.value, dtype=np.int32)
+        cls = np.empty(n.value, dtype=np.uint8)
+        check(lib().fuelgpu_frontier_candidates_fetch(h, n.value, ptr(addr), ptr(cls)), h)
+        return addr, cls
+
+    def search_from_candidates(self, update_min, update_max, addr, cls):
+        """Clustering + split over a candidate list gathered from all ranks (ascending address): the result of
+        search_box on one GPU, bit for bit (fuelgpu_frontier_search_from_candidates)."""
+        h = self._map.handle
+        umin = np.ascontiguousarray(update_min, dtype=np.float64)
+        umax = np.ascontiguousarray(update_max, dtype=np.float64)
+        addr = np.ascontiguousarray(addr, dtype=np.int32)
+        cls = np.ascontiguousarray(cls, dtype=np.uint8)
+        p = self._params()
+        nc, ncell, nf = C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib().fuelgpu_frontier_search_from_candidates(h, ptr(umin), ptr(umax), C.byref(p), addr.size, ptr(addr), ptr(cls),
+                                                            C.byref(nc), C.byref(ncell), C.byref(nf)), h)
+        return self._fetch(nc.value, ncell.value, nf.value)
+
     def search_box_end(self):
         """Wait for the enqueued search and build the Frontier list."""
-        m = self._map
-        h = m.handle
+        h = self._map.handle
         nc, ncell, nf = C.c_int32(), C.c_int32(), C.c_int32()
         check(lib().fuelgpu_frontier_search_end(h, C.byref(nc), C.byref(ncell), C.byref(nf)), h)
-        nc, ncell, nf = nc.value, ncell.value, nf.value
+        return self._fetch(nc.value, ncell.value, nf.value)
+
+    def _fetch(self, nc, ncell, nf):
+        m = self._map
+        h = m.handle
         # arrays of this call; the Frontier objects hold views into them
         offs = np.empty(nc + 1, dtype=np.int32)
         addr = np.empty(ncell, dtype=np.int32)

@@ -218,6 +218,28 @@ FUELGPU_API int fuelgpu_frontier_search_end(FuelMap* map, int32_t* n_clusters, i
 FUELGPU_API int fuelgpu_frontier_fetch(FuelMap* map, int32_t* cell_offsets, int32_t* cell_addr,
                            int32_t* filt_offsets, double* filtered, double* average,
                            double* box_min, double* box_max);
+/* ---- z-sharded frontier sweep ----------------------------------------------------------
+ * The voxel sweep shards on z, the clustering (O(frontier cells)) runs on the union of the candidates:
+ *   1. every rank holds the tri-state of its planes [z_lo, z_hi] plus one halo plane on each side
+ *      (fuelgpu_map_occupancy_plane_dev moves a plane to / from a contiguous device buffer for the exchange);
+ *   2. fuelgpu_frontier_candidates sweeps ITS planes (knownfree && isNeighborUnknown && frontier_flag_ == 0,
+ *      frontier_finder.cpp:108-117,862-877) and returns its candidate cells: address + class (1 = may be absorbed
+ *      by a region growth, 2 = can only seed one, :146-152);
+ *   3. the host program gathers the lists of all ranks and merges them by ascending address (KBs);
+ *   4. fuelgpu_frontier_search_from_candidates clusters + splits the full list on every rank: same kernels and the
+ *      same result as fuelgpu_frontier_search on one GPU, bit for bit; frontier_flag_ is updated for all cells on
+ *      every rank (replicated).  Results through fuelgpu_frontier_fetch as usual. */
+FUELGPU_API int fuelgpu_frontier_candidates(FuelMap* map, const double upd_min[3], const double upd_max[3],
+                                            const FuelFrontierParams* params, int32_t z_lo, int32_t z_hi,
+                                            int32_t* n_candidates);
+FUELGPU_API int fuelgpu_frontier_candidates_fetch(FuelMap* map, int32_t n, int32_t* addr, uint8_t* cls);
+FUELGPU_API int fuelgpu_frontier_search_from_candidates(FuelMap* map, const double upd_min[3], const double upd_max[3],
+                                                        const FuelFrontierParams* params, int32_t n, const int32_t* addr,
+                                                        const uint8_t* cls, int32_t* n_clusters, int32_t* n_cells,
+                                                        int32_t* n_filtered);
+/* plane z of the resident occupancy byte -> plane_dev [nx][ny] (set = 0) or plane_dev -> plane z (set = 1) */
+FUELGPU_API int fuelgpu_map_occupancy_plane_dev(FuelMap* map, int32_t z, void* plane_dev, int32_t set);
+
 /* Order of a cluster's cells in fuelgpu_frontier_fetch.  BY_ADDRESS (default): ascending toAddress, straight
  * from the device.  BFS: the reference's own order (expandFrontier's BFS from the seed, :139-156, kept by
  * splitHorizontally, :217-224), re-derived on the host from the fetched cell sets; average_ and filtered_cells_ are

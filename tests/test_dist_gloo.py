@@ -126,3 +126,42 @@ def test_batch_split_over_ranks():
         a, b, c = ret[r]
         assert np.array_equal(a, x * 2.0) and np.array_equal(b, x[:, 0] + 1.0)
         assert list(c) == [0] * 6 + [1] * 5
+
+
+def cand_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fuel_b200.dist import gather_candidates
+    nz = 8
+    # rank r owns z in [4r, 4r+4): addresses with (addr % nz) in that range; different counts per rank, one rank may be empty
+    rng = np.random.default_rng(3)
+    allc = np.sort(rng.choice(200 * nz, size=57, replace=False)).astype(np.int32)
+    cls_all = (1 + (allc % 2)).astype(np.uint8)
+    if world == 2:
+        mine = (allc % nz) // 4 == rank
+    addr, cls = gather_candidates(allc[mine], cls_all[mine])
+    ret[rank] = (addr, cls)
+    dist.destroy_process_group()
+
+
+def test_candidate_gather_and_merge():
+    """The z-sharded frontier sweep: per-rank candidate lists of different lengths are all-gathered and merged into ONE
+    list ascending by address (z slabs interleave in a z-fastest address); overlapping z ranges are refused."""
+    from fuel_b200.dist import merge_candidates
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(cand_worker, args=(2, port, ret), nprocs=2, join=True)
+    rng = np.random.default_rng(3)
+    allc = np.sort(rng.choice(200 * 8, size=57, replace=False)).astype(np.int32)
+    for r in (0, 1):
+        addr, cls = ret[r]
+        assert np.array_equal(addr, allc) and np.array_equal(cls, (1 + (allc % 2)).astype(np.uint8))
+    import pytest
+    with pytest.raises(ValueError):
+        merge_candidates([(np.array([1, 5]), np.array([1, 1])), (np.array([5, 9]), np.array([1, 2]))])

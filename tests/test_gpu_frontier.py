@@ -202,3 +202,40 @@ def test_large_scene_uses_multi_kernel_path(fuel, orc):
     assert int(rfl.sum()) > 32768, int(rfl.sum())
     assert_same(gpu, ref)
     assert np.array_equal(gfl, rfl)
+
+
+@pytest.mark.parametrize("slabs", [2, 3, 5])
+def test_sharded_sweep_equals_whole_search(fuel, orc, slabs):
+    """SURVEY 8e row 2 on one GPU: the sweep cut into z slabs (fuelgpu_frontier_candidates per slab), the candidate lists
+    merged by address, the clustering run on the union (fuelgpu_frontier_search_from_candidates) == the whole search,
+    bit for bit: clusters, order, cells, average_, filtered_cells_, frontier_flag_.  Also after a first search left flags."""
+    from fuel_b200.dist import merge_candidates
+    n = (64, 50, 24)
+    origin = np.array([-1.0, -2.0, -0.5])
+    g0 = W.Grid(n, origin, 0.1)
+    g = W.Grid(n, origin, 0.1, box_min=origin + 0.1, box_max=g0.map_max - 0.1)
+    inflate, tri = random_scene(n, 3, p_site=0.01, p_unknown=0.5, blobs=7)
+    kw = dict(cluster_min=8, cluster_size_xy=1.0, down_sample=3, min_z=0.4)
+    ext = g0.map_max - origin
+    boxes = [(origin + 0.3 * ext, origin + 0.6 * ext), (origin, g0.map_max)]
+    m1, m2 = make_sdf_map(fuel, g, inflate, tri), make_sdf_map(fuel, g, inflate, tri)
+    ffs = []
+    for m in (m1, m2):
+        env = fuel.EDTEnvironment()
+        env.setMap(m)
+        ffs.append(fuel.FrontierFinder(env, **kw))
+    cuts = np.linspace(0, n[2], slabs + 1).astype(int)
+    for umin, umax in boxes:  # the second search runs on the flags the first one left
+        whole = ffs[0].search_box(umin, umax)
+        parts = [ffs[1].candidates(umin, umax, cuts[i], cuts[i + 1] - 1) for i in range(slabs)]
+        assert sum(a.size for a, _ in parts) > 0
+        addr, cls = merge_candidates(parts)
+        got = ffs[1].search_from_candidates(umin, umax, addr, cls)
+        assert len(got) == len(whole) and len(whole) > 0
+        for a, b in zip(got, whole):
+            assert np.array_equal(a.cells_addr_, b.cells_addr_)
+            assert np.array_equal(a.average_, b.average_) and np.array_equal(a.filtered_cells_, b.filtered_cells_)
+            assert np.array_equal(a.box_min_, b.box_min_) and np.array_equal(a.box_max_, b.box_max_)
+        assert np.array_equal(ffs[0].download_flags(), ffs[1].download_flags())
+    m1.close()
+    m2.close()

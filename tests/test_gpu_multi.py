@@ -20,3 +20,17 @@ def test_sharded_esdf_matches_single_gpu():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+def test_sharded_frontier_search_matches_whole_search():
+    """SURVEY 8e row 2 on 2 GPUs: every rank knows only its own z planes (+ one exchanged halo plane per side), sweeps them,
+    and clusters the gathered candidate list: clusters / cells / average_ / filtered_cells_ / flags == the whole search."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tools", "shard_frontier.py"),
+           "160", "128", "48"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "OK" in out.stdout
