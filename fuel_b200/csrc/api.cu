@@ -737,6 +737,16 @@ static cudaError_t upload_traj(FuelMap* m, FuelTrajConst* d_tc, const FuelTrajCo
                            sizeof(int32_t), B, cudaMemcpyDeviceToDevice, m->stream);
 }
 
+// page-locked (cudaHostRegister / cudaMallocHost) host memory can be DMA'd without the bounce copy
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static int check_bspline_args(FuelMap* m, int32_t B, int32_t n_pts, int32_t mask,
                               const FuelOptParams* p) {
   if (!m || !p) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
@@ -862,8 +872,12 @@ int fuelgpu_bspline_optimize_batch_begin(FuelMap* m, int32_t B, int32_t n_pts, i
       if (traj[b].view_idx < 0 || traj[b].view_idx >= n_pts)
         return fuel_fail(m, FUELGPU_EINVAL, "VIEWCONS needs FuelTrajConst.view_idx in [0, n_pts) (setViewConstraint)");
   FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack, mask));
-  memcpy(h_x, x, xb);
-  FUEL_CUDA(m, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, m->stream));
+  if (is_pinned_host(x)) {  // caller's buffer is page-locked (fuelgpu_host_register): DMA straight from it
+    FUEL_CUDA(m, cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, m->stream));
+  } else {
+    memcpy(h_x, x, xb);
+    FUEL_CUDA(m, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, m->stream));
+  }
   tbegin(m, T_BSPLINE);
   rc = bspline_optimize_batch_dev_impl(m, B, n_pts, mask, p, d_tc, solve, d_x, d_f, d_n);
   tend(m, T_BSPLINE);
