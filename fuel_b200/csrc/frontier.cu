@@ -327,6 +327,23 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
+// as uf_union, returning the root of the merged set as far as this thread has seen it
+__device__ __forceinline__ int uf_union_root(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return a;
+    if (a < b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(&parent[a], b);
+    if (old == a) return b;
+    a = old;
+  }
+}
+
 __device__ __forceinline__ void init_parent_item(int* parent, int* claim, int* csize, int n, int _tid) {
   const int i = _tid;
   if (i < n) {
@@ -369,9 +386,17 @@ __device__ __forceinline__ void union_item(Geom g, const int* __restrict__ cell_
     const int j = jn[q];
     jn[q] = (j >= 0 && cell_cls[j] == 1) ? j : -1;
   }
+  // Any ancestor is a valid start for a find: the neighbours' parents are fetched together (one round trip), the
+  // unions then run from them and from this cell's current root; equal consecutive parents are the same set already.
 #pragma unroll
-  for (int q = 0; q < 13; ++q)
-    if (jn[q] >= 0) uf_union(parent, i, jn[q]);
+  for (int q = 0; q < 13; ++q) jn[q] = jn[q] >= 0 ? parent[jn[q]] : -1;
+  int r = i, last = -1;
+#pragma unroll
+  for (int q = 0; q < 13; ++q) {
+    const int pj = jn[q];
+    if (pj >= 0 && pj != last && pj != r) r = uf_union_root(parent, r, pj);
+    if (pj >= 0) last = pj;
+  }
 }
 __device__ __forceinline__ void flatten_item(int* parent, const uint8_t* __restrict__ cell_cls, int n, int _tid) {
   const int i = _tid;
@@ -392,15 +417,33 @@ __device__ __forceinline__ void claim_item(Geom g, FParams fp, const int* __rest
                      z >= fp.s_lo[2] && z <= fp.s_hi[2];
     if (ins) atomicMin(&claim[label[i]], i);
   } else {
+    // the 26 lookups go out together, then the classes, then the labels: three round trips instead of one per neighbour
+    int jn[26];
+    int t = 0;
+#pragma unroll
     for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
       for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
         for (int dz = -1; dz <= 1; ++dz) {
           if (dx == 0 && dy == 0 && dz == 0) continue;
           const int X = x + dx, Y = y + dy, Z = z + dz;
-          if (X < 0 || Y < 0 || Z < 0 || X >= g.nx || Y >= g.ny || Z >= g.nz) continue;
-          const int j = cellidx[addr_of(g, X, Y, Z)];
-          if (j >= 0 && cell_cls[j] == 1) atomicMin(&claim[label[j]], i);
+          const bool ok = !(X < 0 || Y < 0 || Z < 0 || X >= g.nx || Y >= g.ny || Z >= g.nz);
+          jn[t++] = ok ? cellidx[addr_of(g, X, Y, Z)] : -1;
         }
+#pragma unroll
+    for (int q = 0; q < 26; ++q) {
+      const int j = jn[q];
+      jn[q] = (j >= 0 && cell_cls[j] == 1) ? j : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 26; ++q) jn[q] = jn[q] >= 0 ? label[jn[q]] : -1;
+    int last = -1;
+#pragma unroll
+    for (int q = 0; q < 26; ++q) {
+      if (jn[q] >= 0 && jn[q] != last) atomicMin(&claim[jn[q]], i);
+      if (jn[q] >= 0) last = jn[q];
+    }
   }
 }
 
@@ -544,6 +587,7 @@ __device__ __forceinline__ int leaf_coord(const Geom& g, const FParams& fp, int 
 // PCL VoxelGrid restated per cell: the min-address cell of every occupied leaf computes the
 // leaf centroid (float accumulation in ascending address order) and contributes to the split
 // test (:183-189) and the covariance (:194-200).
+template <bool LOCALMEAN = false>  // true: form the cluster mean from the statistics here (same expression as mean_item)
 __device__ __forceinline__ void downsample_item(Geom g, FParams fp, const int* __restrict__ k_addr,
                                   const int* __restrict__ k_cl, const int* __restrict__ cellidx,
                                   const ClusterMeta* __restrict__ meta, ClusterStat* st,
@@ -573,20 +617,29 @@ __device__ __forceinline__ void downsample_item(Geom g, FParams fp, const int* _
   // cellidx lookups are issued first, then all cluster-id lookups (two memory round trips
   // instead of one per voxel), then the float accumulation runs in the reference order.
   int jj[64];
+  const int a0 = (int)addr_of(g, lo[0], lo[1], lo[2]);
+  const int sx = g.ny * g.nz, sy = g.nz;
+  const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
 #pragma unroll
   for (int dx = 0; dx < 4; ++dx)
 #pragma unroll
     for (int dy = 0; dy < 4; ++dy)
 #pragma unroll
       for (int dz = 0; dz < 4; ++dz) {
-        const int x = lo[0] + dx, y = lo[1] + dy, z = lo[2] + dz;
-        const bool ok = x <= hi[0] && y <= hi[1] && z <= hi[2];
-        jj[(dx * 4 + dy) * 4 + dz] = ok ? cellidx[addr_of(g, x, y, z)] : -1;
+        const bool ok = dx <= ex && dy <= ey && dz <= ez;
+        jj[(dx * 4 + dy) * 4 + dz] = ok ? cellidx[a0 + dx * sx + dy * sy + dz] : -1;
       }
 #pragma unroll
   for (int v = 0; v < 64; ++v) {
     const int j = jj[v];
     jj[v] = (j >= 0 && k_cl[j] == c) ? j : -1;
+  }
+  float px[4], py[4], pz[4];  // the (float) positions of the leaf's voxel rows, formed once
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    px[d] = cell_posf(g, lo[0] + d, 0);
+    py[d] = cell_posf(g, lo[1] + d, 1);
+    pz[d] = cell_posf(g, lo[2] + d, 2);
   }
   float sum[3] = { 0.f, 0.f, 0.f };
   int cnt = 0;
@@ -596,9 +649,9 @@ __device__ __forceinline__ void downsample_item(Geom g, FParams fp, const int* _
     const int j = jj[v];
     if (j >= 0 && owner) {
       if (cnt == 0 && j != k) owner = false;  // a smaller-address cell owns this leaf
-      sum[0] += cell_posf(g, lo[0] + v / 16, 0);
-      sum[1] += cell_posf(g, lo[1] + (v / 4) % 4, 1);
-      sum[2] += cell_posf(g, lo[2] + v % 4, 2);
+      sum[0] += px[v / 16];
+      sum[1] += py[(v / 4) % 4];
+      sum[2] += pz[v % 4];
       ++cnt;
     }
   }
@@ -610,7 +663,13 @@ __device__ __forceinline__ void downsample_item(Geom g, FParams fp, const int* _
   k_cent[3 * k + 2] = cz;
   k_leaf[k] = lc[0] + lc[1] * div_b[0] + lc[2] * div_b[0] * div_b[1];
   atomicAdd(&st[c].nfilt, 1);
-  const double dx = (double)cx - meta[c].mean[0], dy = (double)cy - meta[c].mean[1];
+  double m0 = meta[c].mean[0], m1 = meta[c].mean[1];
+  if (LOCALMEAN) {
+    const double inv = 1.0 / (double)s.n;
+    m0 = ((double)s.sx * inv + 0.5) * g.res + g.origin[0];
+    m1 = ((double)s.sy * inv + 0.5) * g.res + g.origin[1];
+  }
+  const double dx = (double)cx - m0, dy = (double)cy - m1;
   if (sqrt(dx * dx + dy * dy) > fp.size_xy) atomicOr(&st[c].need_split, 1);
 }
 
@@ -942,6 +1001,78 @@ constexpr int SMALL_CTAS = 8;      // one thread-block cluster (portable maximum
 constexpr int SMALL_CAP = 32768;   // candidate cells
 constexpr int SMALL_CCAP = 8192;   // clusters (incl. split products)
 
+
+// Small path: the kept/root marks of 32 consecutive cells are one ballot, so the rank scan runs over ceil(n/32) <= 1024
+// chunk counts (one pass of one CTA) instead of n cells.  Arrays reused as: is_kept[q] / is_root[q] = the ballots of
+// chunk q, kept_off[q] / root_rank[q] = exclusive counts before chunk q.
+__device__ __forceinline__ void mark_chunk_item(const int* __restrict__ seed, const int* __restrict__ csize, int cluster_min,
+                                                int* __restrict__ root_mask, int* __restrict__ kept_mask, int n, int i) {
+  bool kept = false, root = false;
+  if (i < n) {
+    const int s = seed[i];
+    kept = s != NONE && csize[s] > cluster_min;  // expanded.size() > cluster_min_ (:157)
+    root = kept && s == i;
+  }
+  const unsigned mk = __ballot_sync(0xffffffffu, kept), mr = __ballot_sync(0xffffffffu, root);
+  if ((i & 31) == 0 && i < n) {
+    kept_mask[i >> 5] = (int)mk;
+    root_mask[i >> 5] = (int)mr;
+  }
+}
+__device__ void chunk_scan_small(const int* __restrict__ root_mask, const int* __restrict__ kept_mask,
+                                 int* __restrict__ root_off, int* __restrict__ kept_off, int nchunk,
+                                 int* __restrict__ tot_root, int* __restrict__ tot_kept) {
+  __shared__ unsigned wtot2[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const unsigned v = t < nchunk ? ((unsigned)__popc((unsigned)root_mask[t]) << 16) + (unsigned)__popc((unsigned)kept_mask[t]) : 0u;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) wtot2[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    const unsigned x = wtot2[lane];
+    unsigned xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += u;
+    }
+    wtot2[lane] = xi - x;
+    if (lane == 31) {
+      *tot_root = (int)(xi >> 16);
+      *tot_kept = (int)(xi & 0xffffu);
+    }
+  }
+  __syncthreads();
+  if (t < nchunk) {
+    const unsigned ex = wtot2[w] + inc - v;
+    root_off[t] = (int)(ex >> 16);
+    kept_off[t] = (int)(ex & 0xffffu);
+  }
+}
+__device__ __forceinline__ void gather_chunk_item(const int* __restrict__ cell_addr, const int* __restrict__ seed,
+                                                  const int* __restrict__ kept_mask, const int* __restrict__ kept_off,
+                                                  const int* __restrict__ root_mask, const int* __restrict__ root_off,
+                                                  int* __restrict__ k_addr, int* __restrict__ k_cl,
+                                                  int* __restrict__ cellidx, int n, int i) {
+  if (i >= n) return;
+  const unsigned mk = (unsigned)kept_mask[i >> 5];
+  const int a = cell_addr[i];
+  if ((mk >> (i & 31)) & 1u) {
+    const int k = kept_off[i >> 5] + __popc(mk & ((1u << (i & 31)) - 1u));
+    const int s = seed[i];
+    k_addr[k] = a;
+    k_cl[k] = root_off[s >> 5] + __popc((unsigned)root_mask[s >> 5] & ((1u << (s & 31)) - 1u));
+    cellidx[a] = k;
+  } else {
+    cellidx[a] = -1;
+  }
+}
+
 struct SmallBufs {
   int *cell_addr, *parent, *claim, *csize, *seed, *is_root, *is_kept, *root_rank, *kept_off;
   uint8_t* cell_cls;
@@ -956,7 +1087,9 @@ __global__ void __cluster_dims__(SMALL_CTAS, 1, 1) __launch_bounds__(1024) clust
                                                              int* __restrict__ cellidx, SmallBufs b) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int tid = rank * 1024 + threadIdx.x;
+  // items go to warps round-robin over the CTAs (32 consecutive items per warp): a few thousand cells keep all 8 SMs
+  // busy instead of filling the first CTAs only
+  const int tid = (((int)threadIdx.x >> 5) * SMALL_CTAS + rank) * 32 + ((int)threadIdx.x & 31);
   constexpr int NT = 1024 * SMALL_CTAS;
   const int n = b.counters[0];
 #ifdef FUEL_PROF
@@ -987,61 +1120,59 @@ __global__ void __cluster_dims__(SMALL_CTAS, 1, 1) __launch_bounds__(1024) clust
   FOR_ITEMS(i, n) assign_item(b.cell_addr, b.cell_cls, b.parent, b.claim, b.seed, b.csize, flag, n, i);
   cluster.sync();
   STAMP();
-  FOR_ITEMS(i, n) mark_item(b.seed, b.csize, fp.cluster_min, b.is_root, b.is_kept, n, i);
+  FOR_ITEMS(i, n) mark_chunk_item(b.seed, b.csize, fp.cluster_min, b.is_root, b.is_kept, n, i);
   cluster.sync();
   STAMP();
-  if (rank == 0) {
-    block_scan_small2(b.is_root, b.is_kept, b.root_rank, b.kept_off, n, b.counters + 1, b.counters + 2);
-  }
+  if (rank == 0) chunk_scan_small(b.is_root, b.is_kept, b.root_rank, b.kept_off, (n + 31) >> 5, b.counters + 1, b.counters + 2);
   cluster.sync();
   STAMP();
   const int R = b.counters[1], K = b.counters[2];
   int C = R;
   int status = 0;
   if (R > 0 && K > 0) {
-    FOR_ITEMS(i, n) gather_kept_item(b.cell_addr, b.seed, b.is_kept, b.kept_off, b.root_rank, b.k_addr, b.k_cl,
-                                     cellidx, n, i);
-    FOR_ITEMS(c, R) init_meta_item(b.meta, R, c);
+    FOR_ITEMS(i, n) gather_chunk_item(b.cell_addr, b.seed, b.is_kept, b.kept_off, b.is_root, b.root_rank, b.k_addr, b.k_cl,
+                                      cellidx, n, i);
+    FOR_ITEMS(c, R) {
+      init_meta_item(b.meta, R, c);
+      stat_reset_item(b.stat, b.meta, R, c);
+    }
     cluster.sync();
-  STAMP();
+    STAMP();
     for (int level = 0; level < 40; ++level) {
       if (2 * C > SMALL_CCAP) {
         status = 2;
         break;
       }
-      FOR_ITEMS(c, C) stat_reset_item(b.stat, b.meta, C, c);
-      cluster.sync();
-  STAMP();
       FOR_ITEMS(k, K) stat_accum_item(g, b.k_addr, b.k_cl, b.meta, b.stat, K, k);
       cluster.sync();
-  STAMP();
+      STAMP();
+      // the cluster means are written for the later phases while the VoxelGrid pass forms its own copy
       FOR_ITEMS(c, C) mean_item(g, b.meta, b.stat, C, c);
+      FOR_ITEMS(k, K) downsample_item<true>(g, fp, b.k_addr, b.k_cl, cellidx, b.meta, b.stat, b.k_cent, b.k_leaf, K, k);
       cluster.sync();
-  STAMP();
-      FOR_ITEMS(k, K) downsample_item(g, fp, b.k_addr, b.k_cl, cellidx, b.meta, b.stat, b.k_cent, b.k_leaf, K, k);
-      cluster.sync();
-  STAMP();
+      STAMP();
       FOR_ITEMS(k, K) cov_item(b.k_cl, b.k_leaf, b.k_cent, b.meta, b.stat, K, k);
       cluster.sync();
-  STAMP();
+      STAMP();
       FOR_ITEMS(c, C) pca_item(b.meta, b.stat, C, c);
       cluster.sync();
-  STAMP();
+      STAMP();
       FOR_ITEMS(k, K) side_count_item(g, b.k_addr, b.k_cl, b.meta, b.stat, K, k);
       cluster.sync();
-  STAMP();
+      STAMP();
       if (rank == 0) split_alloc(b.meta, b.stat, C, b.counters + 3);
       cluster.sync();
-  STAMP();
+      STAMP();
       FOR_ITEMS(k, K) relabel_item(g, b.k_addr, b.k_cl, b.meta, K, C, k);
       cluster.sync();
-  STAMP();
+      STAMP();
       const int n_new = b.counters[3];
       if (n_new == 0) break;
       FOR_ITEMS(c, C) clear_do_split_item(b.meta, C, c);
       C += n_new;
+      FOR_ITEMS(c, C) stat_reset_item(b.stat, b.meta, C, c);  // for the next level (children included)
       cluster.sync();
-  STAMP();
+      STAMP();
     }
   }
   FOR_ITEMS(i, n) reset_cellidx_item(b.cell_addr, cellidx, n, i);
