@@ -398,6 +398,10 @@ class GpuPlanner:
         # (fuelgpu_frontier_search_begin), the ESDF update and the solver run beside it on the main
         # stream, and the result is collected last (fuelgpu_frontier_search_end)
         self.overlap = overlap
+        # issue order inside an overlapped replan: the frontier search goes first -- its 8-CTA cluster kernel needs whole
+        # SMs and does not get them once the solver's 256 CTAs are resident (measured: it then runs AFTER the solver,
+        # 0.72 ms per replan instead of 0.40).  FUELGPU_BENCH_ORDER=solver_first shows it.
+        self.solver_first = os.environ.get("FUELGPU_BENCH_ORDER", "frontier_first") == "solver_first"
 
     def _frontier_begin(self):
         self.ff.reset_flags()
@@ -409,7 +413,8 @@ class GpuPlanner:
     def replan_resident(self):
         """Inputs already in HBM: occupancy byte, x, trajectory constants."""
         L, C = self.fuel.lib(), self.C
-        self._frontier_begin()
+        if not (self.overlap and self.solver_first):
+            self._frontier_begin()
         if not self.overlap:
             self.n_clusters = len(self.ff.search_box_end())
         self.m.updateESDF3d()
@@ -424,6 +429,8 @@ class GpuPlanner:
         if rc:
             raise RuntimeError(L.fuelgpu_last_error(h))
         if self.overlap:
+            if self.solver_first:
+                self._frontier_begin()
             self.n_clusters = len(self.ff.search_box_end())
 
     def replan_e2e(self):
@@ -433,18 +440,23 @@ class GpuPlanner:
         H2D once, best x / cost / eval count D2H once)."""
         m = self.m
         m.upload(wait=not self.overlap)  # overlap: the mirrors are not touched before the final synchronize()
-        self._frontier_begin()
+        if not (self.overlap and self.solver_first):
+            self._frontier_begin()
         if not self.overlap:
             out = self.ff.search_box_end()
         m.updateESDF3d()
-        m.download(wait=not self.overlap)  # overlap: the D2H mirror copy runs beside the solver
         if self.overlap:
-            # solver enqueued; the frontier result is marshalled on the host while it runs
+            # solver enqueued (its inputs go H2D beside the ESDF kernels), then the D2H mirror copy, which runs beside
+            # the solver; the frontier result is marshalled on the host meanwhile
             self.opt.optimizeBatchBegin(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0, exact_evals=True)
+            if self.solver_first:
+                self._frontier_begin()
+            m.download(wait=False)
             out = self.ff.search_box_end()
             x, f, ne = self.opt.optimizeBatchEnd(out=self.opt_out)
             m.synchronize()  # ESDF host mirror complete
         else:
+            m.download(wait=True)
             x, f, ne = self.opt.optimizeBatch(self.x_host, self.tcs, 20, self.mask, self.evals, xtol_rel=0.0,
                                               out=self.opt_out, exact_evals=True)
         self.last_neval = ne

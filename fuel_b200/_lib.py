@@ -84,6 +84,7 @@ SIGNATURES = {
     "fuelgpu_map_synchronize": (C.c_int, [_vp]),
     "fuelgpu_map_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "fuelgpu_map_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "fuelgpu_map_last_timeline": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "fuelgpu_host_register": (C.c_int, [_vp, C.c_uint64]),
     "fuelgpu_host_unregister": (C.c_int, [_vp]),
     "fuelgpu_map_upload_occupancy": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp]),

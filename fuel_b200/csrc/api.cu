@@ -184,6 +184,8 @@ int fuelgpu_map_create(const FuelGridDesc* grid, int device_id, FuelMap** out) {
   m->stream = m->own_stream;
   CR(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   CR(cudaEventCreateWithFlags(&m->copy_ev, cudaEventDisableTiming));
+  CR(cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking));
+  CR(cudaEventCreateWithFlags(&m->in_ev, cudaEventDisableTiming));
   for (int t = 0; t < T_COUNT; ++t) {
     CR(cudaEventCreate(&m->ev0[t]));
     CR(cudaEventCreate(&m->ev1[t]));
@@ -249,6 +251,11 @@ int fuelgpu_map_destroy(FuelMap* m) {
     cudaStreamDestroy(m->copy_stream);
   }
   if (m->copy_ev) cudaEventDestroy(m->copy_ev);
+  if (m->in_stream) {
+    cudaStreamSynchronize(m->in_stream);
+    cudaStreamDestroy(m->in_stream);
+  }
+  if (m->in_ev) cudaEventDestroy(m->in_ev);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
   return 0;
@@ -282,6 +289,21 @@ int fuelgpu_map_last_timing(FuelMap* m, float ms[8]) {
     ms[t] = -1.f;
     if (m->ev_valid[t]) {
       if (cudaEventSynchronize(m->ev1[t]) == cudaSuccess) cudaEventElapsedTime(&ms[t], m->ev0[t], m->ev1[t]);
+    }
+  }
+  return 0;
+}
+
+int fuelgpu_map_last_timeline(FuelMap* m, float start_ms[8], float end_ms[8]) {
+  if (!m || !start_ms || !end_ms) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
+  for (int t = 0; t < T_COUNT; ++t) {
+    start_ms[t] = end_ms[t] = -1.f;
+    if (!m->ev_valid[t] || !m->ev_valid[T_UPLOAD]) continue;
+    if (cudaEventSynchronize(m->ev1[t]) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&start_ms[t], m->ev0[T_UPLOAD], m->ev0[t]) != cudaSuccess ||
+        cudaEventElapsedTime(&end_ms[t], m->ev0[T_UPLOAD], m->ev1[t]) != cudaSuccess) {
+      cudaGetLastError();  // (a stage older than the last upload: not on this timeline)
+      start_ms[t] = end_ms[t] = -1.f;
     }
   }
   return 0;
@@ -459,6 +481,7 @@ int fuelgpu_esdf_update(FuelMap* m, const int32_t bmin[3], const int32_t bmax[3]
   tbegin(m, T_ESDF);
   rc = esdf_update_impl(m, lo, hi, flags);
   tend(m, T_ESDF);
+  m->dist_ev_ok = rc == 0;
   return rc;
 }
 
@@ -503,6 +526,7 @@ int fuelgpu_esdf_set_from_slabs_dev(FuelMap* m, const void* slabs_dev, int32_t n
     FUEL_LAUNCHES(m, 1);
     FUEL_CUDA(m, cudaGetLastError());
   }
+  m->dist_ev_ok = false;  // (the field no longer comes from the last fuelgpu_esdf_update)
   return 0;
 }
 
@@ -515,9 +539,15 @@ int fuelgpu_esdf_download_async(FuelMap* m, const int32_t bmin[3], const int32_t
   const int64_t plane = (int64_t)m->g.ny * m->g.nz;
   const int64_t off = (int64_t)lo[0] * plane;
   const int64_t cnt = (int64_t)(hi[0] - lo[0] + 1) * plane;
-  FUEL_CUDA(m, cudaEventRecord(m->copy_ev, m->stream));
-  FUEL_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->copy_ev, 0));
+  if (m->dist_ev_ok) {  // after the ESDF update that wrote the field -- not after whatever the main stream got since (a solve)
+    FUEL_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev1[T_ESDF], 0));
+  } else {
+    FUEL_CUDA(m, cudaEventRecord(m->copy_ev, m->stream));
+    FUEL_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->copy_ev, 0));
+  }
+  tbegin(m, T_DOWNLOAD, m->copy_stream);
   FUEL_CUDA(m, cudaMemcpyAsync(out_f32 + off, m->dist + off, cnt * 4, cudaMemcpyDeviceToHost, m->copy_stream));
+  tend(m, T_DOWNLOAD, m->copy_stream);
   return 0;
 }
 
@@ -720,21 +750,22 @@ int fuelgpu_frontier_upload_flags(FuelMap* m, const int8_t* in) {
 // page-locked bounce buffer, one contiguous DMA, then two strided device-side copies into the records.
 // `pin` = host bounce area of >= B*(head+4) bytes, `d_pack` = device scratch of the same size.
 static cudaError_t upload_traj(FuelMap* m, FuelTrajConst* d_tc, const FuelTrajConst* traj, int B, uint8_t* pin,
-                               uint8_t* d_pack, int mask = 0) {
+                               uint8_t* d_pack, int mask = 0, cudaStream_t st = nullptr) {
+  if (!st) st = m->stream;
   bool lean = !(mask & FUELGPU_VIEWCONS);  // the view constraint sits at the end of the record
   for (int b = 0; b < B && lean; ++b) lean = traj[b].n_guide == 0 && traj[b].n_waypt == 0;
-  if (!lean) return cudaMemcpyAsync(d_tc, traj, sizeof(FuelTrajConst) * (size_t)B, cudaMemcpyHostToDevice, m->stream);
+  if (!lean) return cudaMemcpyAsync(d_tc, traj, sizeof(FuelTrajConst) * (size_t)B, cudaMemcpyHostToDevice, st);
   const size_t head = offsetof(FuelTrajConst, guide), rec = head + sizeof(int32_t);
   for (int b = 0; b < B; ++b) {
     memcpy(pin + rec * b, &traj[b], head);
     memcpy(pin + rec * b + head, &traj[b].n_waypt, sizeof(int32_t));
   }
-  cudaError_t e = cudaMemcpyAsync(d_pack, pin, rec * B, cudaMemcpyHostToDevice, m->stream);
+  cudaError_t e = cudaMemcpyAsync(d_pack, pin, rec * B, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
-  e = cudaMemcpy2DAsync(d_tc, sizeof(FuelTrajConst), d_pack, rec, head, B, cudaMemcpyDeviceToDevice, m->stream);
+  e = cudaMemcpy2DAsync(d_tc, sizeof(FuelTrajConst), d_pack, rec, head, B, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return e;
   return cudaMemcpy2DAsync((char*)d_tc + offsetof(FuelTrajConst, n_waypt), sizeof(FuelTrajConst), d_pack + head, rec,
-                           sizeof(int32_t), B, cudaMemcpyDeviceToDevice, m->stream);
+                           sizeof(int32_t), B, cudaMemcpyDeviceToDevice, st);
 }
 
 // page-locked (cudaHostRegister / cudaMallocHost) host memory can be DMA'd without the bounce copy
@@ -871,13 +902,17 @@ int fuelgpu_bspline_optimize_batch_begin(FuelMap* m, int32_t B, int32_t n_pts, i
     for (int b = 0; b < B; ++b)
       if (traj[b].view_idx < 0 || traj[b].view_idx >= n_pts)
         return fuel_fail(m, FUELGPU_EINVAL, "VIEWCONS needs FuelTrajConst.view_idx in [0, n_pts) (setViewConstraint)");
-  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack, mask));
+  // The inputs go out on their own stream -- at once, beside whatever the main stream is still running (the ESDF
+  // update, typically) -- and the solver waits for them.  (The scratch is free: every user of it synchronises.)
+  FUEL_CUDA(m, upload_traj(m, d_tc, traj, B, pin, d_pack, mask, m->in_stream));
   if (is_pinned_host(x)) {  // caller's buffer is page-locked (fuelgpu_host_register): DMA straight from it
-    FUEL_CUDA(m, cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, m->stream));
+    FUEL_CUDA(m, cudaMemcpyAsync(d_x, x, xb, cudaMemcpyHostToDevice, m->in_stream));
   } else {
     memcpy(h_x, x, xb);
-    FUEL_CUDA(m, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, m->stream));
+    FUEL_CUDA(m, cudaMemcpyAsync(d_x, h_x, xb, cudaMemcpyHostToDevice, m->in_stream));
   }
+  FUEL_CUDA(m, cudaEventRecord(m->in_ev, m->in_stream));
+  FUEL_CUDA(m, cudaStreamWaitEvent(m->stream, m->in_ev, 0));
   tbegin(m, T_BSPLINE);
   rc = bspline_optimize_batch_dev_impl(m, B, n_pts, mask, p, d_tc, solve, d_x, d_f, d_n);
   tend(m, T_BSPLINE);

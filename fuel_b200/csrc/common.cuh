@@ -51,6 +51,9 @@ struct FuelMap {
   cudaStream_t own_stream, stream;
   cudaStream_t copy_stream;  // D2H mirror copies that may overlap the main stream
   cudaEvent_t copy_ev;
+  bool dist_ev_ok;           // ev1[T_ESDF] marks the last write of `dist` (a mirror download waits on it, not on later work)
+  cudaStream_t in_stream;    // H2D of the solver inputs: goes out at once, not behind the ESDF kernels of the main stream
+  cudaEvent_t in_ev;
   cudaEvent_t ev0[T_COUNT], ev1[T_COUNT];
   bool ev_valid[T_COUNT];
   FrontierState* fs;

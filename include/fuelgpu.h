@@ -77,6 +77,9 @@ FUELGPU_API int fuelgpu_map_device_ptrs(FuelMap* map, void** occ, void** dist, v
 /* Milliseconds spent on the device by the last call of each stage (CUDA events on the
  * handle's stream): [0] esdf_update [1] frontier_search [2] bspline batch [3] upload [4] download */
 FUELGPU_API int fuelgpu_map_last_timing(FuelMap* map, float ms[8]);
+/* Where the last call of each stage sat on the device timeline: start and end in milliseconds after the start of the
+ * last upload (same stage indices; -1 = stage not run or no upload recorded).  Diagnostic for overlapped sequences. */
+FUELGPU_API int fuelgpu_map_last_timeline(FuelMap* map, float start_ms[8], float end_ms[8]);
 /* Number of kernels this handle has launched since creation (every <<<>>> is counted). */
 FUELGPU_API int fuelgpu_map_launch_count(FuelMap* map, int64_t* count);
 
