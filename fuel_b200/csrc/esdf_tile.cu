@@ -77,6 +77,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   }
 }
 
+// ---- thread-block cluster primitives (lines longer than 512 samples: one tile = 2 CTAs, hulls joined over DSMEM) ----
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\nbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t a, unsigned rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldc32(uint32_t ca) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(ca) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ldc16(uint32_t ca) {
+  uint16_t v;
+  asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(ca) : "memory");
+  return (int)v;
+}
+__device__ __forceinline__ void stc16(uint32_t ca, int v) {
+  asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(ca), "h"((uint16_t)v) : "memory");
+}
+
 // site predicate of the z sweep.  mode 0: optimistic (sdf_map.cpp:156-166) inflate==1;
 // mode 1: non-optimistic (:167-181) inflate==1 || unknown; mode 2: negative field (:203-214)
 // inflate==0.
@@ -211,7 +240,232 @@ __device__ __forceinline__ float fast_sqrt(float x) {
   return r;
 }
 
-template <bool FROMBITS, bool FINAL, int LOGM, int MAXT, int MINB>
+// Hull bookkeeping of a tile as seen by ONE lane.  LO/HI = first / one-past-last live entry of a band (row numbers of
+// the whole line), ent = the entry stored in a row.  Local: this CTA's shared memory.  Remote / Cluster: the arrays of
+// the other CTA of a 2-CTA cluster (rows >= rpc and bands >= nbh live in CTA 1), reached through shared::cluster.
+struct HullLocal {
+  uint16_t* LOl;
+  uint16_t* HIl;
+  uint32_t* Tl;
+  int row0;  // first row held by this CTA
+  __device__ __forceinline__ int lo(int b) const { return LOl[b * 32]; }
+  __device__ __forceinline__ int hi(int b) const { return HIl[b * 32]; }
+  __device__ __forceinline__ void set_lo(int b, int v) const { LOl[b * 32] = (uint16_t)v; }
+  __device__ __forceinline__ void set_hi(int b, int v) const { HIl[b * 32] = (uint16_t)v; }
+  __device__ __forceinline__ uint32_t ent(int row) const { return Tl[(row - row0) * 32]; }
+  // phase 3 (row0 == 0 there)
+  __device__ __forceinline__ uint32_t ent_addr(int row) const { return smem_u32(Tl) + (uint32_t)row * 128u; }
+  __device__ __forceinline__ uint32_t ld(uint32_t a) const { return lds32(a); }
+};
+struct HullRemote {  // bands / rows of the cluster's OTHER CTA, indexed like its own HullLocal
+  uint32_t LOa, HIa, Ta;  // shared::cluster addresses, lane offset included
+  int row0;
+  __device__ __forceinline__ int lo(int b) const { return ldc16(LOa + (uint32_t)b * 64u); }
+  __device__ __forceinline__ int hi(int b) const { return ldc16(HIa + (uint32_t)b * 64u); }
+  __device__ __forceinline__ void set_lo(int b, int v) const { stc16(LOa + (uint32_t)b * 64u, v); }
+  __device__ __forceinline__ void set_hi(int b, int v) const { stc16(HIa + (uint32_t)b * 64u, v); }
+  __device__ __forceinline__ uint32_t ent(int row) const { return ldc32(Ta + (uint32_t)(row - row0) * 128u); }
+};
+struct HullCluster {  // bands / rows of the whole line, whichever CTA holds them
+  uint32_t LOa, HIa, Ta;  // shared::cta addresses of THIS CTA's arrays, lane offset included
+  int nbh, rpc;           // bands / rows per CTA
+  __device__ __forceinline__ int lo(int g) const {
+    const unsigned rk = g >= nbh;
+    return ldc16(mapa_u32(LOa + (uint32_t)(g - (int)rk * nbh) * 64u, rk));
+  }
+  __device__ __forceinline__ int hi(int g) const {
+    const unsigned rk = g >= nbh;
+    return ldc16(mapa_u32(HIa + (uint32_t)(g - (int)rk * nbh) * 64u, rk));
+  }
+  __device__ __forceinline__ uint32_t ent_addr(int row) const {
+    const unsigned rk = row >= rpc;
+    return mapa_u32(Ta + (uint32_t)(row - (int)rk * rpc) * 128u, rk);
+  }
+  __device__ __forceinline__ uint32_t ld(uint32_t a) const { return ldc32(a); }
+};
+
+// join the hull of bands [gl0, gl1) of A (left) with the hull of bands [gr0, gr1) of B (right): with equal curvature
+// the difference of the two envelopes is monotone, so the joint hull is a prefix of the left one followed by a suffix
+// of the right one; the bridge is found by a two-pointer walk from the junction.
+template <class HA, class HB>
+__device__ __forceinline__ void join_hulls(const HA& A, int gl0, int gl1, const HB& B, int gr0, int gr1) {
+  int bl = gl1 - 1;
+  while (bl >= gl0 && A.lo(bl) == A.hi(bl)) --bl;
+  int br = gr0;
+  while (br < gr1 && B.lo(br) == B.hi(br)) ++br;
+  if (bl < gl0 || br >= gr1) return;
+  int il = A.hi(bl) - 1, jr = B.lo(br);
+  uint32_t e = A.ent(il);
+  int vi = unpack_v(e), hi_ = unpack_h(e);
+  e = B.ent(jr);
+  int vj = unpack_v(e), hj = unpack_h(e);
+  // predecessor of the left end / successor of the right end inside their groups
+  int pb = bl, pi = il - 1, vp = 0, hp = 0;
+  bool hasp;
+  int nbd = br, ni = jr + 1, vn = 0, hn = 0;
+  bool hasn;
+  auto find_prev = [&]() {
+    if (pi < A.lo(pb)) {
+      --pb;
+      while (pb >= gl0 && A.lo(pb) == A.hi(pb)) --pb;
+      if (pb >= gl0) pi = A.hi(pb) - 1;
+    }
+    hasp = pb >= gl0;
+    if (hasp) {
+      const uint32_t ee = A.ent(pi);
+      vp = unpack_v(ee);
+      hp = unpack_h(ee);
+    }
+  };
+  auto find_next = [&]() {
+    if (ni >= B.hi(nbd)) {
+      ++nbd;
+      while (nbd < gr1 && B.lo(nbd) == B.hi(nbd)) ++nbd;
+      if (nbd < gr1) ni = B.lo(nbd);
+    }
+    hasn = nbd < gr1;
+    if (hasn) {
+      const uint32_t ee = B.ent(ni);
+      vn = unpack_v(ee);
+      hn = unpack_h(ee);
+    }
+  };
+  find_prev();
+  find_next();
+  while (true) {
+    const long long A_ = (long long)(hj - hi_);
+    const long long dji = (long long)(vj - vi);
+    if (hasp && A_ * (long long)(vi - vp) <= (long long)(hi_ - hp) * dji) {
+      // the left end never gets below the right hull inside its own region: drop it
+      il = pi;
+      bl = pb;
+      vi = vp;
+      hi_ = hp;
+      pi = il - 1;
+      find_prev();
+      continue;
+    }
+    if (hasn && A_ * (long long)(vn - vj) >= (long long)(hn - hj) * dji) {
+      jr = ni;
+      br = nbd;
+      vj = vn;
+      hj = hn;
+      ni = jr + 1;
+      find_next();
+      continue;
+    }
+    break;
+  }
+  for (int b2 = bl + 1; b2 < gl1; ++b2) A.set_hi(b2, A.lo(b2));
+  A.set_hi(bl, il + 1);
+  for (int b2 = gr0; b2 < br; ++b2) B.set_lo(b2, B.hi(b2));
+  B.set_lo(br, jr);
+}
+
+// phase 3: the thread of band `gband` (samples [j0, qend)) evaluates its samples on the joint hull of all nbt bands
+template <bool FINAL, int LOGM, class H>
+__device__ __forceinline__ void evaluate_band(const H& hull, int gband, int nbt, int j0, int qend, char* op,
+                                              unsigned ostride, float res) {
+  int cb = gband;
+  while (cb >= 0 && hull.lo(cb) == hull.hi(cb)) --cb;
+  bool empty = false;
+  if (cb < 0) {
+    cb = gband + 1;
+    while (cb < nbt && hull.lo(cb) == hull.hi(cb)) ++cb;
+    empty = cb >= nbt;
+  } else {
+    // go back while the first entry of band cb has not yet taken over from its predecessor at j0
+    while (true) {
+      int pb = cb - 1;
+      while (pb >= 0 && hull.lo(pb) == hull.hi(pb)) --pb;
+      if (pb < 0) break;
+      const uint32_t e1 = hull.ld(hull.ent_addr(hull.lo(cb))), e0 = hull.ld(hull.ent_addr(hull.hi(pb) - 1));
+      if (unpack_h(e1) - unpack_h(e0) < 2 * j0 * (unpack_v(e1) - unpack_v(e0))) break;
+      cb = pb;
+    }
+  }
+  if (empty) {
+    for (int u = 0; u < qend - j0; ++u) {
+      char* const a = op + (uint64_t)(unsigned)u * ostride;
+      if (FINAL)
+        *reinterpret_cast<float*>(a) = __int_as_float(0x7f800000);
+      else
+        *reinterpret_cast<int32_t*>(a) = INF_I;
+    }
+    return;
+  }
+  // cur = (vc,hc); np -> the entry after it, nend = end of np's band; (dvn,dhn) = next - cur, or (0,1) when
+  // the hull is exhausted (the takeover test 2q*dvn > dhn can then never fire)
+  uint32_t np, nend;
+  {
+    const int l0 = hull.lo(cb);
+    np = hull.ent_addr(l0);
+    nend = np + (uint32_t)(hull.hi(cb) - l0) * 128u;
+  }
+  int vc, hc, dvn, dhn;
+  {
+    const uint32_t e = hull.ld(np);
+    vc = unpack_v(e);
+    hc = unpack_h(e);
+  }
+  // advance np to the following live entry; false when there is none
+  auto step_next = [&]() -> bool {
+    np += 128u;
+    if (np == nend) {
+      ++cb;
+      while (cb < nbt && hull.lo(cb) == hull.hi(cb)) ++cb;
+      if (cb >= nbt) return false;
+      const int l0 = hull.lo(cb);
+      np = hull.ent_addr(l0);
+      nend = np + (uint32_t)(hull.hi(cb) - l0) * 128u;
+    }
+    return true;
+  };
+  if (step_next()) {
+    const uint32_t e = hull.ld(np);
+    dvn = unpack_v(e) - vc;
+    dhn = unpack_h(e) - hc;
+  } else {
+    dvn = 0;
+    dhn = 1;
+  }
+  const int cnt = qend - j0;
+  // val(q) = (q-vc)^2 + f(vc) = hc + q(q - 2vc) is carried incrementally: val(q+1) = val(q) + inc, inc += 2
+  int val = hc + j0 * (j0 - 2 * vc), inc = 2 * (j0 - vc) + 1;
+  char* oa = op;
+#pragma unroll 2
+  for (int u = 0; u < cnt; ++u) {
+    const int q = j0 + u;
+    // the next parabola takes over at the first integer q with (hn-hc) < 2q(vn-vc)
+    if (2 * q * dvn > dhn) {
+      do {
+        vc += dvn;
+        hc += dhn;
+        if (!step_next()) {
+          dvn = 0;
+          dhn = 1;
+          break;
+        }
+        const uint32_t e = hull.ld(np);
+        dvn = unpack_v(e) - vc;
+        dhn = unpack_h(e) - hc;
+      } while (2 * q * dvn > dhn);
+      val = hc + q * (q - 2 * vc);
+      inc = 2 * (q - vc) + 1;
+    }
+    if (FINAL)
+      *reinterpret_cast<float*>(oa) = res * fast_sqrt((float)val);
+    else
+      *reinterpret_cast<int32_t*>(oa) = val;
+    oa += ostride;
+    val += inc;
+    inc += 2;
+  }
+}
+
+// CL: the tile of a line longer than 512 samples is shared by the two CTAs of a thread-block cluster (CTA r holds
+// rows [r*rpc, (r+1)*rpc): 64 KB each, three CTAs per SM instead of one 128 KB CTA); p.nb = bands per CTA.
+template <bool FROMBITS, bool FINAL, int LOGM, int MAXT, int MINB, bool CL>
 __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TileParams p) {
   constexpr int M = 1 << LOGM;  // samples per band (= per thread)
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -224,11 +478,16 @@ __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TilePar
 
   const int lane = threadIdx.x & 31;
   const int band = threadIdx.x >> 5;
-  const int bx = blockIdx.x, o = blockIdx.y;
+  const unsigned rank = CL ? cluster_ctarank() : 0u;
+  const int bx = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, o = blockIdx.y;
+  const int rpc = nb << LOGM;                 // rows per CTA
+  const int row0 = CL ? (int)rank * rpc : 0;  // first row of the line held here
+  const int gband = (CL ? (int)rank * nb : 0) + band;
   uint32_t* const Tl = T + lane;
   uint16_t* const LOl = LO + lane;
   uint16_t* const HIl = HI + lane;
-  const int j0 = band << LOGM;
+  const int j0 = gband << LOGM;  // first sample (row of the line) of this thread's band
+  const int nloc = max(0, min(n - row0, rpc));  // rows of the line held here
 
   // ---- phase 0: bring the tile in ----------------------------------------------------
   if (threadIdx.x == 0) {
@@ -239,9 +498,9 @@ __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TilePar
   __syncthreads();
   if (FROMBITS) {
     if (threadIdx.x == 0) {
-      const unsigned bytes = (unsigned)(((n * 8) + 15) & ~15);
+      const unsigned bytes = (unsigned)(((nloc * 8) + 15) & ~15);
       mbar_expect_tx(bar, bytes);
-      bulk_g2s(side, p.rec + ((int64_t)o * p.NW + p.w0 + bx) * p.NYP, bytes, bar);
+      if (bytes) bulk_g2s(side, p.rec + ((int64_t)o * p.NW + p.w0 + bx) * p.NYP + row0, bytes, bar);
     }
     // one warp polls the mbarrier, the others sleep at the CTA barrier (a spinning try_wait in every
     // warp took 46 % of the issue slots of the SM away from the CTAs that had work)
@@ -257,12 +516,12 @@ __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TilePar
       uint32_t m = 0;
       int dl = BIGD, dr = BIGD;
       if (t < n) {
-        const uint2 r = side[t];
+        const uint2 r = side[t - row0];
         m = r.x;
         dl = (int)(r.y & 0xffffu);
         dr = (int)(r.y >> 16);
       }
-      uint32_t* const Trow = T + (size_t)t * 32;
+      uint32_t* const Trow = T + (size_t)(t - row0) * 32;
       if (__all_sync(FULL, m == 0)) {
         // no site inside this word for any of the warp's 32 rows (the common case in open space)
         if (__all_sync(FULL, dl >= BIGD && dr >= BIGD)) {
@@ -295,12 +554,12 @@ __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TilePar
     __syncwarp();
   } else {
     // the tile is contiguous in P (K1 writes it that way): every warp brings its own band in with ONE bulk copy
-    if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned)n * 128u);
+    if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned)nloc * 128u);
     const int piece = j0 / p.piece_rows;
     const int32_t* const bsrc = p.pin + (int64_t)o * p.in_o + (int64_t)bx * p.in_bx + (int64_t)piece * p.piece_stride +
                                 (int64_t)(j0 - piece * p.piece_rows) * 32;
     if (lane == 0 && j0 < n)
-      bulk_g2s(T + (size_t)j0 * 32, bsrc, (unsigned)(min(n, j0 + M) - j0) * 128u, bar);
+      bulk_g2s(T + (size_t)(j0 - row0) * 32, bsrc, (unsigned)(min(n, j0 + M) - j0) * 128u, bar);
     if (band == 0) mbar_wait(bar, 0);
     __syncthreads();
     // the tile of P is dead once it sits in shared memory: drop its lines from L2 instead of letting them be
@@ -316,9 +575,9 @@ __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TilePar
     int v1 = j0 - 1, h1 = SENT + v1 * v1;  // virtual bottom parabola, never stored, owns nothing in [0,n)
     int dv = 1, dh = -2 * SENT;
     const uint32_t lane4 = (uint32_t)lane * 4u;
-    const uint32_t slot0 = smem_u32(T) + (uint32_t)j0 * 128u + lane4;  // byte address of this line's slot 0
+    const uint32_t slot0 = smem_u32(T) + (uint32_t)(j0 - row0) * 128u + lane4;  // byte address of this line's slot 0
     uint32_t slot = slot0;  // next free slot; entries so far = (slot - slot0) / 128
-    uint32_t rowa = smem_u32(T) + (uint32_t)j0 * 128u;  // row q of the tile
+    uint32_t rowa = smem_u32(T) + (uint32_t)(j0 - row0) * 128u;  // row q of the tile
     uint32_t u4 = 0;                                     // 4 * (q & 31): rotation of row q (FROMBITS)
     const int qend = min(n, j0 + M);
     const int n2m2 = 2 * (n - 1);
@@ -370,186 +629,39 @@ __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TilePar
   }
 
   // ---- phase 2: join adjacent hulls pairwise ---------------------------------------------
+  const HullLocal loc = { LOl, HIl, Tl, row0 };
   for (int s = 1; s < nb; s <<= 1) {
     __syncthreads();
-    if ((band & (2 * s - 1)) == 0 && band + s < nb) {
-      const int gl0 = band, gl1 = band + s, gr0 = band + s, gr1 = min(band + 2 * s, nb);
-      int bl = gl1 - 1;
-      while (bl >= gl0 && LOl[bl * 32] == HIl[bl * 32]) --bl;
-      int br = gr0;
-      while (br < gr1 && LOl[br * 32] == HIl[br * 32]) ++br;
-      if (bl >= gl0 && br < gr1) {
-        int il = HIl[bl * 32] - 1, jr = LOl[br * 32];
-        uint32_t e = Tl[il * 32];
-        int vi = unpack_v(e), hi_ = unpack_h(e);
-        e = Tl[jr * 32];
-        int vj = unpack_v(e), hj = unpack_h(e);
-        // predecessor of the left end / successor of the right end inside their groups
-        int pb = bl, pi = il - 1, vp = 0, hp = 0;
-        bool hasp;
-        int nbd = br, ni = jr + 1, vn = 0, hn = 0;
-        bool hasn;
-        auto find_prev = [&]() {
-          if (pi < (int)LOl[pb * 32]) {
-            --pb;
-            while (pb >= gl0 && LOl[pb * 32] == HIl[pb * 32]) --pb;
-            if (pb >= gl0) pi = HIl[pb * 32] - 1;
-          }
-          hasp = pb >= gl0;
-          if (hasp) {
-            const uint32_t ee = Tl[pi * 32];
-            vp = unpack_v(ee);
-            hp = unpack_h(ee);
-          }
-        };
-        auto find_next = [&]() {
-          if (ni >= (int)HIl[nbd * 32]) {
-            ++nbd;
-            while (nbd < gr1 && LOl[nbd * 32] == HIl[nbd * 32]) ++nbd;
-            if (nbd < gr1) ni = LOl[nbd * 32];
-          }
-          hasn = nbd < gr1;
-          if (hasn) {
-            const uint32_t ee = Tl[ni * 32];
-            vn = unpack_v(ee);
-            hn = unpack_h(ee);
-          }
-        };
-        find_prev();
-        find_next();
-        while (true) {
-          const long long A = (long long)(hj - hi_);
-          const long long dji = (long long)(vj - vi);
-          if (hasp && A * (long long)(vi - vp) <= (long long)(hi_ - hp) * dji) {
-            // the left end never gets below the right hull inside its own region: drop it
-            il = pi;
-            bl = pb;
-            vi = vp;
-            hi_ = hp;
-            pi = il - 1;
-            find_prev();
-            continue;
-          }
-          if (hasn && A * (long long)(vn - vj) >= (long long)(hn - hj) * dji) {
-            jr = ni;
-            br = nbd;
-            vj = vn;
-            hj = hn;
-            ni = jr + 1;
-            find_next();
-            continue;
-          }
-          break;
-        }
-        for (int b2 = bl + 1; b2 < gl1; ++b2) HIl[b2 * 32] = LOl[b2 * 32];
-        HIl[bl * 32] = (uint16_t)(il + 1);
-        for (int b2 = gr0; b2 < br; ++b2) LOl[b2 * 32] = HIl[b2 * 32];
-        LOl[br * 32] = (uint16_t)jr;
-      }
-    }
+    if ((band & (2 * s - 1)) == 0 && band + s < nb) join_hulls(loc, band, band + s, loc, band + s, min(band + 2 * s, nb));
   }
-  __syncthreads();
+  if (CL) {
+    // the two halves of the line: CTA 0 walks its own hull from the top and CTA 1's from the bottom over DSMEM
+    cluster_sync_all();
+    if (rank == 0 && band == 0) {
+      const HullRemote rem = { mapa_u32(smem_u32(LOl), 1u), mapa_u32(smem_u32(HIl), 1u), mapa_u32(smem_u32(Tl), 1u), rpc };
+      join_hulls(loc, 0, nb, rem, 0, nb);
+    }
+    cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
 
   // ---- phase 3: every thread evaluates its own 32 samples on the joint hull -----------------
-  if (j0 >= n) return;
-  if (FINAL && bx * 32 + lane >= p.lanes_total) return;  // padding lane of the last z word: nothing to store
-  const int qend = min(n, j0 + M);
-  const int64_t obase = p.out_base + (int64_t)o * p.out_o + (int64_t)bx * p.out_bx + lane + (int64_t)j0 * p.out_q;
-  // sample j0+u goes to op + u*ostride bytes (the stride fits 32 bits: one IMAD.WIDE per store)
-  char* const op = reinterpret_cast<char*>(p.out) + obase * 4;
-  const unsigned ostride = (unsigned)p.out_q * 4u;
-  int cb = band;
-  while (cb >= 0 && LOl[cb * 32] == HIl[cb * 32]) --cb;
-  bool empty = false;
-  if (cb < 0) {
-    cb = band + 1;
-    while (cb < nb && LOl[cb * 32] == HIl[cb * 32]) ++cb;
-    empty = cb >= nb;
-  } else {
-    // go back while the first entry of band cb has not yet taken over from its predecessor at j0
-    while (true) {
-      int pb = cb - 1;
-      while (pb >= 0 && LOl[pb * 32] == HIl[pb * 32]) --pb;
-      if (pb < 0) break;
-      const uint32_t e1 = Tl[(int)LOl[cb * 32] * 32], e0 = Tl[((int)HIl[pb * 32] - 1) * 32];
-      if (unpack_h(e1) - unpack_h(e0) < 2 * j0 * (unpack_v(e1) - unpack_v(e0))) break;
-      cb = pb;
+  if (j0 < n && !(FINAL && bx * 32 + lane >= p.lanes_total)) {  // (padding lane of the last z word: nothing to store)
+    const int qend = min(n, j0 + M);
+    const int64_t obase = p.out_base + (int64_t)o * p.out_o + (int64_t)bx * p.out_bx + lane + (int64_t)j0 * p.out_q;
+    // sample j0+u goes to op + u*ostride bytes (the stride fits 32 bits: one IMAD.WIDE per store)
+    char* const op = reinterpret_cast<char*>(p.out) + obase * 4;
+    const unsigned ostride = (unsigned)p.out_q * 4u;
+    if (CL) {
+      const HullCluster hull = { smem_u32(LOl), smem_u32(HIl), smem_u32(Tl), nb, rpc };
+      evaluate_band<FINAL, LOGM>(hull, gband, 2 * nb, j0, qend, op, ostride, p.res);
+    } else {
+      evaluate_band<FINAL, LOGM>(loc, gband, nb, j0, qend, op, ostride, p.res);
     }
   }
-  if (empty) {
-    for (int u = 0; u < qend - j0; ++u) {
-      char* const a = op + (uint64_t)(unsigned)u * ostride;
-      if (FINAL)
-        *reinterpret_cast<float*>(a) = __int_as_float(0x7f800000);
-      else
-        *reinterpret_cast<int32_t*>(a) = INF_I;
-    }
-    return;
-  }
-  // cur = (vc,hc); np -> the entry after it, nend = end of np's band; (dvn,dhn) = next - cur, or (0,1) when
-  // the hull is exhausted (the takeover test 2q*dvn > dhn can then never fire)
-  const uint32_t Tla = smem_u32(Tl);  // shared-window address of this line's column
-  uint32_t np = Tla + (uint32_t)LOl[cb * 32] * 128u;
-  uint32_t nend = Tla + (uint32_t)HIl[cb * 32] * 128u;
-  int vc, hc, dvn, dhn;
-  {
-    const uint32_t e = lds32(np);
-    vc = unpack_v(e);
-    hc = unpack_h(e);
-  }
-  // advance np to the following live entry; false when there is none
-  auto step_next = [&]() -> bool {
-    np += 128u;
-    if (np == nend) {
-      int c2 = (int)(((nend - Tla) >> 7) - 1) >> LOGM;  // band of the entry just left
-      ++c2;
-      while (c2 < nb && LOl[c2 * 32] == HIl[c2 * 32]) ++c2;
-      if (c2 >= nb) return false;
-      np = Tla + (uint32_t)LOl[c2 * 32] * 128u;
-      nend = Tla + (uint32_t)HIl[c2 * 32] * 128u;
-    }
-    return true;
-  };
-  if (step_next()) {
-    const uint32_t e = lds32(np);
-    dvn = unpack_v(e) - vc;
-    dhn = unpack_h(e) - hc;
-  } else {
-    dvn = 0;
-    dhn = 1;
-  }
-  const int cnt = qend - j0;
-  // val(q) = (q-vc)^2 + f(vc) = hc + q(q - 2vc) is carried incrementally: val(q+1) = val(q) + inc, inc += 2
-  int val = hc + j0 * (j0 - 2 * vc), inc = 2 * (j0 - vc) + 1;
-  char* oa = op;
-#pragma unroll 2
-  for (int u = 0; u < cnt; ++u) {
-    const int q = j0 + u;
-    // the next parabola takes over at the first integer q with (hn-hc) < 2q(vn-vc)
-    if (2 * q * dvn > dhn) {
-      do {
-        vc += dvn;
-        hc += dhn;
-        if (!step_next()) {
-          dvn = 0;
-          dhn = 1;
-          break;
-        }
-        const uint32_t e = lds32(np);
-        dvn = unpack_v(e) - vc;
-        dhn = unpack_h(e) - hc;
-      } while (2 * q * dvn > dhn);
-      val = hc + q * (q - 2 * vc);
-      inc = 2 * (q - vc) + 1;
-    }
-    if (FINAL)
-      *reinterpret_cast<float*>(oa) = p.res * fast_sqrt((float)val);
-    else
-      *reinterpret_cast<int32_t*>(oa) = val;
-    oa += ostride;
-    val += inc;
-    inc += 2;
-  }
+  // a CTA's shared memory must outlive the other CTA's walks through it
+  if (CL) cluster_sync_all();
 }
 
 size_t tile_smem_bytes(int nb, int m, bool frombits) {
@@ -559,43 +671,69 @@ size_t tile_smem_bytes(int nb, int m, bool frombits) {
 }
 
 int g_band_log2 = -1;  // FUELGPU_ESDF_BAND=64 selects 64-sample bands (default 32)
+bool g_use_cluster = true;  // FUELGPU_ESDF_CLUSTER=0: long lines as one 1024-thread CTA per tile (the older form)
 
 template <bool FROMBITS, bool FINAL>
 cudaError_t launch_tile(cudaStream_t st, TileParams p, int gx, int gy) {
   if (g_band_log2 < 0) {
     const char* e = getenv("FUELGPU_ESDF_BAND");
     g_band_log2 = (e && atoi(e) == 64) ? 6 : 5;  // 32 measured faster (more warps per tile: 0.66 vs 0.68 ms at 512^3)
+    const char* c = getenv("FUELGPU_ESDF_CLUSTER");
+    g_use_cluster = !(c && atoi(c) == 0);
   }
   // bands of 64 samples halve the per-thread fixed work (hull joins, start search) but also the warps per tile
   const int logm = (p.n > 128 && g_band_log2 == 6 && (FROMBITS || p.piece_rows % 64 == 0)) ? 6 : 5;
   const int m = 1 << logm;
   const int nb = (p.n + m - 1) / m;
-  p.nb = nb;
-  const size_t smem = tile_smem_bytes(nb, m, FROMBITS);
-  dim3 grid((unsigned)gx, (unsigned)gy);
-#define FUEL_TILE_LAUNCH(LOGM, MAXT, MINB)                                                                 \
+  // lines longer than 512 samples: the tile is split over the two CTAs of a cluster (64 KB each, 3 CTAs per SM)
+  // instead of one 128 KB CTA that owns the SM alone
+  const bool cl = logm == 5 && nb > 16 && g_use_cluster && (FROMBITS || p.piece_rows % 32 == 0);
+  p.nb = cl ? (nb + 1) / 2 : nb;
+  const size_t smem = tile_smem_bytes(p.nb, m, FROMBITS);
+  dim3 grid((unsigned)(cl ? 2 * gx : gx), (unsigned)gy);
+#define FUEL_TILE_LAUNCH(LOGM, MAXT, MINB, CLUSTER)                                                        \
   do {                                                                                                     \
-    auto kfn = envelope_tile_kernel<FROMBITS, FINAL, LOGM, MAXT, MINB>;                                    \
+    auto kfn = envelope_tile_kernel<FROMBITS, FINAL, LOGM, MAXT, MINB, CLUSTER>;                           \
     static bool attr_done = false;                                                                         \
     if (!attr_done) {                                                                                      \
       cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  \
       if (e != cudaSuccess) return e;                                                                      \
       attr_done = true;                                                                                    \
     }                                                                                                      \
-    kfn<<<grid, nb * 32, smem, st>>>(p);                                                                   \
+    if (CLUSTER) {                                                                                         \
+      cudaLaunchConfig_t cfg;                                                                              \
+      memset(&cfg, 0, sizeof(cfg));                                                                        \
+      cfg.gridDim = grid;                                                                                  \
+      cfg.blockDim = dim3((unsigned)p.nb * 32);                                                            \
+      cfg.dynamicSmemBytes = smem;                                                                         \
+      cfg.stream = st;                                                                                     \
+      cudaLaunchAttribute at[1];                                                                           \
+      at[0].id = cudaLaunchAttributeClusterDimension;                                                      \
+      at[0].val.clusterDim.x = 2;                                                                          \
+      at[0].val.clusterDim.y = 1;                                                                          \
+      at[0].val.clusterDim.z = 1;                                                                          \
+      cfg.attrs = at;                                                                                      \
+      cfg.numAttrs = 1;                                                                                    \
+      cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, p);                                                    \
+      if (e != cudaSuccess) return e;                                                                      \
+    } else {                                                                                               \
+      kfn<<<grid, p.nb * 32, smem, st>>>(p);                                                               \
+    }                                                                                                      \
   } while (0)
-  if (logm == 5) {
+  if (cl) {
+    FUEL_TILE_LAUNCH(5, 512, 3, true);
+  } else if (logm == 5) {
     if (nb <= 8)
-      FUEL_TILE_LAUNCH(5, 256, 6);
+      FUEL_TILE_LAUNCH(5, 256, 6, false);
     else if (nb <= 16)
-      FUEL_TILE_LAUNCH(5, 512, 3);
+      FUEL_TILE_LAUNCH(5, 512, 3, false);
     else
-      FUEL_TILE_LAUNCH(5, 1024, 1);
+      FUEL_TILE_LAUNCH(5, 1024, 1, false);
   } else {
     if (nb <= 8)
-      FUEL_TILE_LAUNCH(6, 256, 3);
+      FUEL_TILE_LAUNCH(6, 256, 3, false);
     else
-      FUEL_TILE_LAUNCH(6, 512, 1);
+      FUEL_TILE_LAUNCH(6, 512, 1, false);
   }
 #undef FUEL_TILE_LAUNCH
   return cudaGetLastError();

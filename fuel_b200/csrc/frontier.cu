@@ -289,6 +289,162 @@ __global__ void __launch_bounds__(CLS_BLOCK) compact_kernel(Geom g, FParams fp,
   }
 }
 
+// ---- 1b. the same sweep, 32 voxels per thread (maps with nz % 32 == 0) -----------------------------------
+// One thread per map-aligned 32-voxel z word of a domain row (x, y): the word and its four x/y neighbour words come
+// in as 16-byte loads (10 + 2 for frontier_flag_), the predicates are byte-parallel bit operations, the z neighbours
+// are shifts of the word's own UNKNOWN mask plus the two bytes beyond its ends.  Word index = row * NW + w, so the
+// cells still come out in ascending address.  HBM sees the occupancy byte and the flag byte once: 2 B/voxel.
+constexpr int WORD_BLOCK = 256;
+
+struct WordGeom {
+  int NW;   // words per row
+  int wz0;  // first map word (z >> 5) of the domain
+  int64_t nwords;
+};
+
+__device__ __forceinline__ uint32_t bits4(uint32_t t) { return ((t & 0x01010101u) * 0x01020408u) >> 24; }
+// bit i <-> voxel i of the 32 bytes (v0 = bytes 0..15, v1 = bytes 16..31)
+__device__ __forceinline__ uint32_t unknown_mask32(const uint4& v0, const uint4& v1) {
+  auto u = [](uint32_t w) { return bits4(~(w | (w >> 1))); };  // (b & 3) == 0
+  return u(v0.x) | (u(v0.y) << 4) | (u(v0.z) << 8) | (u(v0.w) << 12) | (u(v1.x) << 16) | (u(v1.y) << 20) |
+         (u(v1.z) << 24) | (u(v1.w) << 28);
+}
+__device__ __forceinline__ uint32_t free_mask32(const uint4& v0, const uint4& v1) {
+  auto u = [](uint32_t w) { return bits4(w & ~(w >> 1)); };  // (b & 3) == 1
+  return u(v0.x) | (u(v0.y) << 4) | (u(v0.z) << 8) | (u(v0.w) << 12) | (u(v1.x) << 16) | (u(v1.y) << 20) |
+         (u(v1.z) << 24) | (u(v1.w) << 28);
+}
+__device__ __forceinline__ uint32_t zero_mask32(const uint4& v0, const uint4& v1) {
+  // byte == 0: bit 7 of ((b & 0x7f) + 0x7f) | b is clear
+  auto u = [](uint32_t w) { return bits4(~((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) >> 7)); };
+  return u(v0.x) | (u(v0.y) << 4) | (u(v0.z) << 8) | (u(v0.w) << 12) | (u(v1.x) << 16) | (u(v1.y) << 20) |
+         (u(v1.z) << 24) | (u(v1.w) << 28);
+}
+// bits of the word starting at zb whose z lies in [lo, hi] (inclusive)
+__device__ __forceinline__ uint32_t zrange_mask(int zb, int lo, int hi) {
+  const int a = max(lo - zb, 0), b = min(hi - zb, 31);
+  if (a > b) return 0u;
+  return (0xffffffffu >> (31 - b)) & (0xffffffffu << a);
+}
+
+__device__ __forceinline__ void word_coords(const FParams& fp, const WordGeom& wg, int64_t W, int& x, int& y, int& zb) {
+  const unsigned row = (unsigned)(W / wg.NW);
+  const int w = (int)(W - (int64_t)row * wg.NW);
+  const unsigned xr = row / (unsigned)fp.dom_n[1];
+  y = fp.dom_lo[1] + (int)(row - xr * (unsigned)fp.dom_n[1]);
+  x = fp.dom_lo[0] + (int)xr;
+  zb = (wg.wz0 + w) << 5;
+}
+
+__global__ void __launch_bounds__(WORD_BLOCK) classify_words_kernel(Geom g, FParams fp, WordGeom wg,
+                                                                    const uint8_t* __restrict__ occ,
+                                                                    const int8_t* __restrict__ flag,
+                                                                    uint32_t* __restrict__ maskE,
+                                                                    uint32_t* __restrict__ maskS,
+                                                                    int* __restrict__ blockcnt) {
+  const int64_t W = (int64_t)blockIdx.x * WORD_BLOCK + threadIdx.x;
+  uint32_t mE = 0, mS = 0;
+  if (W < wg.nwords) {
+    int x, y, zb;
+    word_coords(fp, wg, W, x, y, zb);
+    const int64_t a0 = addr_of(g, x, y, zb);
+    const uint4* c = reinterpret_cast<const uint4*>(occ + a0);
+    const uint4 c0 = __ldg(c), c1 = __ldg(c + 1);
+    const uint32_t fr = free_mask32(c0, c1);
+    const uint32_t dz = zrange_mask(zb, fp.dom_lo[2], fp.dom_lo[2] + fp.dom_n[2] - 1);
+    if (fr & dz) {
+      const uint32_t uc = unknown_mask32(c0, c1);
+      uint32_t un = (uc << 1) | (uc >> 1);
+      if (zb > 0 && (__ldg(occ + a0 - 1) & 3) == FUELGPU_UNKNOWN) un |= 1u;
+      if (zb + 32 < g.nz && (__ldg(occ + a0 + 32) & 3) == FUELGPU_UNKNOWN) un |= 0x80000000u;
+      const int64_t sx = (int64_t)g.ny * g.nz;
+      if (x > 0) {
+        const uint4* q = reinterpret_cast<const uint4*>(occ + a0 - sx);
+        un |= unknown_mask32(__ldg(q), __ldg(q + 1));
+      }
+      if (x + 1 < g.nx) {
+        const uint4* q = reinterpret_cast<const uint4*>(occ + a0 + sx);
+        un |= unknown_mask32(__ldg(q), __ldg(q + 1));
+      }
+      if (y > 0) {
+        const uint4* q = reinterpret_cast<const uint4*>(occ + a0 - g.nz);
+        un |= unknown_mask32(__ldg(q), __ldg(q + 1));
+      }
+      if (y + 1 < g.ny) {
+        const uint4* q = reinterpret_cast<const uint4*>(occ + a0 + g.nz);
+        un |= unknown_mask32(__ldg(q), __ldg(q + 1));
+      }
+      uint32_t P = fr & un & dz;
+      if (P) {
+        const uint4* fq = reinterpret_cast<const uint4*>(flag + a0);
+        P &= zero_mask32(__ldg(fq), __ldg(fq + 1));
+      }
+      if (P) {
+        const bool inbox = x >= g.box_min[0] && x < g.box_max[0] && y >= g.box_min[1] && y < g.box_max[1];
+        const bool ins = x >= fp.s_lo[0] && x <= fp.s_hi[0] && y >= fp.s_lo[1] && y <= fp.s_hi[1];
+        if (inbox) mE = P & zrange_mask(zb, max(g.box_min[2], fp.z_min_idx), g.box_max[2] - 1);
+        if (ins) mS = P & zrange_mask(zb, fp.s_lo[2], fp.s_hi[2]) & ~mE;
+      }
+    }
+    maskE[W] = mE;
+    maskS[W] = mS;
+  }
+  __shared__ int wsum[WORD_BLOCK / 32];
+  int v = __popc(mE) + __popc(mS);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < WORD_BLOCK / 32; ++i) t += wsum[i];
+    blockcnt[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(WORD_BLOCK) compact_words_kernel(Geom g, FParams fp, WordGeom wg,
+                                                                   const uint32_t* __restrict__ maskE,
+                                                                   const uint32_t* __restrict__ maskS,
+                                                                   const int* __restrict__ blockoff,
+                                                                   int* __restrict__ cell_addr,
+                                                                   uint8_t* __restrict__ cell_cls,
+                                                                   int* __restrict__ cellidx, int cap) {
+  const int64_t W = (int64_t)blockIdx.x * WORD_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t mE = 0, mS = 0;
+  if (W < wg.nwords) {
+    mE = maskE[W];
+    mS = maskS[W];
+  }
+  uint32_t m = mE | mS;
+  const int cnt = __popc(m);
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  __shared__ int wsum[WORD_BLOCK / 32];
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (!m) return;
+  int idx = blockoff[blockIdx.x] + inc - cnt;
+  for (int i = 0; i < w; ++i) idx += wsum[i];
+  int x, y, zb;
+  word_coords(fp, wg, W, x, y, zb);
+  const int a0 = (int)addr_of(g, x, y, zb);
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    if (idx >= cap) return;  // small-path capacity exceeded: the caller falls back and recompacts
+    cell_addr[idx] = a0 + b;
+    cell_cls[idx] = ((mE >> b) & 1u) ? 1 : 2;  // 1 = E, 2 = S
+    if (cellidx) cellidx[a0 + b] = idx;
+    ++idx;
+  }
+}
+
 // ---- 2. union-find over E cells, 26-connectivity -----------------------------------------
 // find with path halving.  The plain stores race benignly with the atomicMin hooks: a parent
 // entry is only ever replaced by another member of the same set with a smaller index, so the
@@ -871,10 +1027,6 @@ __device__ void split_alloc(ClusterMeta* meta, const ClusterStat* __restrict__ s
   }
   if (threadIdx.x == 0) *n_new = carry;
 }
-__global__ void __launch_bounds__(1024) split_alloc_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st,
-                                                           int C, int* __restrict__ n_new) {
-  split_alloc(meta, st, C, n_new);
-}
 
 __device__ __forceinline__ void relabel_item(Geom g, const int* __restrict__ k_addr, int* __restrict__ k_cl,
                                const ClusterMeta* __restrict__ meta, int K, int C_old, int _tid) {
@@ -943,52 +1095,95 @@ __global__ void gather_kept_kernel(const int* __restrict__ cell_addr, const int*
   gather_kept_item(cell_addr, seed, is_kept, kept_off, root_rank, k_addr, k_cl, cellidx, n, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void stat_reset_kernel(ClusterStat* st, const ClusterMeta* __restrict__ meta, int C) {
-  stat_reset_item(st, meta, C, blockIdx.x * blockDim.x + threadIdx.x);
+// The split levels run without the host: the counts live in device memory (ctl), every level kernel leaves at once
+// when the previous level made no new cluster (ctl->n_new == 0), so the host enqueues levels blind and looks at the
+// counters once per batch.  The cluster count of level L is read from ccur and written (by the single-CTA
+// split_alloc) to cnext: the two slots alternate, so no kernel of a level races with the update.
+struct LevelCtl {
+  const int* R;    // root clusters (scan total)
+  const int* K;    // kept cells (scan total)
+  int* n_new;      // clusters created by the last level that ran; doubles as the "keep going" flag
+  int* c_final;    // cluster count after the last level that ran
+  int* ccur;       // cluster count at the start of this level
+  int* cnext;      // ... of the next one
+};
+
+__global__ void stat_reset_kernel(ClusterStat* st, const ClusterMeta* __restrict__ meta, LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;
+  stat_reset_item(st, meta, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void stat_accum_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
-                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K) {
-  stat_accum_item(g, k_addr, k_cl, meta, st, K, blockIdx.x * blockDim.x + threadIdx.x);
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;
+  stat_accum_item(g, k_addr, k_cl, meta, st, *ctl.K, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void mean_kernel(Geom g, ClusterMeta* meta, const ClusterStat* __restrict__ st, int C) {
-  mean_item(g, meta, st, C, blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void mean_kernel(Geom g, ClusterMeta* meta, const ClusterStat* __restrict__ st, LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;
+  mean_item(g, meta, st, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void downsample_kernel(Geom g, FParams fp, const int* __restrict__ k_addr,
                                   const int* __restrict__ k_cl, const int* __restrict__ cellidx,
                                   const ClusterMeta* __restrict__ meta, ClusterStat* st,
-                                  float* __restrict__ k_cent, int* __restrict__ k_leaf, int K) {
-  downsample_item(g, fp, k_addr, k_cl, cellidx, meta, st, k_cent, k_leaf, K, blockIdx.x * blockDim.x + threadIdx.x);
+                                  float* __restrict__ k_cent, int* __restrict__ k_leaf, LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;
+  downsample_item(g, fp, k_addr, k_cl, cellidx, meta, st, k_cent, k_leaf, *ctl.K, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void cov_kernel(const int* __restrict__ k_cl, const int* __restrict__ k_leaf,
                            const float* __restrict__ k_cent, const ClusterMeta* __restrict__ meta,
-                           ClusterStat* st, int K) {
-  cov_item(k_cl, k_leaf, k_cent, meta, st, K, blockIdx.x * blockDim.x + threadIdx.x);
+                           ClusterStat* st, LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;
+  cov_item(k_cl, k_leaf, k_cent, meta, st, *ctl.K, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void pca_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st, int C) {
-  pca_item(meta, st, C, blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void pca_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st, LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;
+  pca_item(meta, st, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void side_count_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
-                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, int K) {
-  side_count_item(g, k_addr, k_cl, meta, st, K, blockIdx.x * blockDim.x + threadIdx.x);
+                                  const ClusterMeta* __restrict__ meta, ClusterStat* st, LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;
+  side_count_item(g, k_addr, k_cl, meta, st, *ctl.K, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+__global__ void __launch_bounds__(1024) split_alloc_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st,
+                                                           LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;  // (uniform: nothing below has written it yet)
+  const int C = *ctl.ccur;
+  __shared__ int made;
+  split_alloc(meta, st, C, &made);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *ctl.cnext = C + made;
+    *ctl.c_final = C + made;
+    *ctl.n_new = made;
+  }
+}
+
+// the cells of the ftr2 halves take their new ids; afterwards the parents' split marks are cleared
 __global__ void relabel_kernel(Geom g, const int* __restrict__ k_addr, int* __restrict__ k_cl,
-                               const ClusterMeta* __restrict__ meta, int K, int C_old) {
-  relabel_item(g, k_addr, k_cl, meta, K, C_old, blockIdx.x * blockDim.x + threadIdx.x);
+                               const ClusterMeta* __restrict__ meta, LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;
+  relabel_item(g, k_addr, k_cl, meta, *ctl.K, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void clear_do_split_kernel(ClusterMeta* meta, int C) {
-  clear_do_split_item(meta, C, blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void clear_do_split_kernel(ClusterMeta* meta, LevelCtl ctl) {
+  if (*ctl.n_new == 0) return;
+  clear_do_split_item(meta, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void init_meta_kernel(ClusterMeta* meta, int R) {
+__global__ void init_meta_kernel(ClusterMeta* meta, LevelCtl ctl) {
+  const int R = *ctl.R;
   init_meta_item(meta, R, blockIdx.x * blockDim.x + threadIdx.x);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *ctl.ccur = R;
+    *ctl.c_final = R;
+    *ctl.n_new = (R > 0 && *ctl.K > 0) ? 1 : 0;
+  }
 }
 
 
@@ -1244,6 +1439,14 @@ struct DevBuf {
 
 }  // namespace
 
+struct SweepPlan {  // how the voxel sweep of a search is laid out
+  bool words = false;  // 32 voxels per thread (nz % 32 == 0) or one voxel per thread
+  unsigned nb = 0;     // CTAs = entries of blockcnt / blockoff
+  size_t nmask = 0;    // mask words
+  int64_t ndom = 0;
+  WordGeom wg;
+};
+
 struct HostView {  // result arrays in pinned host memory
   const int *addr, *cl, *leaf;
   const float* cent;
@@ -1265,8 +1468,7 @@ struct FrontierState {
   // a search that has been enqueued (begin) but not yet collected (end)
   bool pend_active = false, pend_empty = true;
   FParams pend_fp;
-  unsigned pend_nb = 0;
-  int64_t pend_ndom = 0;
+  SweepPlan pend_plan;
   HostView pend_hv;
   cudaStream_t stream = nullptr;  // the frontier subsystem's own stream
   cudaEvent_t ev_in = nullptr;
@@ -1360,6 +1562,54 @@ static int scan_ints(FuelMap* m, const int* in, int* out, int n, int* total) {
   scan_add_kernel<<<nchunk, 1024, 0, s>>>(out, n, f->scan_off.p);
   FUEL_LAUNCHES(m, 3);
   return 0;
+}
+
+static SweepPlan sweep_plan(const Geom& g, const FParams& fp) {
+  SweepPlan pl;
+  pl.ndom = (int64_t)fp.dom_n[0] * fp.dom_n[1] * fp.dom_n[2];
+  pl.words = (g.nz % 32) == 0 && pl.ndom > 0;
+  if (pl.words) {
+    const int z0 = fp.dom_lo[2], z1 = fp.dom_lo[2] + fp.dom_n[2] - 1;
+    pl.wg.wz0 = z0 >> 5;
+    pl.wg.NW = (z1 >> 5) - pl.wg.wz0 + 1;
+    pl.wg.nwords = (int64_t)fp.dom_n[0] * fp.dom_n[1] * pl.wg.NW;
+    pl.nb = nblk(pl.wg.nwords, WORD_BLOCK);
+    pl.nmask = (size_t)pl.nb * WORD_BLOCK;
+  } else {
+    pl.nb = nblk(pl.ndom, CLS_BLOCK);
+    pl.nmask = (size_t)pl.nb * (CLS_BLOCK / 32);
+  }
+  return pl;
+}
+
+// classification sweep + scan of the per-CTA counts; d_counters[0] receives the candidate count
+static int sweep_classify(FuelMap* m, const FParams& fp, const SweepPlan& pl, cudaStream_t s) {
+  FrontierState* f = m->fs;
+  ENSURE(f->maskE, pl.nmask);
+  ENSURE(f->maskS, pl.nmask);
+  ENSURE(f->blockcnt, pl.nb);
+  ENSURE(f->blockoff, pl.nb);
+  if (pl.words)
+    classify_words_kernel<<<pl.nb, WORD_BLOCK, 0, s>>>(m->g, fp, pl.wg, m->occ, m->flag, f->maskE.p, f->maskS.p,
+                                                       f->blockcnt.p);
+  else
+    classify_kernel<<<pl.nb, CLS_BLOCK, 0, s>>>(m->g, fp, m->occ, m->flag, f->maskE.p, f->maskS.p, f->blockcnt.p,
+                                                pl.ndom);
+  FUEL_LAUNCHES(m, 1);
+  if (scan_ints(m, f->blockcnt.p, f->blockoff.p, (int)pl.nb, f->d_counters + 0)) return FUELGPU_ENOMEM;
+  return 0;
+}
+
+// masks + scanned offsets -> address-ordered cell list (at most `cap` cells are written)
+static void sweep_compact(FuelMap* m, const FParams& fp, const SweepPlan& pl, int* cellidx, int cap, cudaStream_t s) {
+  FrontierState* f = m->fs;
+  if (pl.words)
+    compact_words_kernel<<<pl.nb, WORD_BLOCK, 0, s>>>(m->g, fp, pl.wg, f->maskE.p, f->maskS.p, f->blockoff.p,
+                                                      f->cell_addr.p, f->cell_cls.p, cellidx, cap);
+  else
+    compact_kernel<<<pl.nb, CLS_BLOCK, 0, s>>>(m->g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p,
+                                               f->cell_cls.p, cellidx, pl.ndom, cap);
+  FUEL_LAUNCHES(m, 1);
 }
 
 static size_t view_bytes(int K, int C) {
@@ -1698,19 +1948,13 @@ int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double um
   f->pend_active = false;
   f->pend_empty = true;
 
-  const int64_t ndom = (int64_t)fp.dom_n[0] * fp.dom_n[1] * fp.dom_n[2];
-  if (ndom <= 0) return 0;
+  const SweepPlan pl = sweep_plan(g, fp);
+  if (pl.ndom <= 0) return 0;
   f->pend_empty = false;
-  const unsigned nb = nblk(ndom, CLS_BLOCK);
-  const size_t nwords = (size_t)nb * (CLS_BLOCK / 32);
-  ENSURE(f->maskE, nwords);
-  ENSURE(f->maskS, nwords);
-  ENSURE(f->blockcnt, nb);
-  ENSURE(f->blockoff, nb);
-
-  classify_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, m->occ, m->flag, f->maskE.p, f->maskS.p, f->blockcnt.p, ndom);
-  FUEL_LAUNCHES(m, 1);
-  if (scan_ints(m, f->blockcnt.p, f->blockoff.p, (int)nb, f->d_counters + 0)) return FUELGPU_ENOMEM;
+  {
+    const int rc = sweep_classify(m, fp, pl, s);
+    if (rc) return rc;
+  }
   // ---- small path: one compaction + ONE single-CTA launch, one host sync ------------------------
   {
     ENSURE(f->cell_addr, SMALL_CAP); ENSURE(f->cell_cls, SMALL_CAP); ENSURE(f->parent, SMALL_CAP);
@@ -1719,8 +1963,7 @@ int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double um
     ENSURE(f->kept_off, SMALL_CAP); ENSURE(f->k_addr, SMALL_CAP); ENSURE(f->k_cl, SMALL_CAP);
     ENSURE(f->k_leaf, SMALL_CAP); ENSURE(f->k_cent, (size_t)3 * SMALL_CAP);
     ENSURE(f->meta, SMALL_CCAP); ENSURE(f->stat, SMALL_CCAP);
-    compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p,
-                                            f->cell_cls.p, f->cellidx, ndom, SMALL_CAP);
+    sweep_compact(m, fp, pl, f->cellidx, SMALL_CAP, s);
     SmallBufs sb;
     sb.cell_addr = f->cell_addr.p; sb.parent = f->parent.p; sb.claim = f->claim.p; sb.csize = f->csize.p;
     sb.seed = f->seed.p; sb.is_root = f->is_root.p; sb.is_kept = f->is_kept.p; sb.root_rank = f->root_rank.p;
@@ -1728,7 +1971,7 @@ int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double um
     sb.k_leaf = f->k_leaf.p; sb.k_cent = f->k_cent.p; sb.meta = f->meta.p; sb.stat = f->stat.p;
     sb.counters = f->d_counters;
     cluster_small_kernel<<<SMALL_CTAS, 1024, 0, s>>>(g, fp, m->flag, f->cellidx, sb);
-    FUEL_LAUNCHES(m, 2);
+    FUEL_LAUNCHES(m, 1);
     // one host sync in the common case: the counters and a speculative prefix of the results
     // (K0 cells, C0 clusters) are downloaded together; a second stage only if they did not fit
     constexpr int K0 = 12288, C0 = 256;
@@ -1740,8 +1983,7 @@ int frontier_search_begin_impl(FuelMap* m, const double umin[3], const double um
     rc0 = enqueue_download(m, K0, C0, f->h_pin + 64, &hv);
     if (rc0) return rc0;
     f->pend_fp = fp;
-    f->pend_nb = nb;
-    f->pend_ndom = ndom;
+    f->pend_plan = pl;
     f->pend_active = true;
   }
   // classify / union / claim kernels read `occ` on the frontier stream: a later writer of `occ` on the main
@@ -1762,8 +2004,7 @@ int frontier_search_end_impl(FuelMap* m, int32_t* n_clusters, int32_t* n_cells, 
   }
   f->pend_active = false;
   const FParams fp = f->pend_fp;
-  const unsigned nb = f->pend_nb;
-  const int64_t ndom = f->pend_ndom;
+  const SweepPlan pl = f->pend_plan;
   int n_cand = 0;
   {
     constexpr int K0 = 12288, C0 = 256;
@@ -1792,14 +2033,14 @@ int frontier_search_end_impl(FuelMap* m, int32_t* n_clusters, int32_t* n_cells, 
   ENSURE(f->is_root, n_cand); ENSURE(f->is_kept, n_cand); ENSURE(f->root_rank, n_cand);
   ENSURE(f->kept_off, n_cand);
 
-  compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p,
-                                          f->cell_cls.p, f->cellidx, ndom, n_cand);
-  FUEL_LAUNCHES(m, 1);
+  sweep_compact(m, fp, pl, f->cellidx, n_cand, s);
   return frontier_cluster_large(m, fp, n_cand, n_clusters, n_cells, n_filtered);
 }
 
 // the multi-kernel clustering + split over n_cand compacted candidate cells (cell_addr / cell_cls ascending by
-// address, cellidx[addr] = index already set): union-find, claims, flags, kept-cell gather, split levels, marshal
+// address, cellidx[addr] = index already set): union-find, claims, flags, kept-cell gather, split levels, marshal.
+// Nothing here waits for the device until the split levels are enqueued: the root / kept-cell / cluster counts
+// stay in device memory (LevelCtl), arrays are sized by their bound n_cand.
 static int frontier_cluster_large(FuelMap* m, const FParams& fp, int n_cand, int32_t* n_clusters, int32_t* n_cells,
                                   int32_t* n_filtered) {
   FrontierState* f = m->fs;
@@ -1809,81 +2050,69 @@ static int frontier_cluster_large(FuelMap* m, const FParams& fp, int n_cand, int
   ENSURE(f->claim, n_cand); ENSURE(f->csize, n_cand); ENSURE(f->seed, n_cand);
   ENSURE(f->is_root, n_cand); ENSURE(f->is_kept, n_cand); ENSURE(f->root_rank, n_cand);
   ENSURE(f->kept_off, n_cand);
+  // kept cells K <= n_cand; every cluster holds at least one kept cell, so the cluster count never exceeds K
+  ENSURE(f->k_addr, n_cand); ENSURE(f->k_cl, n_cand); ENSURE(f->k_leaf, n_cand); ENSURE(f->k_cent, (size_t)3 * n_cand);
+  ENSURE(f->meta, (size_t)n_cand + 1024);
+  ENSURE(f->stat, (size_t)n_cand + 1024);
   const unsigned cb = nblk(n_cand, 256);
   init_parent_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->claim.p, f->csize.p, n_cand);
-  FUEL_LAUNCHES(m, 1);
   union_kernel<<<cb, 256, 0, s>>>(g, f->cell_addr.p, f->cell_cls.p, f->cellidx, f->parent.p, n_cand);
-  FUEL_LAUNCHES(m, 1);
   flatten_kernel<<<cb, 256, 0, s>>>(f->parent.p, f->cell_cls.p, n_cand);
-  FUEL_LAUNCHES(m, 1);
   claim_kernel<<<cb, 256, 0, s>>>(g, fp, f->cell_addr.p, f->cell_cls.p, f->cellidx, f->parent.p, f->claim.p, n_cand);
-  FUEL_LAUNCHES(m, 1);
   assign_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cell_cls.p, f->parent.p, f->claim.p, f->seed.p,
                                    f->csize.p, m->flag, n_cand);
-  FUEL_LAUNCHES(m, 1);
   mark_kernel<<<cb, 256, 0, s>>>(f->seed.p, f->csize.p, fp.cluster_min, f->is_root.p, f->is_kept.p, n_cand);
-  FUEL_LAUNCHES(m, 1);
+  FUEL_LAUNCHES(m, 6);
   if (scan_ints(m, f->is_root.p, f->root_rank.p, n_cand, f->d_counters + 1)) return FUELGPU_ENOMEM;
   if (scan_ints(m, f->is_kept.p, f->kept_off.p, n_cand, f->d_counters + 2)) return FUELGPU_ENOMEM;
-  int cnt[3];
-  FUEL_CUDA(m, cudaMemcpyAsync(cnt, f->d_counters, sizeof(int) * 3, cudaMemcpyDeviceToHost, s));
-  FUEL_CUDA(m, cudaStreamSynchronize(s));
-  const int R = cnt[1], K = cnt[2];
-  if (R == 0 || K == 0) {
-    reset_cellidx_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cellidx, n_cand);
-  FUEL_LAUNCHES(m, 1);
-    FUEL_CUDA(m, cudaGetLastError());
-    return 0;
-  }
-  ENSURE(f->k_addr, K); ENSURE(f->k_cl, K); ENSURE(f->k_leaf, K); ENSURE(f->k_cent, (size_t)3 * K);
   gather_kept_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->seed.p, f->is_kept.p, f->kept_off.p,
                                         f->root_rank.p, f->k_addr.p, f->k_cl.p, f->cellidx, n_cand);
   FUEL_LAUNCHES(m, 1);
 
   // ---- split levels -------------------------------------------------------------------
-  // at most one new cluster per kept cell; K bounds the cluster count
-  ENSURE(f->meta, (size_t)2 * R + 1024);
-  ENSURE(f->stat, (size_t)2 * R + 1024);
-  int C = R;
-  init_meta_kernel<<<nblk(R, 256), 256, 0, s>>>(f->meta.p, R);
+  LevelCtl ctl;
+  ctl.R = f->d_counters + 1;
+  ctl.K = f->d_counters + 2;
+  ctl.n_new = f->d_counters + 3;
+  ctl.c_final = f->d_counters + 5;
+  ctl.ccur = f->d_counters + 6;
+  ctl.cnext = f->d_counters + 7;
+  // a root cluster has more than cluster_min cells; every level at most doubles the cluster count
+  const int64_t r_ub = n_cand / ((fp.cluster_min > 0 ? fp.cluster_min : 0) + 1) + 1;
+  init_meta_kernel<<<nblk(r_ub, 256), 256, 0, s>>>(f->meta.p, ctl);
   FUEL_LAUNCHES(m, 1);
-  const unsigned kb = nblk(K, 256);
-  for (int level = 0; level < 40; ++level) {
-    // every active cluster may spawn one new cluster this level
-    if (f->meta.grow_preserve((size_t)2 * C, C, s) || f->stat.grow_preserve((size_t)2 * C, C, s))
-      return fuel_fail(m, FUELGPU_ENOMEM, "frontier: device allocation failed");
-    const unsigned ccb = nblk(C, 256);
-    stat_reset_kernel<<<ccb, 256, 0, s>>>(f->stat.p, f->meta.p, C);
-  FUEL_LAUNCHES(m, 1);
-    stat_accum_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, K);
-  FUEL_LAUNCHES(m, 1);
-    mean_kernel<<<ccb, 256, 0, s>>>(g, f->meta.p, f->stat.p, C);
-  FUEL_LAUNCHES(m, 1);
-    downsample_kernel<<<kb, 256, 0, s>>>(g, fp, f->k_addr.p, f->k_cl.p, f->cellidx, f->meta.p, f->stat.p,
-                                         f->k_cent.p, f->k_leaf.p, K);
-  FUEL_LAUNCHES(m, 1);
-    cov_kernel<<<kb, 256, 0, s>>>(f->k_cl.p, f->k_leaf.p, f->k_cent.p, f->meta.p, f->stat.p, K);
-  FUEL_LAUNCHES(m, 1);
-    pca_kernel<<<ccb, 256, 0, s>>>(f->meta.p, f->stat.p, C);
-  FUEL_LAUNCHES(m, 1);
-    side_count_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, K);
-  FUEL_LAUNCHES(m, 1);
-    split_alloc_kernel<<<1, 1024, 0, s>>>(f->meta.p, f->stat.p, C, f->d_counters + 3);
-  FUEL_LAUNCHES(m, 1);
-    relabel_kernel<<<kb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, K, C);
-  FUEL_LAUNCHES(m, 1);
-    int n_new = 0;
-    FUEL_CUDA(m, cudaMemcpyAsync(&n_new, f->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
-    FUEL_CUDA(m, cudaStreamSynchronize(s));
-    if (n_new == 0) break;
-    clear_do_split_kernel<<<ccb, 256, 0, s>>>(f->meta.p, C);
-  FUEL_LAUNCHES(m, 1);
-    C += n_new;
+  int cnt[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  constexpr int LEVELS_PER_BATCH = 12, MAX_LEVELS = 36;  // (a cluster stops splitting at depth 32: pca_item)
+  for (int level = 0; level < MAX_LEVELS; ++level) {
+    int64_t c_ub = level < 24 ? (r_ub << level) : (int64_t)n_cand;
+    if (c_ub > n_cand) c_ub = n_cand;
+    const unsigned ccb = nblk(c_ub, 256);
+    stat_reset_kernel<<<ccb, 256, 0, s>>>(f->stat.p, f->meta.p, ctl);
+    stat_accum_kernel<<<cb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, ctl);
+    mean_kernel<<<ccb, 256, 0, s>>>(g, f->meta.p, f->stat.p, ctl);
+    downsample_kernel<<<cb, 256, 0, s>>>(g, fp, f->k_addr.p, f->k_cl.p, f->cellidx, f->meta.p, f->stat.p,
+                                         f->k_cent.p, f->k_leaf.p, ctl);
+    cov_kernel<<<cb, 256, 0, s>>>(f->k_cl.p, f->k_leaf.p, f->k_cent.p, f->meta.p, f->stat.p, ctl);
+    pca_kernel<<<ccb, 256, 0, s>>>(f->meta.p, f->stat.p, ctl);
+    side_count_kernel<<<cb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, ctl);
+    split_alloc_kernel<<<1, 1024, 0, s>>>(f->meta.p, f->stat.p, ctl);
+    relabel_kernel<<<cb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, ctl);
+    clear_do_split_kernel<<<ccb, 256, 0, s>>>(f->meta.p, ctl);
+    FUEL_LAUNCHES(m, 10);
+    int* t = ctl.ccur;
+    ctl.ccur = ctl.cnext;
+    ctl.cnext = t;
+    if ((level + 1) % LEVELS_PER_BATCH == 0 || level + 1 == MAX_LEVELS) {
+      FUEL_CUDA(m, cudaMemcpyAsync(cnt, f->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, s));
+      FUEL_CUDA(m, cudaStreamSynchronize(s));
+      if (cnt[3] == 0) break;
+    }
   }
-
   reset_cellidx_kernel<<<cb, 256, 0, s>>>(f->cell_addr.p, f->cellidx, n_cand);
   FUEL_LAUNCHES(m, 1);
   FUEL_CUDA(m, cudaGetLastError());
+  const int R = cnt[1], K = cnt[2], C = cnt[5];
+  if (R == 0 || K == 0) return 0;
   return frontier_marshal(m, K, C, n_clusters, n_cells, n_filtered);
 }
 
@@ -1912,26 +2141,19 @@ int frontier_candidates_impl(FuelMap* m, const double umin[3], const double umax
   if (dz1 < dz0) return 0;
   fp.dom_lo[2] = dz0;
   fp.dom_n[2] = dz1 - dz0 + 1;
-  const int64_t ndom = (int64_t)fp.dom_n[0] * fp.dom_n[1] * fp.dom_n[2];
-  if (ndom <= 0) return 0;
-  const unsigned nb = nblk(ndom, CLS_BLOCK);
-  const size_t nwords = (size_t)nb * (CLS_BLOCK / 32);
-  ENSURE(f->maskE, nwords);
-  ENSURE(f->maskS, nwords);
-  ENSURE(f->blockcnt, nb);
-  ENSURE(f->blockoff, nb);
-  classify_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, m->occ, m->flag, f->maskE.p, f->maskS.p, f->blockcnt.p, ndom);
-  FUEL_LAUNCHES(m, 1);
-  if (scan_ints(m, f->blockcnt.p, f->blockoff.p, (int)nb, f->d_counters + 0)) return FUELGPU_ENOMEM;
+  const SweepPlan pl = sweep_plan(g, fp);
+  if (pl.ndom <= 0) return 0;
+  {
+    const int rc = sweep_classify(m, fp, pl, s);
+    if (rc) return rc;
+  }
   int n = 0;
   FUEL_CUDA(m, cudaMemcpyAsync(&n, f->d_counters, sizeof(int), cudaMemcpyDeviceToHost, s));
   FUEL_CUDA(m, cudaStreamSynchronize(s));
   if (n > 0) {
     ENSURE(f->cell_addr, n);
     ENSURE(f->cell_cls, n);
-    compact_kernel<<<nb, CLS_BLOCK, 0, s>>>(g, fp, f->maskE.p, f->maskS.p, f->blockoff.p, f->cell_addr.p, f->cell_cls.p,
-                                            nullptr, ndom, n);
-    FUEL_LAUNCHES(m, 1);
+    sweep_compact(m, fp, pl, nullptr, n, s);
     FUEL_CUDA(m, cudaGetLastError());
   }
   *n_out = n;

@@ -154,6 +154,29 @@ def test_maximum_axis_extent(fuel, orc, n):
     m.close()
 
 
+@pytest.mark.parametrize("n,p_site", [((700, 40, 33), 0.004), ((37, 1000, 64), 0.002), ((600, 520, 32), 0.0005),
+                                      ((1024, 70, 32), 0.02), ((513, 545, 40), 0.3)])
+def test_long_lines_cluster_tiles(fuel, orc, n, p_site):
+    """Lines of 513..1024 samples: the tile is shared by the two CTAs of a cluster and the hulls of the two halves are
+    joined over distributed shared memory.  Dense and sparse hulls, partial last bands, then a box that starts off the
+    grid origin (box-relative rows)."""
+    g = W.Grid(n, (0.3, -1.0, 0.0), 0.1)
+    inflate, tri = random_scene(n, 1000 + n[0], p_site=p_site, p_unknown=0.2, blobs=5)
+    m = make_sdf_map(fuel, g, inflate, tri, optimistic=True)
+    m.updateESDF3d()
+    got = m.download().copy()
+    ref = orc.update_esdf3d(orc_grid(orc, g), inflate, tri, [0, 0, 0], np.array(n) - 1, True, False, threads=16)
+    compare(got, ref)
+    lo = np.array([3, 2, 1])
+    hi = np.array(n) - np.array([2, 4, 1])
+    m.local_bound_min_, m.local_bound_max_ = lo.copy(), hi.copy()
+    m.updateESDF3d()
+    got2 = m.download().copy()
+    ref2 = orc.update_esdf3d(orc_grid(orc, g), inflate, tri, lo, hi, True, False, dist=ref.copy(), threads=16)
+    compare(got2, ref2)
+    m.close()
+
+
 def test_rejects_bad_arguments(fuel):
     with pytest.raises(fuel.FuelGpuError):
         fuel.SDFMap((1025, 4, 4), 0.1, (0, 0, 0))  # beyond the 1024-per-axis limit

@@ -56,6 +56,11 @@ CASES = [
     ((64, 50, 24), 3, 1, 20, 1.0, (0.3, 0.6), 0.4),
     ((30, 30, 30), 4, 3, 3, 0.6, (0.0, 1.0), -10.0),
     ((72, 64, 20), 5, 2, 10, 1.5, (0.1, 0.5), 0.9),
+    # nz % 32 == 0: the 32-voxels-per-thread sweep (classify_words_kernel / compact_words_kernel)
+    ((40, 36, 32), 6, 2, 5, 2.0, (0.0, 1.0), 0.4),
+    ((33, 29, 64), 7, 1, 3, 0.8, (0.2, 0.7), 0.4),
+    ((24, 20, 96), 8, 3, 0, 0.6, (0.0, 1.0), 3.3),
+    ((50, 41, 64), 9, 1, 8, 1.0, (0.1, 0.9), -10.0),
 ]
 
 
@@ -204,13 +209,41 @@ def test_large_scene_uses_multi_kernel_path(fuel, orc):
     assert np.array_equal(gfl, rfl)
 
 
-@pytest.mark.parametrize("slabs", [2, 3, 5])
-def test_sharded_sweep_equals_whole_search(fuel, orc, slabs):
+@pytest.mark.parametrize("nz", [48, 64])
+def test_large_scene_levels_without_host(fuel, orc, nz):
+    """The multi-kernel path keeps its counts on the device (LevelCtl): many split levels (small cluster_size_xy), both
+    sweep layouts (nz = 64: 32 voxels per thread), and a second search on the flags the first one left."""
+    n = (160, 144, nz)
+    origin = np.array([-3.0, 1.0, -0.4])
+    g0 = W.Grid(n, origin, 0.1)
+    g = W.Grid(n, origin, 0.1, box_min=origin + 0.2, box_max=g0.map_max - 0.2)
+    inflate, tri = random_scene(n, 123 + nz, p_site=0.002, p_unknown=0.5, blobs=80)
+    kw = dict(cluster_min=12, cluster_size_xy=0.45, down_sample=3, min_z=0.4)
+    m = make_sdf_map(fuel, g, inflate, tri)
+    env = fuel.EDTEnvironment()
+    env.setMap(m)
+    ff = fuel.FrontierFinder(env, **kw)
+    ext = g0.map_max - origin
+    u1 = (origin + 0.0 * ext, origin + 0.55 * ext)
+    gpu1 = ff.search_box(*u1)
+    ref1, fl1 = run_orc(orc, g, tri, *u1, cell_order=1, **kw)
+    assert int(fl1.sum()) > 32768, int(fl1.sum())
+    assert_same(gpu1, ref1)
+    assert np.array_equal(ff.download_flags(), fl1)
+    gpu2 = ff.search_box(origin, g0.map_max)
+    ref2, fl2 = run_orc(orc, g, tri, origin, g0.map_max, flags=fl1, cell_order=1, **kw)
+    assert_same(gpu2, ref2)
+    assert np.array_equal(ff.download_flags(), fl2)
+    m.close()
+
+
+@pytest.mark.parametrize("slabs,nz", [(2, 24), (3, 24), (5, 24), (2, 64), (3, 64), (5, 96)])
+def test_sharded_sweep_equals_whole_search(fuel, orc, slabs, nz):
     """SURVEY 8e row 2 on one GPU: the sweep cut into z slabs (fuelgpu_frontier_candidates per slab), the candidate lists
     merged by address, the clustering run on the union (fuelgpu_frontier_search_from_candidates) == the whole search,
     bit for bit: clusters, order, cells, average_, filtered_cells_, frontier_flag_.  Also after a first search left flags."""
     from fuel_b200.dist import merge_candidates
-    n = (64, 50, 24)
+    n = (64, 50, nz)
     origin = np.array([-1.0, -2.0, -0.5])
     g0 = W.Grid(n, origin, 0.1)
     g = W.Grid(n, origin, 0.1, box_min=origin + 0.1, box_max=g0.map_max - 0.1)
