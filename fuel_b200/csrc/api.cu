@@ -612,7 +612,10 @@ int fuelgpu_frontier_candidates(FuelMap* m, const double upd_min[3], const doubl
   if (!m || !upd_min || !upd_max || !p || !n_candidates) return fuel_fail(m, FUELGPU_EINVAL, "null argument");
   if (z_lo < 0 || z_hi >= m->g.nz || z_lo > z_hi) return fuel_fail(m, FUELGPU_EINVAL, "bad z range");
   FUEL_CUDA(m, cudaSetDevice(m->dev));
-  return frontier_candidates_impl(m, upd_min, upd_max, p, z_lo, z_hi, n_candidates);
+  tbegin(m, T_FRONTIER, frontier_stream(m));  // (the sweep alone: fuelgpu_map_last_timing reports it as the frontier stage)
+  const int rc = frontier_candidates_impl(m, upd_min, upd_max, p, z_lo, z_hi, n_candidates);
+  tend(m, T_FRONTIER, frontier_stream_raw(m));
+  return rc;
 }
 
 int fuelgpu_frontier_candidates_fetch(FuelMap* m, int32_t n, int32_t* addr, uint8_t* cls) {

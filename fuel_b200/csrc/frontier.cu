@@ -571,7 +571,13 @@ __device__ __forceinline__ void claim_item(Geom g, FParams fp, const int* __rest
   if (cell_cls[i] == 1) {
     const bool ins = x >= fp.s_lo[0] && x <= fp.s_hi[0] && y >= fp.s_lo[1] && y <= fp.s_hi[1] &&
                      z >= fp.s_lo[2] && z <= fp.s_hi[2];
-    if (ins) atomicMin(&claim[label[i]], i);
+    // neighbouring cells mostly share a component: one atomic per component and warp instead of one per cell
+    const int key = ins ? label[i] : -1;
+    const unsigned grp = __match_any_sync(__activemask(), key);
+    if (key >= 0) {
+      const int mn = __reduce_min_sync(grp, i);
+      if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicMin(&claim[key], mn);
+    }
   } else {
     // the 26 lookups go out together, then the classes, then the labels: three round trips instead of one per neighbour
     int jn[26];
@@ -608,13 +614,18 @@ __device__ __forceinline__ void assign_item(const int* __restrict__ cell_addr, c
                               const int* __restrict__ label, const int* __restrict__ claim,
                               int* __restrict__ seed, int* csize, int8_t* __restrict__ flag, int n, int _tid) {
   const int i = _tid;
-  if (i >= n) return;
-  const int s = cell_cls[i] == 1 ? claim[label[i]] : i;
-  seed[i] = s;
-  if (s != NONE) {
-    atomicAdd(&csize[s], 1);
-    flag[cell_addr[i]] = 1;  // frontier_flag_ set for every absorbed cell (:132,:155)
+  int key = -1;
+  if (i < n) {
+    const int s = cell_cls[i] == 1 ? claim[label[i]] : i;
+    seed[i] = s;
+    if (s != NONE) {
+      key = s;
+      flag[cell_addr[i]] = 1;  // frontier_flag_ set for every absorbed cell (:132,:155)
+    }
   }
+  // cells of a warp mostly share their seed: one size update per seed and warp
+  const unsigned grp = __match_any_sync(__activemask(), key);
+  if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&csize[key], __popc(grp));
 }
 
 // per cell: 1 if it is the seed of a kept cluster (for the rank scan), and kept-cell marks
@@ -830,28 +841,63 @@ __device__ __forceinline__ void downsample_item(Geom g, FParams fp, const int* _
 }
 
 // covariance terms as exact two-part fixed point: p = hi*2^-20 + lo*2^-82
-__device__ __forceinline__ void fx_add(long long* hi, long long* lo, double p) {
-  const double h = rint(p * 1048576.0);             // 2^20
-  const double l = (p - h * (1.0 / 1048576.0));     // exact, |l| <= 2^-21
-  atomicAdd((unsigned long long*)hi, (unsigned long long)(long long)h);
-  atomicAdd((unsigned long long*)lo, (unsigned long long)(long long)rint(l * 4835703278458516698824704.0));  // 2^82
-}
 __device__ __forceinline__ double fx_get(long long hi, long long lo) {
   return (double)hi * (1.0 / 1048576.0) + (double)lo * (1.0 / 4835703278458516698824704.0);
 }
 
-__device__ __forceinline__ void cov_item(const int* __restrict__ k_cl, const int* __restrict__ k_leaf,
+// sum of a 64-bit value over the lanes of grp (mod 2^64, like the atomics it replaces): three 21/21/22-bit limbs
+// go through the 32-bit warp reduction
+__device__ __forceinline__ unsigned long long group_sum_u64(unsigned grp, unsigned long long v) {
+  const unsigned a = (unsigned)(v & 0x1fffffull), b = (unsigned)((v >> 21) & 0x1fffffull), c = (unsigned)(v >> 42);
+  const unsigned long long sa = __reduce_add_sync(grp, a), sb = __reduce_add_sync(grp, b), sc = __reduce_add_sync(grp, c);
+  return sa + (sb << 21) + (sc << 42);
+}
+__device__ __forceinline__ void fx_split(double p, unsigned long long* hi, unsigned long long* lo) {
+  const double h = rint(p * 1048576.0);          // 2^20
+  const double l = (p - h * (1.0 / 1048576.0));  // exact, |l| <= 2^-21
+  *hi = (unsigned long long)(long long)h;
+  *lo = (unsigned long long)(long long)rint(l * 4835703278458516698824704.0);  // 2^82
+}
+
+// The sums are exact integers (two-part fixed point), so the lanes of a warp that share a cluster are added up in the
+// warp first and ONE lane issues the six atomics: same result, a fraction of the atomic traffic on the cluster's record.
+template <bool LOCALMEAN = false>  // true: form the cluster mean from the statistics here (same expression as mean_item)
+__device__ __forceinline__ void cov_item(Geom g, const int* __restrict__ k_cl, const int* __restrict__ k_leaf,
                            const float* __restrict__ k_cent, const ClusterMeta* __restrict__ meta,
                            ClusterStat* st, int K, int _tid) {
   const int k = _tid;
-  if (k >= K) return;
-  const int c = k_cl[k];
-  if (!meta[c].active || k_leaf[k] < 0 || !st[c].need_split) return;
-  const double dx = (double)k_cent[3 * k] - meta[c].mean[0];
-  const double dy = (double)k_cent[3 * k + 1] - meta[c].mean[1];
-  fx_add(&st[c].cxx_hi, &st[c].cxx_lo, dx * dx);
-  fx_add(&st[c].cxy_hi, &st[c].cxy_lo, dx * dy);
-  fx_add(&st[c].cyy_hi, &st[c].cyy_lo, dy * dy);
+  int c = -1;
+  if (k < K) {
+    c = k_cl[k];
+    if (!meta[c].active || k_leaf[k] < 0 || !st[c].need_split) c = -1;
+  }
+  const unsigned grp = __match_any_sync(__activemask(), c);
+  if (c < 0) return;
+  double m0 = meta[c].mean[0], m1 = meta[c].mean[1];
+  if (LOCALMEAN) {
+    const ClusterStat& s = st[c];
+    const double inv = 1.0 / (double)s.n;
+    m0 = ((double)s.sx * inv + 0.5) * g.res + g.origin[0];
+    m1 = ((double)s.sy * inv + 0.5) * g.res + g.origin[1];
+  }
+  const double dx = (double)k_cent[3 * k] - m0;
+  const double dy = (double)k_cent[3 * k + 1] - m1;
+  unsigned long long v[6];
+  fx_split(dx * dx, &v[0], &v[1]);
+  fx_split(dx * dy, &v[2], &v[3]);
+  fx_split(dy * dy, &v[4], &v[5]);
+  if (grp & (grp - 1)) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) v[q] = group_sum_u64(grp, v[q]);
+  }
+  if ((int)(threadIdx.x & 31) != __ffs(grp) - 1) return;
+  ClusterStat* sc = &st[c];
+  atomicAdd((unsigned long long*)&sc->cxx_hi, v[0]);
+  atomicAdd((unsigned long long*)&sc->cxx_lo, v[1]);
+  atomicAdd((unsigned long long*)&sc->cxy_hi, v[2]);
+  atomicAdd((unsigned long long*)&sc->cxy_lo, v[3]);
+  atomicAdd((unsigned long long*)&sc->cyy_hi, v[4]);
+  atomicAdd((unsigned long long*)&sc->cyy_lo, v[5]);
 }
 
 // Eigen 3.3 EigenSolver<Matrix2d> restated for a symmetric matrix: RealSchur (findSmallSubdiagEntry,
@@ -1108,40 +1154,34 @@ struct LevelCtl {
   int* cnext;      // ... of the next one
 };
 
-__global__ void stat_reset_kernel(ClusterStat* st, const ClusterMeta* __restrict__ meta, LevelCtl ctl) {
-  if (*ctl.n_new == 0) return;
-  stat_reset_item(st, meta, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
-}
-
 __global__ void stat_accum_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
                                   const ClusterMeta* __restrict__ meta, ClusterStat* st, LevelCtl ctl) {
   if (*ctl.n_new == 0) return;
   stat_accum_item(g, k_addr, k_cl, meta, st, *ctl.K, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void mean_kernel(Geom g, ClusterMeta* meta, const ClusterStat* __restrict__ st, LevelCtl ctl) {
-  if (*ctl.n_new == 0) return;
-  mean_item(g, meta, st, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
-}
-
+// VoxelGrid pass and covariance form the cluster mean from the statistics themselves (LOCALMEAN: the expression of
+// mean_item); the mean is stored by pca_kernel for the later consumers (side test, relabel, average_)
 __global__ void downsample_kernel(Geom g, FParams fp, const int* __restrict__ k_addr,
                                   const int* __restrict__ k_cl, const int* __restrict__ cellidx,
                                   const ClusterMeta* __restrict__ meta, ClusterStat* st,
                                   float* __restrict__ k_cent, int* __restrict__ k_leaf, LevelCtl ctl) {
   if (*ctl.n_new == 0) return;
-  downsample_item(g, fp, k_addr, k_cl, cellidx, meta, st, k_cent, k_leaf, *ctl.K, blockIdx.x * blockDim.x + threadIdx.x);
+  downsample_item<true>(g, fp, k_addr, k_cl, cellidx, meta, st, k_cent, k_leaf, *ctl.K, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void cov_kernel(const int* __restrict__ k_cl, const int* __restrict__ k_leaf,
+__global__ void cov_kernel(Geom g, const int* __restrict__ k_cl, const int* __restrict__ k_leaf,
                            const float* __restrict__ k_cent, const ClusterMeta* __restrict__ meta,
                            ClusterStat* st, LevelCtl ctl) {
   if (*ctl.n_new == 0) return;
-  cov_item(k_cl, k_leaf, k_cent, meta, st, *ctl.K, blockIdx.x * blockDim.x + threadIdx.x);
+  cov_item<true>(g, k_cl, k_leaf, k_cent, meta, st, *ctl.K, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void pca_kernel(ClusterMeta* meta, const ClusterStat* __restrict__ st, LevelCtl ctl) {
+__global__ void pca_kernel(Geom g, ClusterMeta* meta, const ClusterStat* __restrict__ st, LevelCtl ctl) {
   if (*ctl.n_new == 0) return;
-  pca_item(meta, st, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  mean_item(g, meta, st, *ctl.ccur, c);
+  pca_item(meta, st, *ctl.ccur, c);
 }
 
 __global__ void side_count_kernel(Geom g, const int* __restrict__ k_addr, const int* __restrict__ k_cl,
@@ -1171,15 +1211,21 @@ __global__ void relabel_kernel(Geom g, const int* __restrict__ k_addr, int* __re
   relabel_item(g, k_addr, k_cl, meta, *ctl.K, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void clear_do_split_kernel(ClusterMeta* meta, LevelCtl ctl) {
+// end of a level: the parents' split marks are cleared and the statistics of every cluster that is still active
+// (children included) are reset for the next level
+__global__ void next_level_kernel(ClusterMeta* meta, ClusterStat* st, LevelCtl ctl) {
   if (*ctl.n_new == 0) return;
-  clear_do_split_item(meta, *ctl.ccur, blockIdx.x * blockDim.x + threadIdx.x);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  clear_do_split_item(meta, *ctl.ccur, c);
+  stat_reset_item(st, meta, *ctl.cnext, c);
 }
 
-__global__ void init_meta_kernel(ClusterMeta* meta, LevelCtl ctl) {
+__global__ void init_meta_kernel(ClusterMeta* meta, ClusterStat* st, LevelCtl ctl) {
   const int R = *ctl.R;
-  init_meta_item(meta, R, blockIdx.x * blockDim.x + threadIdx.x);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  init_meta_item(meta, R, c);
+  stat_reset_item(st, meta, R, c);
+  if (c == 0) {
     *ctl.ccur = R;
     *ctl.c_final = R;
     *ctl.n_new = (R > 0 && *ctl.K > 0) ? 1 : 0;
@@ -1346,7 +1392,7 @@ __global__ void __cluster_dims__(SMALL_CTAS, 1, 1) __launch_bounds__(1024) clust
       FOR_ITEMS(k, K) downsample_item<true>(g, fp, b.k_addr, b.k_cl, cellidx, b.meta, b.stat, b.k_cent, b.k_leaf, K, k);
       cluster.sync();
       STAMP();
-      FOR_ITEMS(k, K) cov_item(b.k_cl, b.k_leaf, b.k_cent, b.meta, b.stat, K, k);
+      FOR_ITEMS(k, K) cov_item(g, b.k_cl, b.k_leaf, b.k_cent, b.meta, b.stat, K, k);
       cluster.sync();
       STAMP();
       FOR_ITEMS(c, C) pca_item(b.meta, b.stat, C, c);
@@ -2079,26 +2125,26 @@ static int frontier_cluster_large(FuelMap* m, const FParams& fp, int n_cand, int
   ctl.cnext = f->d_counters + 7;
   // a root cluster has more than cluster_min cells; every level at most doubles the cluster count
   const int64_t r_ub = n_cand / ((fp.cluster_min > 0 ? fp.cluster_min : 0) + 1) + 1;
-  init_meta_kernel<<<nblk(r_ub, 256), 256, 0, s>>>(f->meta.p, ctl);
+  init_meta_kernel<<<nblk(r_ub, 256), 256, 0, s>>>(f->meta.p, f->stat.p, ctl);
   FUEL_LAUNCHES(m, 1);
   int cnt[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
   constexpr int LEVELS_PER_BATCH = 12, MAX_LEVELS = 36;  // (a cluster stops splitting at depth 32: pca_item)
+  auto c_bound = [&](int level) -> int64_t {
+    const int64_t c = level < 24 ? (r_ub << level) : (int64_t)n_cand;
+    return c > n_cand ? (int64_t)n_cand : c;
+  };
   for (int level = 0; level < MAX_LEVELS; ++level) {
-    int64_t c_ub = level < 24 ? (r_ub << level) : (int64_t)n_cand;
-    if (c_ub > n_cand) c_ub = n_cand;
-    const unsigned ccb = nblk(c_ub, 256);
-    stat_reset_kernel<<<ccb, 256, 0, s>>>(f->stat.p, f->meta.p, ctl);
+    const unsigned ccb = nblk(c_bound(level), 256);
     stat_accum_kernel<<<cb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, ctl);
-    mean_kernel<<<ccb, 256, 0, s>>>(g, f->meta.p, f->stat.p, ctl);
     downsample_kernel<<<cb, 256, 0, s>>>(g, fp, f->k_addr.p, f->k_cl.p, f->cellidx, f->meta.p, f->stat.p,
                                          f->k_cent.p, f->k_leaf.p, ctl);
-    cov_kernel<<<cb, 256, 0, s>>>(f->k_cl.p, f->k_leaf.p, f->k_cent.p, f->meta.p, f->stat.p, ctl);
-    pca_kernel<<<ccb, 256, 0, s>>>(f->meta.p, f->stat.p, ctl);
+    cov_kernel<<<cb, 256, 0, s>>>(g, f->k_cl.p, f->k_leaf.p, f->k_cent.p, f->meta.p, f->stat.p, ctl);
+    pca_kernel<<<ccb, 256, 0, s>>>(g, f->meta.p, f->stat.p, ctl);
     side_count_kernel<<<cb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, f->stat.p, ctl);
     split_alloc_kernel<<<1, 1024, 0, s>>>(f->meta.p, f->stat.p, ctl);
     relabel_kernel<<<cb, 256, 0, s>>>(g, f->k_addr.p, f->k_cl.p, f->meta.p, ctl);
-    clear_do_split_kernel<<<ccb, 256, 0, s>>>(f->meta.p, ctl);
-    FUEL_LAUNCHES(m, 10);
+    next_level_kernel<<<nblk(c_bound(level + 1), 256), 256, 0, s>>>(f->meta.p, f->stat.p, ctl);
+    FUEL_LAUNCHES(m, 8);
     int* t = ctl.ccur;
     ctl.ccur = ctl.cnext;
     ctl.cnext = t;
