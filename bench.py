@@ -585,7 +585,8 @@ def sharded_esdf_arm(local, rank, world, reps=5):
     dev = "cuda:%d" % local
     out = {}
     # ---- parity: sharded == single GPU, voxel for voxel (finite values to 1e-6 relative, same +inf set) ----
-    npar = (32 * world * 2, 96, 32 * world)
+    # (x lines of 1024 samples: the x tiles are the 2-CTA cluster form reading their rows as `world` pieces)
+    npar = (1024, 96, 32 * world)
     g, inflate = W.random_boxes_map(n=npar, seed=11, n_boxes=48, ground_idx=3)
     sh = ShardedESDF(npar, g.res, optimistic=True, device=local)
     z0, z1 = sh.z_range()
@@ -868,7 +869,7 @@ def run_ours(args):
         "esdf": "dominant stage of the office replan: a 0.96 M-voxel map is L2-resident and launch-latency-bound; the "
                 "HBM-bound ESDF case is roofline_esdf512"}
     roofline = {"kernel": {"esdf": "esdf_update (zpack + envelope tiles)", "frontier": "frontier_search (sweep + clustering)",
-                           "bspline": "optimize_warp_kernel (K evaluations of the batch in one launch)"}[dom],
+                           "bspline": "optimize_gram_kernel<6> (persistent L-BFGS solver: K evaluations of the batch in one launch)"}[dom],
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": profile_traffic("office_" + dom), "algorithmic_bytes": alg[dom],
                 "peak_source": peak_src, "note": notes[dom]}

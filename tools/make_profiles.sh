@@ -15,6 +15,11 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
 ncu --set full --import-source on --cache-control none --clock-control none -k regex:"zpack|envelope" -s 33 -c 3 \
     -o gpurun_out/r02_esdf512_full python tools/esdf512.py V1 2 > /dev/null 2>&1
 # 512^3 frontier search: every kernel
+# (one search = 6 launches of the sweep + small-path attempt, 1 recompaction, 20 of union-find/claims/scans, then
+#  8 per split level enqueued in batches of 12 levels: the window covers the second search of the run)
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --cache-control none --clock-control none \
-    -s 60 -c 200 --csv --log-file gpurun_out/r02_frontier512_launches.csv python tools/frontier512.py > /dev/null 2>&1
+    -s 226 -c 222 --csv --log-file gpurun_out/r02_frontier512_launches.csv python tools/frontier512.py > /dev/null 2>&1
+# the long-line case (BASELINE config 4 geometry, one GPU): 2-CTA cluster tiles
+python tools/esdf_long.py 1024 1024 256 4 > gpurun_out/r02_esdf_long.log 2>&1
+FUELGPU_ESDF_CLUSTER=0 python tools/esdf_long.py 1024 1024 256 4 >> gpurun_out/r02_esdf_long.log 2>&1
 ls -la gpurun_out

@@ -90,8 +90,15 @@ if os.path.exists(src):
 src = os.path.join(G, tag + "_frontier512_launches.csv")
 if os.path.exists(src):
     cols = ("dram__bytes_read.sum", "dram__bytes_write.sum")
-    launch_summary(src, os.path.join(P, tag + "_frontier512_launches.txt"),
-                   "tools/frontier512.py (512^3 frontier search, large multi-kernel path), launches 60..259", cols)
+    agg, tot = launch_summary(src, os.path.join(P, tag + "_frontier512_launches.txt"),
+                              "tools/frontier512.py (512^3 frontier search, large multi-kernel path), launches 226..447 = "
+                              "one search; kernels of a split level that has nothing left to do return at once", cols)
+    rd = sum(a.get("dram__bytes_read.sum", 0) for a in agg.values())
+    wr = sum(a.get("dram__bytes_write.sum", 0) for a in agg.values())
+    with open(os.path.join(P, tag + "_frontier512_launches.txt"), "a") as f:
+        f.write("DRAM read %.1f MB + write %.1f MB over the window; algorithmic 268.4 MB (2 B/voxel)\n" % (rd / 1e6, wr / 1e6))
+    traffic["frontier512"] = {"bytes": rd + wr, "read": rd, "write": wr,
+                              "source": "profiles/%s_frontier512_launches.txt (sum over the launches of one search)" % tag}
 rep = os.path.join(G, tag + "_esdf512_full.ncu-rep")
 if os.path.exists(rep):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, "pipe_alu", "pipe_fma",
@@ -107,14 +114,15 @@ if os.path.exists(so):
     for l in sass:
         if "Function :" in l:
             fn = l.strip()
-        if any(t in l for t in ("UBLKCP", "SYNCS", "CCTL.E.RML2", "UTMA")):
+        if any(t in l for t in ("UBLKCP", "SYNCS", "CCTL.E.RML2", "UTMA", "UCGABAR")):
             if fn:
                 keep.append(fn)
                 fn = None
             keep.append(l.rstrip())
     open(os.path.join(P, tag + "_esdf_tile_sass_tma.txt"), "w").write(
-        "cuobjdump -sass fuel_b200/build/esdf_tile.o | grep UBLKCP|SYNCS|CCTL.E.RML2 -- the bulk-async copies "
-        "(cp.async.bulk -> UBLKCP.S.G), their mbarrier traffic (SYNCS.*) and the L2 discards of the consumed partial "
-        "(discard.global.L2 -> CCTL.E.RML2) in the tile kernels\n" + "\n".join(keep) + "\n")
+        "cuobjdump -sass fuel_b200/build/esdf_tile.o | grep UBLKCP|SYNCS|CCTL.E.RML2|UCGABAR -- the bulk-async copies "
+        "(cp.async.bulk -> UBLKCP.S.G), their mbarrier traffic (SYNCS.*), the L2 discards of the consumed partial "
+        "(discard.global.L2 -> CCTL.E.RML2) and the cluster barriers of the 2-CTA long-line tiles (barrier.cluster -> "
+        "UCGABAR_ARV / UCGABAR_WAIT; their DSMEM accesses are the LD.E / ST.E.U16 through mapa addresses) in the tile kernels\n" + "\n".join(keep) + "\n")
 json.dump(traffic, open(tp, "w"), indent=1)
 print("profiles/ updated:", sorted(os.listdir(P)))
