@@ -102,9 +102,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_workload(batch, seed_offset=0):
+def build_workload(batch, seed_offset=0, workload="office"):
     from fuel_b200 import workloads as W
-    g, inflate = W.office_map()
+    g, inflate = W.office3_map() if workload == "office3" else W.office_map()
     tri = W.office_known(g, inflate)
     tr = W.make_trajectories(g, inflate, B=batch, n_pts=20, seed=20260922 + seed_offset)
     return g, inflate, tri, tr
@@ -339,7 +339,7 @@ def workload_config(args):
 # our arm
 # --------------------------------------------------------------------------------------------
 class GpuPlanner:
-    def __init__(self, dev, batch, evals, seed_offset=0, overlap=True):
+    def __init__(self, dev, batch, evals, seed_offset=0, overlap=True, workload="office"):
         import ctypes as C
 
         import torch
@@ -350,7 +350,7 @@ class GpuPlanner:
         self.C, self.torch, self.fuel = C, torch, fuel_b200
         self.dev = dev
         self.evals = evals
-        g, inflate, tri, tr = build_workload(batch, seed_offset)
+        g, inflate, tri, tr = build_workload(batch, seed_offset, workload)
         self.g = g
         self.B = batch
         m = fuel_b200.SDFMap(g.n, g.res, g.origin, g.box_min, g.box_max, optimistic=True, device=dev)
@@ -654,8 +654,12 @@ def sharded_esdf_arm(local, rank, world, reps=5):
         ms.append(float(t.item()))
         stages.append(sh.last_timing())
     sent = sh.bytes_exchanged()
+    p2p = sh.uses_peer_memory()
     sh.close()
-    out.update({"map": list(n), "n_gpus": world, "ms": float(np.median(ms)), "ms_all": [round(v, 3) for v in ms],
+    out.update({"map": list(n), "n_gpus": world,
+                "exchange": ("peer memory: the zy tile kernels store the int32 partial straight into the destination rank's "
+                             "buffer over NVLink (CUDA IPC), one 4 B/rank all-gather as the barrier") if p2p else
+                            "ncclSend/ncclRecv rounds on a second stream", "ms": float(np.median(ms)), "ms_all": [round(v, 3) for v in ms],
                 "stage_ms_rank0": {k: round(float(np.median([s_[k] for s_ in stages])), 3) for k in stages[0]},
                 "bytes_sent_per_rank": sent, "voxels": int(np.prod(n)),
                 "note": "device time of one whole-map update, max over ranks; stages: occupancy all-to-all (1 B/voxel), "
@@ -683,6 +687,51 @@ def sharded_esdf_arm(local, rank, world, reps=5):
         del occ1, buf1
     if world > 1:
         dist.barrier()
+    return out
+
+
+def config5_arm(local, rank, world, args, steps=10):
+    """BASELINE config 5: office3.pcd 200x300x40, one independent planner per GPU, 4096-trajectory batch each -- the same
+    resident replan (ESDF update + frontier search + K evaluations per trajectory in the device solver) as the metric,
+    on the bigger map and batch.  Collective-safe: every rank reaches the all_reduce whatever happened before it."""
+    import torch
+    import torch.distributed as dist
+    ms, info = float("nan"), {}
+    try:
+        P5 = GpuPlanner(local, 4096, args.evals, seed_offset=100 * rank, overlap=not args.no_overlap, workload="office3")
+        for _ in range(3):
+            P5.l2_flush()
+            P5.replan_resident()
+        torch.cuda.synchronize(local)
+        evs, stage = [], {"esdf": [], "frontier": [], "bspline": []}
+        for _ in range(steps):
+            P5.l2_flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(P5.stream)
+            P5.replan_resident()
+            e1.record(P5.stream)
+            evs.append((e0, e1))
+            t = P5.m.last_timing()
+            for k in stage:
+                stage[k].append(t[k])
+        torch.cuda.synchronize(local)
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        nev = P5.d_n.cpu().numpy()
+        info = {"stage_ms": {k: float(np.median(v)) for k, v in stage.items()}, "evals_done_min": int(nev.min()),
+                "n_frontier_clusters": P5.n_clusters, "voxels": int(P5.g.nvox)}
+        P5.m.close()
+    except Exception as e:  # noqa: BLE001
+        info = {"error": repr(e)}
+    t = torch.tensor([ms if ms == ms else 1e30], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mx = float(t.item())
+    out = {"workload": "office3.pcd 200x300x40 @0.1m, %d independent planner(s), 4096-trajectory x 20 ctrl-pt batch each, "
+                       "%d evaluations per trajectory, inputs resident" % (world, args.evals),
+           "steps": steps}
+    out.update(info)
+    if mx < 1e29:
+        out.update({"value": world * steps / (mx * 1e-3), "unit": UNIT, "ms_per_step": mx / steps})
     return out
 
 
@@ -752,6 +801,24 @@ def next_rows_timing(dev):
     return out
 
 
+def bind_near_gpu(local):
+    """Pin this process to the CPUs NVML lists as local to its GPU (same NUMA node / PCIe root): with one process per
+    GPU the host side of a replan (launches, pinned-buffer copies, result marshalling) otherwise runs wherever the
+    launcher left it.  FUELGPU_BENCH_BIND=0 disables it.  Returns the number of CPUs in the new set, or None."""
+    if os.environ.get("FUELGPU_BENCH_BIND", "1") == "0":
+        return None
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -761,6 +828,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libfuelgpu has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
+    cpus_bound = bind_near_gpu(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__
@@ -844,6 +912,8 @@ def run_ours(args):
             sharded = sharded_esdf_arm(local, rank, world)
         except Exception as e:  # noqa: BLE001
             sharded = {"error": repr(e)}
+
+    config5 = None if args.no_config5 else config5_arm(local, rank, world, args)
 
     if rank != 0:
         if world > 1:
@@ -932,9 +1002,13 @@ def run_ours(args):
         "n_frontier_clusters": P.n_clusters,
         "evals_done_min": evals_min, "evals_done_mean": evals_mean,
     }
+    if cpus_bound is not None:
+        line["host_cpus_bound_near_gpu"] = cpus_bound
     line.update(extra)
     if sharded is not None:
         line["sharded_esdf"] = sharded
+    if config5 is not None:
+        line["config5_office3_b4096"] = config5
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -950,6 +1024,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--no-esdf512", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the config-4 z-sharded ESDF arm at N > 1")
+    ap.add_argument("--no-config5", action="store_true", help="skip the office3 / 4096-trajectory replan (BASELINE config 5)")
     ap.add_argument("--no-overlap", action="store_true", help="run the frontier search after the ESDF update instead of beside it")
     args = ap.parse_args()
     if args.impl == "reference":

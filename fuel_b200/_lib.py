@@ -141,6 +141,7 @@ SIGNATURES = {
     "fuelgpu_sharded_esdf_update": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "fuelgpu_sharded_esdf_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "fuelgpu_sharded_esdf_bytes_exchanged": (_i64, [_vp]),
+    "fuelgpu_sharded_esdf_uses_peer_memory": (C.c_int, [_vp]),
     "fuelgpu_sharded_esdf_allgather": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fuelgpu_sharded_esdf_destroy": (C.c_int, [_vp]),
     "fuelgpu_esdf_set_from_slabs_dev": (C.c_int, [_vp, _vp, _i32]),

@@ -7,9 +7,14 @@
 //      x range (G chunks of nz/G planes each);
 //   2. zpack + zy tiles on the x-slab (esdf_tile.cu), written straight into the send layout of step 3; the tiles
 //      are produced destination by destination;
-//   3. THE exchange of the 2-D partial (int32): x-slabs -> z-slabs, one grouped ncclSend/ncclRecv pair per round,
-//      round k (peer r+k / r-k) is enqueued on a second stream as soon as the tiles of destination r+k are done,
-//      so the transfer of round k overlaps the tiles of round k+1;
+//   3. THE exchange of the 2-D partial (int32): x-slabs -> z-slabs.  Peer-memory form (default where the ranks can
+//      map each other's memory: one process per GPU, NVLink/NVSwitch): there is no exchange step at all -- the zy
+//      tile kernel of destination d stores its rows STRAIGHT INTO rank d's receive buffer over NVLink (the buffers
+//      are CUDA-IPC mapped once at creation, the handles travel through an ncclAllGather), so the transfer IS the
+//      kernel's output traffic, tile by tile; one 4-byte-per-rank all-gather afterwards is the barrier that tells
+//      every rank that all its sources have finished writing.  NCCL form (fallback, FUELGPU_SHARDED_P2P=0): one
+//      grouped ncclSend/ncclRecv pair per round, round k (peer r+k / r-k) enqueued on a second stream as soon as
+//      the tiles of destination r+k are done, so the transfer of round k overlaps the tiles of round k+1;
 //   4. x tiles on the own z-slab: rows of a tile are G contiguous pieces (one per source rank), result in metres
 //      in the caller's z-slab of distance_buffer_.
 // NCCL is bound at run time (dlopen of libnccl.so.2, the copy already loaded by the host process if any), so
@@ -18,6 +23,9 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
+
+#include <vector>
 
 namespace {
 
@@ -80,6 +88,10 @@ struct FuelShardedEsdf {
   int32_t* psend;  // [G dest][wl][ny][nxl][32]
   int32_t* precv;  // [G src][wl][ny][nxl][32]
   size_t blk;      // int32 per (rank, rank) block of the partial
+  // peer-memory exchange: precv of every rank mapped here (peer_recv[r] == precv), and the barrier's scratch
+  bool p2p;
+  int32_t* peer_recv[64];
+  int32_t* sync_buf;  // [1 + G]
   cudaStream_t comm_stream;
   cudaEvent_t ev_round[64];
   cudaEvent_t ev_comm_done;
@@ -138,11 +150,18 @@ int fuelgpu_comm_info(const FuelComm* c, int32_t* nranks, int32_t* rank) {
 int fuelgpu_sharded_esdf_destroy(FuelShardedEsdf* s) {
   if (!s) return 0;
   cudaSetDevice(s->c->dev);
-  if (s->comm_stream) {
-    cudaStreamSynchronize(s->comm_stream);
-    cudaStreamDestroy(s->comm_stream);
+  if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+  if (s->p2p) {
+    // (collective in this mode, like the creation: nobody frees its receive buffer while a peer still maps it)
+    cudaDeviceSynchronize();
+    for (int g = 0; g < s->c->nranks; ++g)
+      if (g != s->c->rank && s->peer_recv[g]) cudaIpcCloseMemHandle(s->peer_recv[g]);
+    if (g_nccl.ok && s->c->comm && s->comm_stream &&
+        g_nccl.AllGather(s->sync_buf, s->sync_buf + 1, 1, ncclInt32, s->c->comm, s->comm_stream) == ncclSuccess)
+      cudaStreamSynchronize(s->comm_stream);
   }
-  void* ptrs[] = { s->occ_x, s->rec, s->psend, s->precv };
+  if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+  void* ptrs[] = { s->occ_x, s->rec, s->psend, s->precv, s->sync_buf };
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 64; ++i)
@@ -196,10 +215,66 @@ int fuelgpu_sharded_esdf_create(FuelComm* c, const int32_t n[3], double resoluti
   for (int i = 0; i < G; ++i) CR(cudaEventCreateWithFlags(&s->ev_round[i], cudaEventDisableTiming));
   CR(cudaEventCreateWithFlags(&s->ev_comm_done, cudaEventDisableTiming));
   for (int i = 0; i < 5; ++i) CR(cudaEventCreate(&s->ev_t[i]));
+  CR(cudaMalloc(&s->sync_buf, sizeof(int32_t) * (1 + G) + 64 * (size_t)(1 + G)));
+  CR(cudaMemset(s->sync_buf, 0, sizeof(int32_t) * (1 + G)));
 #undef CR
+  // peer-memory exchange: every rank publishes the IPC handle of its receive buffer (all-gather over the
+  // communicator), maps the others' and agrees (all ranks or none) that it worked
+  s->p2p = false;
+  const char* env = getenv("FUELGPU_SHARDED_P2P");
+  const bool want = G > 1 && !(env && atoi(env) == 0);
+  if (G > 1) {
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    int ok = want && cudaIpcGetMemHandle(&mine, s->precv) == cudaSuccess ? 1 : 0;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    char* hbuf = (char*)(s->sync_buf + 1 + G);  // [1 + G] x 64 bytes
+    std::vector<cudaIpcMemHandle_t> all(G);
+    cudaError_t e = cudaMemcpy(hbuf, &mine, 64, cudaMemcpyHostToDevice);
+    ncclResult_t nr = ncclSuccess;
+    if (e == cudaSuccess) nr = g_nccl.AllGather(hbuf, hbuf + 64, 64, ncclUint8, c->comm, s->comm_stream);
+    if (e == cudaSuccess && nr == ncclSuccess) e = cudaStreamSynchronize(s->comm_stream);
+    if (e == cudaSuccess && nr == ncclSuccess) e = cudaMemcpy(all.data(), hbuf + 64, 64 * (size_t)G, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess || nr != ncclSuccess) ok = 0;
+    if (ok) {
+      for (int g = 0; g < G && ok; ++g) {
+        if (g == c->rank) {
+          s->peer_recv[g] = s->precv;
+          continue;
+        }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = 0;
+        } else {
+          s->peer_recv[g] = (int32_t*)ptr;
+        }
+      }
+    }
+    // all or none: the minimum of the ranks' flags (gathered like the handles)
+    int32_t flag = ok, flags[64];
+    e = cudaMemcpy(s->sync_buf, &flag, 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) nr = g_nccl.AllGather(s->sync_buf, s->sync_buf + 1, 1, ncclInt32, c->comm, s->comm_stream);
+    if (e == cudaSuccess && nr == ncclSuccess) e = cudaStreamSynchronize(s->comm_stream);
+    if (e == cudaSuccess && nr == ncclSuccess) e = cudaMemcpy(flags, s->sync_buf + 1, 4 * (size_t)G, cudaMemcpyDeviceToHost);
+    bool all_ok = e == cudaSuccess && nr == ncclSuccess;
+    for (int g = 0; g < G && all_ok; ++g) all_ok = flags[g] == 1;
+    if (all_ok) {
+      s->p2p = true;
+    } else {
+      for (int g = 0; g < G; ++g) {
+        if (g != c->rank && s->peer_recv[g]) cudaIpcCloseMemHandle(s->peer_recv[g]);
+        s->peer_recv[g] = nullptr;
+      }
+      cudaGetLastError();
+    }
+  }
   *out = s;
   return 0;
 }
+
+// 1 when the partial travels by direct stores into the peers' receive buffers, 0 when it goes through ncclSend/Recv
+int fuelgpu_sharded_esdf_uses_peer_memory(const FuelShardedEsdf* s) { return s && s->p2p ? 1 : 0; }
 
 int fuelgpu_sharded_esdf_update(FuelShardedEsdf* s, void* cuda_stream, const void* occ_slab_dev, int flags,
                                 void* dist_slab_dev) {
@@ -232,11 +307,13 @@ int fuelgpu_sharded_esdf_update(FuelShardedEsdf* s, void* cuda_stream, const voi
   for (int kk = 0; kk < G; ++kk) {
     const int k = (kk + 1) % G;  // 1, 2, ..., G-1, 0
     const int d = (r + k) % G, src = (r - k + G) % G;
-    int32_t* dstP = d == r ? s->precv + (size_t)r * s->blk : s->psend + (size_t)d * s->blk;
+    // peer-memory form: rank d's receive slot of source r, written over NVLink by the tile kernel itself
+    int32_t* dstP = d == r ? s->precv + (size_t)r * s->blk
+                           : (s->p2p ? s->peer_recv[d] + (size_t)r * s->blk : s->psend + (size_t)d * s->blk);
     rc = edt_stage_zy(st, s->rec, s->nxl, s->ny, s->NW, d * s->wl, s->wl, dstP, 32, (int64_t)s->ny * s->nxl * 32,
                       (int64_t)s->nxl * 32);
     if (rc) return fuel_fail(nullptr, rc, "zy stage failed");
-    if (d == r) continue;
+    if (d == r || s->p2p) continue;
     FUEL_CUDA(nullptr, cudaEventRecord(s->ev_round[k], st));
     FUEL_CUDA(nullptr, cudaStreamWaitEvent(s->comm_stream, s->ev_round[k], 0));
     FUEL_NCCL(g_nccl.GroupStart());
@@ -245,8 +322,15 @@ int fuelgpu_sharded_esdf_update(FuelShardedEsdf* s, void* cuda_stream, const voi
     FUEL_NCCL(g_nccl.GroupEnd());
   }
   FUEL_CUDA(nullptr, cudaEventRecord(s->ev_t[2], st));
-  FUEL_CUDA(nullptr, cudaEventRecord(s->ev_comm_done, s->comm_stream));
-  FUEL_CUDA(nullptr, cudaStreamWaitEvent(st, s->ev_comm_done, 0));
+  if (s->p2p) {
+    // every source has finished storing into my receive buffer once this tiny all-gather completes (a kernel's
+    // stores are performed at system scope when it ends; the collective orders the ranks' streams).  The slots of
+    // the NEXT update are not written before step 1 of that update has met every peer, i.e. after its x tiles.
+    FUEL_NCCL(g_nccl.AllGather(s->sync_buf, s->sync_buf + 1, 1, ncclInt32, c->comm, st));
+  } else {
+    FUEL_CUDA(nullptr, cudaEventRecord(s->ev_comm_done, s->comm_stream));
+    FUEL_CUDA(nullptr, cudaStreamWaitEvent(st, s->ev_comm_done, 0));
+  }
   FUEL_CUDA(nullptr, cudaEventRecord(s->ev_t[3], st));
   // 4. x tiles on my z-slab
   rc = edt_stage_x(st, s->precv, (int64_t)s->nxl * 32, (int64_t)s->ny * s->nxl * 32, (int64_t)s->blk, s->nxl, s->nx, s->ny,

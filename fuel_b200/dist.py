@@ -147,6 +147,11 @@ class ShardedESDF:
     def bytes_exchanged(self):
         return int(_lib.lib().fuelgpu_sharded_esdf_bytes_exchanged(self.handle))
 
+    def uses_peer_memory(self):
+        """True when the zy tile kernels store the partial straight into the peers' receive buffers (CUDA IPC over
+        NVLink) instead of handing it to ncclSend/ncclRecv."""
+        return bool(_lib.lib().fuelgpu_sharded_esdf_uses_peer_memory(self.handle))
+
     # ---- host-orchestrated twin (CPU tests): same decomposition, torch.distributed collectives ----
     def _update_host(self, occ_slab):
         zy_fn, x_fn = self.stage_fns

@@ -408,6 +408,10 @@ FUELGPU_API int fuelgpu_sharded_esdf_update(FuelShardedEsdf* s, void* cuda_strea
  * exchange rounds of the 2-D partial overlap them), [2] wait for the last rounds, [3] x tiles, [4] total */
 FUELGPU_API int fuelgpu_sharded_esdf_last_timing(FuelShardedEsdf* s, float ms[5]);
 FUELGPU_API int64_t fuelgpu_sharded_esdf_bytes_exchanged(const FuelShardedEsdf* s);
+/* 1 when the 2-D partial travels by direct stores of the zy tile kernels into the peers' receive buffers (CUDA-IPC
+ * mapped at creation; one process per GPU, peer access available), 0 when it goes through ncclSend/ncclRecv rounds
+ * (FUELGPU_SHARDED_P2P=0 or no peer mapping).  In the peer-memory mode fuelgpu_sharded_esdf_destroy is collective. */
+FUELGPU_API int fuelgpu_sharded_esdf_uses_peer_memory(const FuelShardedEsdf* s);
 /* every rank gets all z-slabs: out_dev [G][nx][ny][nz/G] float32 (what a trajectory batch split over the ranks
  * samples) */
 FUELGPU_API int fuelgpu_sharded_esdf_allgather(FuelShardedEsdf* s, void* cuda_stream, const void* dist_slab_dev,

@@ -48,9 +48,9 @@ for _ in range(5):
     ms.append(float(t.item()))
 tm = sh.last_timing()
 if rank == 0:
-    print("sharded ESDF %s on %d GPUs: ms (max over ranks) %s  best %.3f  stages(rank0) %s  sent/rank %.1f MB"
-          % (n, world, ["%.3f" % v for v in ms], min(ms), {k: round(v, 3) for k, v in tm.items()},
-             sh.bytes_exchanged() / 1e6))
+    print("sharded ESDF %s on %d GPUs (%s): ms (max over ranks) %s  best %.3f  stages(rank0) %s  sent/rank %.1f MB"
+          % (n, world, "peer-memory stores" if sh.uses_peer_memory() else "ncclSend/Recv",
+             ["%.3f" % v for v in ms], min(ms), {k: round(v, 3) for k, v in tm.items()}, sh.bytes_exchanged() / 1e6))
 if check:
     full = sh.gather_full(part)
     torch.cuda.synchronize()
