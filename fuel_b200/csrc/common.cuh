@@ -109,6 +109,8 @@ int edt_stage_zpack(cudaStream_t st, const uint8_t* occ, void* rec, int nxl, int
                     int mode);
 int edt_stage_zy(cudaStream_t st, const void* rec, int nxl, int ny, int NW, int w0, int wn, int32_t* P, int64_t out_o,
                  int64_t out_bx, int64_t out_q);
+int edt_stage_zy_scatter(cudaStream_t st, const void* rec, int nxl, int ny, int NW, int32_t* const* tab, int ntab, int wl,
+                         int64_t out_o, int64_t out_bx, int64_t out_q);
 int edt_stage_x(cudaStream_t st, const int32_t* P, int64_t in_o, int64_t in_bx, int64_t piece_stride, int piece_rows, int nx,
                 int ny, int wn, float* out, int64_t out_o, int64_t out_bx, int64_t out_q, int lanes_total, float res,
                 int discard);

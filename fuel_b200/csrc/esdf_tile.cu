@@ -226,6 +226,10 @@ struct TileParams {
   // output: sample q of lane l at out + out_base + o*out_o + bx*out_bx + q*out_q + l  (int32 or float)
   void* out;
   int64_t out_base, out_o, out_bx, out_q;
+  // optional: the tiles of words [k*out_tab_wl, (k+1)*out_tab_wl) go to out_tab[k] instead of `out` (bx counted from the
+  // start of that group): one launch whose output is scattered over several buffers (the peers of a sharded update)
+  void* out_tab[16];
+  int out_tab_wl;  // 0 = unused
   int lanes_total;  // valid z positions counted from bx = 0 (lanes beyond are not stored when FINAL)
   int discard_input;  // !FROMBITS: drop the tile's lines from L2 once they are in shared memory
   float res;
@@ -649,9 +653,16 @@ __global__ void __launch_bounds__(MAXT, MINB) envelope_tile_kernel(const TilePar
   // ---- phase 3: every thread evaluates its own 32 samples on the joint hull -----------------
   if (j0 < n && !(FINAL && bx * 32 + lane >= p.lanes_total)) {  // (padding lane of the last z word: nothing to store)
     const int qend = min(n, j0 + M);
-    const int64_t obase = p.out_base + (int64_t)o * p.out_o + (int64_t)bx * p.out_bx + lane + (int64_t)j0 * p.out_q;
+    char* outp = reinterpret_cast<char*>(p.out);
+    int bxo = bx;
+    if (!FINAL && p.out_tab_wl > 0) {
+      const int k = bx / p.out_tab_wl;
+      outp = reinterpret_cast<char*>(p.out_tab[k]);
+      bxo = bx - k * p.out_tab_wl;
+    }
+    const int64_t obase = p.out_base + (int64_t)o * p.out_o + (int64_t)bxo * p.out_bx + lane + (int64_t)j0 * p.out_q;
     // sample j0+u goes to op + u*ostride bytes (the stride fits 32 bits: one IMAD.WIDE per store)
-    char* const op = reinterpret_cast<char*>(p.out) + obase * 4;
+    char* const op = outp + obase * 4;
     const unsigned ostride = (unsigned)p.out_q * 4u;
     if (CL) {
       const HullCluster hull = { smem_u32(LOl), smem_u32(HIl), smem_u32(Tl), nb, rpc };
@@ -876,6 +887,28 @@ int edt_stage_zy(cudaStream_t st, const void* rec, int nxl, int ny, int NW, int 
   p1.out_q = out_q;
   p1.lanes_total = 1 << 30;
   return launch_tile<true, false>(st, p1, wn, nxl) == cudaSuccess ? 0 : FUELGPU_ECUDA;
+}
+
+// the same for ALL words of the line at once, scattered over ntab output buffers: words [k*wl, (k+1)*wl) go to tab[k]
+// with the word index counted from k*wl (ntab <= 16)
+int edt_stage_zy_scatter(cudaStream_t st, const void* rec, int nxl, int ny, int NW, int32_t* const* tab, int ntab, int wl,
+                         int64_t out_o, int64_t out_bx, int64_t out_q) {
+  if (ntab < 1 || ntab > 16 || ntab * wl != NW) return FUELGPU_EINVAL;
+  TileParams p1;
+  memset(&p1, 0, sizeof(p1));
+  p1.n = ny;
+  p1.rec = (const uint2*)rec;
+  p1.NW = NW;
+  p1.NYP = (ny + 1) & ~1;
+  p1.w0 = 0;
+  p1.out = tab[0];
+  for (int k = 0; k < ntab; ++k) p1.out_tab[k] = tab[k];
+  p1.out_tab_wl = wl;
+  p1.out_o = out_o;
+  p1.out_bx = out_bx;
+  p1.out_q = out_q;
+  p1.lanes_total = 1 << 30;
+  return launch_tile<true, false>(st, p1, NW, nxl) == cudaSuccess ? 0 : FUELGPU_ECUDA;
 }
 
 // x tiles: grid (wn, ny); tile rows per TileParams (pieces); result in metres to out[y*out_o + w*out_bx + x*out_q + lane]

@@ -302,9 +302,18 @@ int fuelgpu_sharded_esdf_update(FuelShardedEsdf* s, void* cuda_stream, const voi
   // 2. records of my x range (z lines assembled from the G chunks)
   int rc = edt_stage_zpack(st, s->occ_x, s->rec, s->nxl, s->ny, s->nzl, G, (int64_t)chunk, mode);
   if (rc) return fuel_fail(nullptr, rc, "zpack stage failed");
+  // 2+3 (peer-memory form). ONE launch over all words: the tiles of destination d's words store into rank d's
+  // receive slot of source r (my own words into my own buffer)
+  if (s->p2p && G <= 16) {
+    int32_t* tab[16];
+    for (int d = 0; d < G; ++d) tab[d] = (d == r ? s->precv : s->peer_recv[d]) + (size_t)r * s->blk;
+    rc = edt_stage_zy_scatter(st, s->rec, s->nxl, s->ny, s->NW, tab, G, s->wl, 32, (int64_t)s->ny * s->nxl * 32,
+                              (int64_t)s->nxl * 32);
+    if (rc) return fuel_fail(nullptr, rc, "zy stage failed");
+  }
   // 2+3. zy tiles destination by destination, the peers first and this rank's own block last (it needs no
   // transfer and is written straight into the receive buffer); round k's transfer overlaps round k+1's tiles
-  for (int kk = 0; kk < G; ++kk) {
+  for (int kk = 0; kk < G && !(s->p2p && G <= 16); ++kk) {
     const int k = (kk + 1) % G;  // 1, 2, ..., G-1, 0
     const int d = (r + k) % G, src = (r - k + G) % G;
     // peer-memory form: rank d's receive slot of source r, written over NVLink by the tile kernel itself
