@@ -91,8 +91,8 @@ src = os.path.join(G, tag + "_frontier512_launches.csv")
 if os.path.exists(src):
     cols = ("dram__bytes_read.sum", "dram__bytes_write.sum")
     agg, tot = launch_summary(src, os.path.join(P, tag + "_frontier512_launches.txt"),
-                              "tools/frontier512.py (512^3 frontier search, large multi-kernel path), launches 226..447 = "
-                              "one search; kernels of a split level that has nothing left to do return at once", cols)
+                              "tools/frontier512.py (512^3 frontier search, large multi-kernel path), launches 239..357 = "
+                              "the third search of the run; kernels of a split level that has nothing left to do return at once", cols)
     rd = sum(a.get("dram__bytes_read.sum", 0) for a in agg.values())
     wr = sum(a.get("dram__bytes_write.sum", 0) for a in agg.values())
     with open(os.path.join(P, tag + "_frontier512_launches.txt"), "a") as f:
