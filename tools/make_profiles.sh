@@ -16,9 +16,9 @@ ncu --set full --import-source on --cache-control none --clock-control none -k r
     -o gpurun_out/r02_esdf512_full python tools/esdf512.py V1 2 > /dev/null 2>&1
 # 512^3 frontier search: every kernel
 # (one search = 6 launches of the sweep + small-path attempt, 1 recompaction, 20 of union-find/claims/scans, then
-#  8 per split level enqueued in batches of 12 levels: the window covers the second search of the run)
+#  8 per split level enqueued in batches of 12 levels = 119 launches after 1 of the upload: the window is the third search)
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --cache-control none --clock-control none \
-    -s 226 -c 222 --csv --log-file gpurun_out/r02_frontier512_launches.csv python tools/frontier512.py > /dev/null 2>&1
+    -s 239 -c 119 --csv --log-file gpurun_out/r02_frontier512_launches.csv python tools/frontier512.py > /dev/null 2>&1
 # the long-line case (BASELINE config 4 geometry, one GPU): 2-CTA cluster tiles
 python tools/esdf_long.py 1024 1024 256 4 > gpurun_out/r02_esdf_long.log 2>&1
 FUELGPU_ESDF_CLUSTER=0 python tools/esdf_long.py 1024 1024 256 4 >> gpurun_out/r02_esdf_long.log 2>&1
